@@ -1,0 +1,180 @@
+"""Inference engine: wires parser, acoustic model and decoder together.
+
+Mirrors danspeech/DanSpeechRecognizer.py (class DanSpeechRecognizer :12-231): same constructor,
+attributes, ``update_model`` / ``update_decoder`` / ``enable_streaming`` / ``streaming_transcribe`` /
+``transcribe`` semantics.  Every stage runs on the GPU; ``with_gpu=False`` raises because this
+framework has no CPU path.  ``transcribe_batch`` is an addition (the reference engine is batch-1).
+"""
+import warnings
+
+import torch
+
+from . import _native as N
+from .audio.parsers import InferenceSpectrogramAudioParser, SpectrogramAudioParser
+from .deepspeech.decoder import BeamCTCDecoder, GreedyDecoder
+from .errors.recognizer_errors import ModelNotInitialized
+
+
+class NoLmInstantiatedWarning(Warning):
+    pass
+
+
+class DanSpeechRecognizer(object):
+
+    def __init__(self, model_name=None, lm_name=None, alpha=1.3, beta=0.2, with_gpu=True, beam_width=64,
+                 device=None):
+        if not with_gpu:
+            raise N.NativeError("danspeech_b200 runs on a B200 GPU only (with_gpu=False has no implementation)")
+        N.require_cuda()
+        self.device = torch.device(device or "cuda")
+        print("Using device: {0}".format(self.device))
+
+        self.model = None
+        self.model_name = None
+        self.labels = None
+        self.audio_config = None
+        self.audio_parser = None
+        self.lm = None
+        self.decoder = None
+        self.alpha = alpha
+        self.beta = beta
+        self.beam_width = beam_width
+        self.secondary_model = None
+        if model_name:
+            self.update_model(model_name)
+        if lm_name:
+            if not self.model:
+                raise ModelNotInitialized("Trying to initialize LM without also choosing a DanSpeech model.")
+            self.update_decoder(lm_name)
+
+    def update_model(self, model):
+        self.audio_config = model.audio_conf
+        self.model = model.to(self.device)
+        self.model.eval()
+        self.audio_parser = SpectrogramAudioParser(self.audio_config, device=self.device)
+        self.labels = self.model.labels
+        # as DanSpeechRecognizer.py:54-56 (quirk Q4: labels are assigned first, so an existing decoder is
+        # only rebuilt when lm/alpha/beta/beam_width change)
+        self.update_decoder(labels=self.labels)
+
+    def update_decoder(self, lm=None, alpha=None, beta=None, labels=None, beam_width=None):
+        """Same update rules as DanSpeechRecognizer.py:58-95."""
+        update = False
+        if not self.lm and not self.decoder:
+            update = True
+            self.lm = "greedy"
+        if lm and self.lm != lm:
+            update = True
+            self.lm = lm
+        if alpha and self.alpha != alpha:
+            update = True
+            self.alpha = alpha
+        if beta and self.beta != beta:
+            update = True
+            self.beta = beta
+        if labels and labels != self.labels:
+            update = True
+            self.labels = labels
+        if beam_width and beam_width != self.beam_width:
+            update = True
+            self.beam_width = beam_width
+        if update:
+            if self.lm != "greedy":
+                self.decoder = BeamCTCDecoder(labels=self.labels, lm_path=self.lm, alpha=self.alpha, beta=self.beta,
+                                              beam_width=self.beam_width, num_processes=6, cutoff_prob=1.0,
+                                              cutoff_top_n=40, blank_index=self.labels.index("_"))
+            else:
+                self.decoder = GreedyDecoder(labels=self.labels, blank_index=self.labels.index("_"))
+
+    # ------------------------------------------------------------------ streaming (DanSpeechRecognizer.py:98-216)
+    def enable_streaming(self, secondary_model=None, return_string_parts=True):
+        self.full_output = []
+        self.iterating_transcript = ""
+        if secondary_model:
+            self.secondary_model = secondary_model.to(self.device)
+            self.secondary_model.eval()
+        else:
+            self.secondary_model = None
+        self.spectrograms = []
+        self.greedy_decoder = GreedyDecoder(labels=self.labels, blank_index=self.labels.index("_"))
+        self.audio_parser = InferenceSpectrogramAudioParser(audio_config=self.audio_config, device=self.device)
+        self.string_parts = bool(return_string_parts)
+
+    def disable_streaming(self, keep_secondary_model=False):
+        self.audio_parser = SpectrogramAudioParser(self.audio_config, device=self.device)
+        self.greedy_decoder = None
+        self.reset_streaming_params()
+        self.string_parts = False
+        if not keep_secondary_model:
+            self.secondary_model = None
+
+    def reset_streaming_params(self):
+        self.iterating_transcript = ""
+        self.full_output = []
+        self.spectrograms = []
+
+    def streaming_transcribe(self, recording, is_last, is_first):
+        recording = self.audio_parser.parse_audio(recording, is_last)
+        out = ""
+        if len(recording) != 0:
+            if self.secondary_model:
+                self.spectrograms.append(recording)
+            recording = recording.view(1, 1, recording.size(0), recording.size(1))
+            out = self.model(recording, is_first, is_last)
+            if is_first:
+                return ""
+            self.full_output.append(out)
+            decoded_out, _ = self.greedy_decoder.decode(out)
+            transcript = decoded_out[0][0]
+            # "collapsing characters hack" (DanSpeechRecognizer.py:169-174)
+            if self.iterating_transcript and transcript and self.iterating_transcript[-1] == transcript[0]:
+                self.iterating_transcript = self.iterating_transcript + transcript[1:]
+                transcript = transcript[1:]
+            else:
+                self.iterating_transcript += transcript
+            out = transcript if self.string_parts else self.iterating_transcript
+
+        if is_last:
+            if len(self.iterating_transcript) > 1:
+                if self.secondary_model:
+                    final = torch.cat(self.spectrograms, dim=1)
+                    self.spectrograms = []
+                    final = final.view(1, 1, final.size(0), final.size(1))
+                    input_sizes = torch.IntTensor([final.size(3)]).int()
+                    out, _ = self.secondary_model(final, input_sizes)
+                    decoded_out, _ = self.decoder.decode(out)
+                    self.reset_streaming_params()
+                    return decoded_out[0][0]
+                if self.lm != "greedy":
+                    final_out = torch.cat(self.full_output, dim=1)
+                    decoded_out, _ = self.decoder.decode(final_out)
+                    self.reset_streaming_params()
+                    return decoded_out[0][0]
+                out = self.iterating_transcript
+                self.reset_streaming_params()
+                return out
+            return ""
+        return out
+
+    # ------------------------------------------------------------------ offline (DanSpeechRecognizer.py:218-231)
+    def transcribe(self, recording, show_all=False):
+        spect, input_sizes = self.audio_parser.parse_batch([recording])
+        out, output_sizes = self.model(spect, input_sizes)
+        decoded_output, _ = self.decoder.decode(out, output_sizes)
+        if show_all:
+            if self.lm == "greedy":
+                warnings.warn("You are trying to get all beams but no LM has been instantiated.",
+                              NoLmInstantiatedWarning)
+            return decoded_output[0]
+        return decoded_output[0][0]
+
+    def transcribe_batch(self, recordings, show_all=False):
+        """Batched ``transcribe``: sorts by length (pack_padded_sequence contract), restores input order."""
+        order = sorted(range(len(recordings)), key=lambda i: -len(recordings[i]))
+        spect, input_sizes = self.audio_parser.parse_batch([recordings[i] for i in order])
+        out, output_sizes = self.model(spect, input_sizes)
+        decoded_output, _ = self.decoder.decode(out, output_sizes)
+        results = [None] * len(recordings)
+        for pos, i in enumerate(order):
+            results[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
+        return results

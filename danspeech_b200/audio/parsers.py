@@ -1,0 +1,166 @@
+"""Audio -> normalised log-magnitude spectrogram on the GPU.
+
+Mirrors the interface of danspeech/audio/parsers.py (AudioParser :13-34,
+SpectrogramAudioParser :37-72, InferenceSpectrogramAudioParser :75-170); the arithmetic runs in
+csrc/spectrogram.cu through the C ABI (dsb_spectrogram_f32 / dsb_spectrogram_stream_f32).
+
+Differences that are deliberate and documented in INTEGRATION.md:
+  * tensors are returned on the CUDA device (the reference returns CPU tensors that the engine
+    immediately moves with ``.to(device)``, DanSpeechRecognizer.py:220-221);
+  * ``parse_batch`` is an addition: the reference engine is batch-1 only.
+"""
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from .. import _native as N
+
+_SUPPORTED_WINDOWS = ("hamming",)
+
+
+class AudioParser(ABC):
+    """Audio-config holder (reference: parsers.py:13-34)."""
+
+    def __init__(self, audio_config=None):
+        self.audio_config = audio_config or {}
+        self.normalize = self.audio_config.get("normalize", True)
+        self.sampling_rate = self.audio_config.get("sampling_rate", 16000)
+        self.window = self.audio_config.get("window", "hamming")
+        self.window_stride = self.audio_config.get("window_stride", 0.01)
+        self.window_size = self.audio_config.get("window_size", 0.02)
+        self.n_fft = int(self.sampling_rate * self.window_size)
+        self.hop_length = int(self.sampling_rate * self.window_stride)
+        if self.window not in _SUPPORTED_WINDOWS or self.n_fft != 320 or self.hop_length != 160:
+            raise NotImplementedError(
+                "danspeech_b200 spectrogram kernel is specialised for the DanSpeech audio config "
+                "(16 kHz, hamming, 20 ms / 10 ms); got %r" % (self.audio_config,))
+
+    @abstractmethod
+    def parse_audio(self, recording):
+        pass
+
+
+def _as_f32(recording):
+    a = np.ascontiguousarray(np.asarray(recording), dtype=np.float32).reshape(-1)
+    return a
+
+
+class SpectrogramAudioParser(AudioParser):
+    """Offline parser (reference: parsers.py:37-72)."""
+
+    def __init__(self, audio_config=None, device=None):
+        super().__init__(audio_config)
+        self.device = device
+
+    def _dev(self):
+        N.require_cuda()
+        return torch.device(self.device or "cuda")
+
+    def parse_device(self, audio, n_samples, max_samples, out=None, out_stride=None):
+        """audio: cuda f32 [B, stride]; n_samples: cuda i32 [B].  Returns ([B,161,out_stride], mean_std[B,2])."""
+        L = N.lib()
+        B, stride = audio.shape
+        frames = L.dsb_spectrogram_num_frames(int(max_samples))
+        out_stride = out_stride or frames
+        if out is None:
+            out = torch.empty((B, 161, out_stride), dtype=torch.float32, device=audio.device)
+        mean_std = torch.empty((B, 2), dtype=torch.float32, device=audio.device)
+        partials = torch.empty((B, L.dsb_spectrogram_partials(out_stride), 2), dtype=torch.float64, device=audio.device)
+        N.check(L.dsb_spectrogram_f32(N.ptr(audio), stride, N.ptr(n_samples), B, int(max_samples), N.ptr(out),
+                                      out_stride, N.ptr(mean_std), N.ptr(partials), 1 if self.normalize else 0,
+                                      N.current_stream()), "dsb_spectrogram_f32")
+        return out, mean_std
+
+    def parse_batch(self, recordings):
+        """List of 1-D arrays -> (spect cuda f32 [B,1,161,Tmax] zero-padded, lengths IntTensor[B] (CPU))."""
+        dev = self._dev()
+        arrs = [_as_f32(r) for r in recordings]
+        ns = [len(a) for a in arrs]
+        max_n = max(ns)
+        stride = (max_n + 3) // 4 * 4
+        host = torch.zeros((len(arrs), stride), dtype=torch.float32, pin_memory=True)
+        for i, a in enumerate(arrs):
+            host[i, : len(a)] = torch.from_numpy(a)
+        audio = host.to(dev, non_blocking=True)
+        n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
+        out, _ = self.parse_device(audio, n_dev, max_n)
+        lengths = torch.IntTensor([1 + n // self.hop_length for n in ns])
+        return out.view(len(arrs), 1, 161, out.shape[2]), lengths
+
+    def parse_audio(self, recording):
+        """1-D numpy array at raw int16 sample scale -> FloatTensor[161, 1 + n//160] (on the CUDA device)."""
+        spect, _ = self.parse_batch([recording])
+        return spect[0, 0]
+
+
+class InferenceSpectrogramAudioParser(AudioParser):
+    """Streaming parser with adaptive normalisation (reference: parsers.py:75-170).
+
+    The sample carry-over buffer and the running-statistics recurrence are host state exactly as in
+    the reference; the STFT/log1p/statistics/normalisation run on the GPU.
+    """
+
+    def __init__(self, audio_config=None, device=None):
+        super().__init__(audio_config)
+        self.device = device
+        self.dataset_mean = 5.492418704733003
+        self.dataset_std = 1.7552755216970917
+        self.alpha_increment = 0.1
+        self.reset()
+
+    def reset(self):
+        self.buffer = None
+        self.has_buffer = False
+        self.input_mean = 0
+        self.input_std = 0
+        self.alpha = 0
+
+    def parse_audio(self, part_of_recording, is_last=False):
+        if is_last and len(part_of_recording) < self.n_fft:
+            self.reset()
+            return []
+        N.require_cuda()
+        dev = torch.device(self.device or "cuda")
+        part = np.asarray(part_of_recording, dtype=np.float64).reshape(-1)
+        if self.has_buffer:
+            part = np.concatenate((self.buffer, part), axis=None)
+        extra = len(part) % self.hop_length
+        if extra != 0:
+            extra_arr = part[-extra:]
+            part = part[:-extra]
+        self.buffer = part[-self.hop_length:]
+        if extra != 0:
+            self.buffer = np.concatenate((self.buffer, extra_arr), axis=None)
+        self.has_buffer = True
+
+        L = N.lib()
+        n = len(part)
+        stride = (n + 3) // 4 * 4
+        host = torch.zeros((1, stride), dtype=torch.float32)
+        host[0, :n] = torch.from_numpy(part.astype(np.float32))
+        audio = host.to(dev)
+        n_dev = torch.tensor([n], dtype=torch.int32, device=dev)
+        frames = 1 + (n - self.n_fft) // self.hop_length
+        out = torch.empty((1, 161, frames), dtype=torch.float32, device=dev)
+        stats = torch.empty((1, 2), dtype=torch.float64, device=dev)
+        partials = torch.empty((1, L.dsb_spectrogram_partials(frames), 2), dtype=torch.float64, device=dev)
+        N.check(L.dsb_spectrogram_stream_f32(N.ptr(audio), stride, N.ptr(n_dev), 1, n, N.ptr(out), frames,
+                                             N.ptr(stats), N.ptr(partials), N.current_stream()),
+                "dsb_spectrogram_stream_f32")
+        chunk_mean, chunk_std = stats[0].tolist()
+
+        # running statistics, as parsers.py:146-157
+        self.alpha += self.alpha_increment
+        self.input_mean = (self.input_mean + chunk_mean) / 2
+        self.input_std = (self.input_std + chunk_std) / 2
+        if self.alpha < 1.0:
+            mean = self.input_mean * self.alpha + (1 - self.alpha) * self.dataset_mean
+            std = self.input_std * self.alpha + (1 - self.alpha) * self.dataset_std
+        else:
+            mean, std = self.input_mean, self.input_std
+        ms = torch.tensor([[mean, std]], dtype=torch.float32, device=dev)
+        nf = torch.tensor([frames], dtype=torch.int32, device=dev)
+        N.check(L.dsb_spectrogram_stream_normalize(N.ptr(out), frames, N.ptr(nf), 1, N.ptr(ms), N.current_stream()),
+                "dsb_spectrogram_stream_normalize")
+        return out[0]

@@ -1,0 +1,64 @@
+// Shared helpers for the danspeech_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include "../../include/danspeech_b200.h"
+
+namespace dsb {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+int set_error(int code, const char* fmt, ...);
+
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define DSB_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return dsb::set_error(DSB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                               \
+  } while (0)
+
+#define DSB_CHECK_LAUNCH()                                                                     \
+  do {                                                                                         \
+    dsb::count_launch();                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return dsb::set_error(DSB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                  \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+  } while (0)
+
+#define DSB_REQUIRE(cond, ...)                                        \
+  do {                                                                \
+    if (!(cond)) return dsb::set_error(DSB_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+}  // namespace dsb

@@ -1,0 +1,72 @@
+// Internal model representation shared by the model-path translation units.
+#pragma once
+#include "common.cuh"
+#include <map>
+#include <string>
+#include <vector>
+
+namespace dsb {
+
+constexpr int kFreqBins = 161;
+constexpr int kConvKW = 11;   // every DanSpeech conv is kH x 11 with time padding 5
+constexpr int kConvPT = 5;
+
+struct ConvLayer {
+  int cin = 0, cout = 0, kh = 0, sd = 2, st = 1, pd = 0;
+  int din = 0, dout = 0;
+  float* w = nullptr;      // BN-folded weights [cout][cin][kh][11] fp32
+  float* bias = nullptr;   // BN-folded bias [cout]
+  // bf16 tensor-core path
+  __nv_bfloat16* w_tc = nullptr;   // [kh][kw][cout][cin_pad] (conv2/3) or [kh][cout][16] (conv1, kw padded to 16)
+};
+
+struct RnnLayer {
+  int in_size = 0, H = 0, gates = 3, dirs = 1;
+  float* w_ih = nullptr;   // [dirs*gates*H, in_size], BatchNorm1d folded in (layers >= 1)
+  float* b_ih = nullptr;   // [dirs*gates*H]
+  float* w_hh = nullptr;   // [dirs][gates*H][H]
+  float* b_hh = nullptr;   // [dirs][gates*H]
+  __nv_bfloat16* w_ih_tc = nullptr;   // bf16 copy of w_ih
+  __nv_bfloat16* w_hh_tc = nullptr;   // bf16 copy of w_hh
+};
+
+struct HostTensor {
+  const float* data;
+  int64_t numel;
+};
+
+}  // namespace dsb
+
+struct dsb_model {
+  dsb_model_desc desc{};
+  int precision = -1;
+  bool finalized = false;
+  std::map<std::string, dsb::HostTensor> tensors;
+  std::vector<dsb::ConvLayer> convs;
+  std::vector<dsb::RnnLayer> rnns;
+  int rnn_input = 0;                 // C*D fed to the first recurrent layer
+  float* lookahead_w = nullptr;      // [H][context]
+  float* fc_w = nullptr;             // BN-folded [C][H]
+  float* fc_b = nullptr;             // BN-folded [C]
+  std::vector<void*> owned;          // device allocations to free
+};
+
+namespace dsb {
+
+// ---- kernels implemented across the translation units (fp32 CUDA-core path) ----
+int conv2d_bn_htanh_f32(const float* x, int B, int cin, int din, int tin, const ConvLayer& L, const int32_t* d_len,
+                        float* y, int tout, bool rnn_layout, cudaStream_t st);
+int gemm_bias_f32(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K,
+                  cudaStream_t st);
+int rnn_layer_f32(const dsb_model* m, const RnnLayer& L, const float* gates_x, const int32_t* d_len, int B, int Tmax,
+                  int Trows, float* y, float* h_state, float* c_state, cudaStream_t st);
+int lookahead_htanh_f32(const float* x, const float* w, float* y, int T, int B, int H, int context, cudaStream_t st);
+int softmax_argmax_f32(const float* logits, float* probs, int32_t* argmax, int T, int B, int C, cudaStream_t st);
+
+// ---- bf16 tensor-core path (tcgen05 / TMEM / TMA) ----
+int finalize_tc(dsb_model* m, cudaStream_t st);
+size_t forward_tc_workspace_bytes(const dsb_model* m, int B, int T);
+int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B, int T, float* probs,
+               int32_t* argmax, void* workspace, cudaStream_t st);
+
+}  // namespace dsb

@@ -1,0 +1,408 @@
+// Fused spectrogram front-end for sm_100a.
+//
+// Replaces danspeech/audio/parsers.py:50-72 (SpectrogramAudioParser.parse_audio) and the
+// STFT/log1p half of parsers.py:101-163 (InferenceSpectrogramAudioParser.parse_audio):
+//   reflect-pad(160) -> frames of 320 every 160 -> symmetric Hamming -> rfft-320 -> |.| -> log1p
+//   -> (S - mean) / unbiased-std over the whole utterance.
+//
+// One CTA = 32 consecutive frames of one utterance.  The 5 280 samples the tile touches are
+// staged once in shared memory (frames overlap by 50 %), each warp then transforms 4 frames:
+// the real 320-point FFT is a 160-point complex FFT (radix 5 in registers x radix-2^5 across
+// the lanes with warp shuffles) plus the usual even/odd untangling.  log1p|X| is transposed
+// through shared memory so that global stores are 128-byte rows of the [161, T] output.
+//
+// HBM-bound: algorithmic bytes = 4*n (samples) + 4*161*T (output) per utterance.  The
+// normalisation needs the global mean/std first, so the kernel runs twice: MODE_STATS only
+// reduces (re-reading the audio, which the second pass then finds in L2) and MODE_NORM
+// recomputes and writes the normalised result -- cheaper in DRAM traffic than writing raw
+// values and normalising in place.
+#include "common.cuh"
+#include <math.h>
+#include <mutex>
+
+namespace dsb {
+
+constexpr int kNfft = 320;
+constexpr int kHop = 160;
+constexpr int kBins = 161;
+constexpr int kFT = 32;                             // frames per CTA
+constexpr int kTileSamples = kHop * (kFT - 1) + kNfft;  // 5280
+constexpr int kWarps = 8;
+
+enum { MODE_STATS = 0, MODE_NORM = 1, MODE_RAW = 2 };
+
+struct SpecTables {
+  float window[kNfft];      // symmetric Hamming
+  float2 tw160[5][32];      // W160^(lane*k1)
+  float2 tw32[4][32];       // radix-2 DIF stage twiddles, halves 16, 8, 4, 2
+  float2 tw320[kBins + 3];  // W320^k, k = 0..160
+};
+__device__ SpecTables g_tab;
+
+static std::once_flag g_tab_once;
+static cudaError_t g_tab_err = cudaSuccess;
+
+static void init_tables() {
+  static SpecTables h;
+  const double PI = 3.14159265358979323846;
+  for (int k = 0; k < kNfft; ++k) h.window[k] = (float)(0.54 - 0.46 * cos(2.0 * PI * k / (kNfft - 1)));
+  for (int k1 = 0; k1 < 5; ++k1)
+    for (int l = 0; l < 32; ++l) {
+      double a = -2.0 * PI * (double)(l * k1) / 160.0;
+      h.tw160[k1][l] = make_float2((float)cos(a), (float)sin(a));
+    }
+  const int halves[4] = {16, 8, 4, 2};
+  for (int s = 0; s < 4; ++s)
+    for (int l = 0; l < 32; ++l) {
+      int hh = halves[s];
+      double a = -2.0 * PI * (double)(l & (hh - 1)) / (double)(2 * hh);
+      h.tw32[s][l] = make_float2((float)cos(a), (float)sin(a));
+    }
+  for (int k = 0; k < kBins + 3; ++k) {
+    double a = -2.0 * PI * (double)k / 320.0;
+    h.tw320[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  g_tab_err = cudaMemcpyToSymbol(g_tab, &h, sizeof(h));
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// numpy 'reflect' padding index (periodic extension with period 2(n-1), no edge repeat).
+__device__ __forceinline__ int reflect_index(int j, int n) {
+  if (j >= 0 && j < n) return j;
+  if (n == 1) return 0;
+  int period = 2 * (n - 1);
+  j %= period;
+  if (j < 0) j += period;
+  return j < n ? j : period - j;
+}
+
+struct SpecSmem {
+  float samples[kTileSamples];
+  float2 z[kWarps][160];
+  float tile[kBins][kFT + 1];
+  float window[kNfft];
+  float2 tw320[kBins + 3];
+  double red[kWarps][2];
+  float mean_std[2];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kWarps * 32)
+spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const int32_t* __restrict__ n_samples,
+                   float* __restrict__ out, int64_t out_stride, float* __restrict__ mean_std_out,
+                   double* __restrict__ partials, int n_partials, int center, int normalize) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SpecSmem& sm = *reinterpret_cast<SpecSmem*>(smem_raw);
+
+  const int b = blockIdx.y;
+  const int tile_idx = blockIdx.x;
+  const int t0 = tile_idx * kFT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(n_samples[b], (int)audio_stride);
+  const int n_frames = center ? 1 + n / kHop : (n >= kNfft ? 1 + (n - kNfft) / kHop : 0);
+  const float* y = audio + (int64_t)b * audio_stride;
+
+  // mean / std from the MODE_STATS partials (fixed summation order -> deterministic).
+  if (MODE == MODE_NORM) {
+    if (warp == 0) {
+      double s = 0.0, q = 0.0;
+      const int used = normalize ? (n_frames + kFT - 1) / kFT : 0;
+      for (int i = lane; i < used; i += 32) {
+        s += partials[((int64_t)b * n_partials + i) * 2 + 0];
+        q += partials[((int64_t)b * n_partials + i) * 2 + 1];
+      }
+      s = warp_sum(s);
+      q = warp_sum(q);
+      if (lane == 0) {
+        double N = (double)n_frames * kBins;
+        double mean = s / N;
+        double var = (q - s * s / N) / (N - 1.0);   // torch.std: unbiased
+        float m = normalize ? (float)mean : 0.0f;
+        float sd = normalize ? (float)sqrt(var > 0.0 ? var : 0.0) : 1.0f;
+        sm.mean_std[0] = m;
+        sm.mean_std[1] = sd;
+        if (tile_idx == 0 && mean_std_out) {
+          mean_std_out[b * 2 + 0] = m;
+          mean_std_out[b * 2 + 1] = sd;
+        }
+      }
+    }
+  }
+
+  const int frames_here = min(kFT, n_frames - t0);   // may be <= 0 (pure zero fill)
+  if (frames_here > 0) {
+    // ---- stage samples (reflect padding at both utterance ends) ----
+    const int g0 = t0 * kHop - (center ? kNfft / 2 : 0);
+    const int need = kHop * (frames_here - 1) + kNfft;
+    const bool interior = (g0 >= 0) && (g0 + need <= n) && ((audio_stride & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(audio) & 15) == 0);
+    if (interior) {
+      const float4* src = reinterpret_cast<const float4*>(y + g0);   // g0 % 4 == 0
+      float4* dst = reinterpret_cast<float4*>(sm.samples);
+      for (int i = tid; i < need / 4; i += kWarps * 32) dst[i] = __ldg(src + i);
+    } else {
+      for (int i = tid; i < need; i += kWarps * 32) {
+        int j = g0 + i;
+        float v = 0.0f;
+        if (center) v = __ldg(y + reflect_index(j, n));
+        else if (j < n) v = __ldg(y + j);
+        sm.samples[i] = v;
+      }
+    }
+    for (int i = tid; i < kNfft; i += kWarps * 32) sm.window[i] = g_tab.window[i];
+    for (int i = tid; i < kBins + 3; i += kWarps * 32) sm.tw320[i] = g_tab.tw320[i];
+  }
+  // per-lane twiddles (registers)
+  float2 tw160[5], tw32[4];
+#pragma unroll
+  for (int k1 = 0; k1 < 5; ++k1) tw160[k1] = g_tab.tw160[k1][lane];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) tw32[s] = g_tab.tw32[s][lane];
+  __syncthreads();
+
+  double dsum = 0.0, dsq = 0.0;
+  const float C1 = 0.30901699437494742f, C2 = -0.80901699437494742f;
+  const float S1 = 0.95105651629515357f, S2 = 0.58778525229247313f;
+  const int rlane = __brev((unsigned)lane) >> 27;
+
+  for (int f = warp; f < frames_here; f += kWarps) {
+    const float* s = sm.samples + f * kHop;
+    float2 z[5];
+#pragma unroll
+    for (int n1 = 0; n1 < 5; ++n1) {
+      int idx = 2 * (32 * n1 + lane);
+      float2 v = *reinterpret_cast<const float2*>(s + idx);
+      float2 w = *reinterpret_cast<const float2*>(sm.window + idx);
+      z[n1] = make_float2(v.x * w.x, v.y * w.y);
+    }
+    // radix-5 over n1
+    float2 a1 = make_float2(z[1].x + z[4].x, z[1].y + z[4].y);
+    float2 a2 = make_float2(z[2].x + z[3].x, z[2].y + z[3].y);
+    float2 b1 = make_float2(z[1].x - z[4].x, z[1].y - z[4].y);
+    float2 b2 = make_float2(z[2].x - z[3].x, z[2].y - z[3].y);
+    float2 Y[5];
+    Y[0] = make_float2(z[0].x + a1.x + a2.x, z[0].y + a1.y + a2.y);
+    float2 p1 = make_float2(z[0].x + C1 * a1.x + C2 * a2.x, z[0].y + C1 * a1.y + C2 * a2.y);
+    float2 p2 = make_float2(z[0].x + C2 * a1.x + C1 * a2.x, z[0].y + C2 * a1.y + C1 * a2.y);
+    float2 q1 = make_float2(S1 * b1.x + S2 * b2.x, S1 * b1.y + S2 * b2.y);
+    float2 q2 = make_float2(S2 * b1.x - S1 * b2.x, S2 * b1.y - S1 * b2.y);
+    // -i*q = (q.y, -q.x)
+    Y[1] = make_float2(p1.x + q1.y, p1.y - q1.x);
+    Y[4] = make_float2(p1.x - q1.y, p1.y + q1.x);
+    Y[2] = make_float2(p2.x + q2.y, p2.y - q2.x);
+    Y[3] = make_float2(p2.x - q2.y, p2.y + q2.x);
+#pragma unroll
+    for (int k1 = 1; k1 < 5; ++k1) Y[k1] = cmul(Y[k1], tw160[k1]);
+    // five interleaved 32-point DIF FFTs across the lanes
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+      const int half = 16 >> st;
+      const bool upper = (lane & half) != 0;
+#pragma unroll
+      for (int k1 = 0; k1 < 5; ++k1) {
+        float px = __shfl_xor_sync(0xffffffffu, Y[k1].x, half);
+        float py = __shfl_xor_sync(0xffffffffu, Y[k1].y, half);
+        if (!upper) {
+          Y[k1] = make_float2(Y[k1].x + px, Y[k1].y + py);
+        } else {
+          float2 d = make_float2(px - Y[k1].x, py - Y[k1].y);
+          Y[k1] = (st < 4) ? cmul(d, tw32[st < 4 ? st : 0]) : d;
+        }
+      }
+    }
+    // lane holds k2 = bitrev5(lane): Z[k1 + 5*k2]
+    __syncwarp();
+#pragma unroll
+    for (int k1 = 0; k1 < 5; ++k1) sm.z[warp][k1 + 5 * rlane] = Y[k1];
+    __syncwarp();
+    // untangle: X[k] = (Zk + conj(ZN-k))/2 - i/2 * W320^k * (Zk - conj(ZN-k))
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      int k = lane + 32 * j;
+      if (k <= 160) {
+        float2 zk = sm.z[warp][k == 160 ? 0 : k];
+        float2 zn = sm.z[warp][k == 0 || k == 160 ? 0 : 160 - k];
+        zn.y = -zn.y;
+        float2 e = make_float2(zk.x + zn.x, zk.y + zn.y);
+        float2 o = make_float2(zk.x - zn.x, zk.y - zn.y);
+        float2 wo = cmul(sm.tw320[k], o);
+        // -i*wo = (wo.y, -wo.x)
+        float re = 0.5f * (e.x + wo.y);
+        float im = 0.5f * (e.y - wo.x);
+        float mag = sqrtf(re * re + im * im);
+        float v = log1pf(mag);
+        if (MODE != MODE_NORM) {
+          dsum += (double)v;
+          dsq += (double)v * (double)v;
+        }
+        if (MODE != MODE_STATS) sm.tile[k][f] = v;
+      }
+    }
+    __syncwarp();
+  }
+
+  if (MODE != MODE_NORM) {
+    dsum = warp_sum(dsum);
+    dsq = warp_sum(dsq);
+    if (lane == 0) {
+      sm.red[warp][0] = dsum;
+      sm.red[warp][1] = dsq;
+    }
+  }
+  __syncthreads();
+  if (MODE != MODE_NORM) {
+    if (tid == 0 && tile_idx < n_partials) {
+      double s = 0.0, q = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        s += sm.red[w][0];
+        q += sm.red[w][1];
+      }
+      partials[((int64_t)b * n_partials + tile_idx) * 2 + 0] = s;
+      partials[((int64_t)b * n_partials + tile_idx) * 2 + 1] = q;
+    }
+  }
+  if (MODE != MODE_STATS) {
+    float mean = 0.0f, sd = 1.0f;
+    if (MODE == MODE_NORM) {
+      mean = sm.mean_std[0];
+      sd = sm.mean_std[1];
+    }
+    const int t = t0 + lane;
+    if (t < out_stride) {
+      float* o = out + (int64_t)b * kBins * out_stride + t;
+      const bool valid = lane < frames_here;
+      for (int k = warp; k < kBins; k += kWarps) {
+        float v = 0.0f;
+        if (valid) {
+          v = sm.tile[k][lane];
+          if (MODE == MODE_NORM) v = (v - mean) / sd;
+        }
+        o[(int64_t)k * out_stride] = v;
+      }
+    }
+  }
+}
+
+// mean and biased std per stream from the MODE_RAW partials (numpy np.mean / np.std, parsers.py:148-149)
+__global__ void stream_stats_kernel(const double* __restrict__ partials, int n_partials,
+                                    const int32_t* __restrict__ n_samples, double* __restrict__ stats, int S) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  int n = n_samples[s];
+  int n_frames = n >= kNfft ? 1 + (n - kNfft) / kHop : 0;
+  int used = (n_frames + kFT - 1) / kFT;
+  double a = 0.0, q = 0.0;
+  for (int i = 0; i < used; ++i) {
+    a += partials[((int64_t)s * n_partials + i) * 2 + 0];
+    q += partials[((int64_t)s * n_partials + i) * 2 + 1];
+  }
+  double N = (double)n_frames * kBins;
+  double mean = N > 0 ? a / N : 0.0;
+  double var = N > 0 ? q / N - mean * mean : 0.0;
+  stats[s * 2 + 0] = mean;
+  stats[s * 2 + 1] = sqrt(var > 0.0 ? var : 0.0);
+}
+
+__global__ void stream_normalize_kernel(float* __restrict__ spect, int64_t out_stride,
+                                        const int32_t* __restrict__ n_frames, const float* __restrict__ mean_std) {
+  int s = blockIdx.y;
+  int nf = n_frames[s];
+  float mean = mean_std[s * 2 + 0], sd = mean_std[s * 2 + 1];
+  int64_t total = (int64_t)kBins * out_stride;
+  float* p = spect + (int64_t)s * total;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % out_stride);
+    if (t < nf) p[i] = (p[i] - mean) / sd;
+  }
+}
+
+static int ensure_tables() {
+  std::call_once(g_tab_once, init_tables);
+  if (g_tab_err != cudaSuccess)
+    return set_error(DSB_ERR_CUDA, "spectrogram table upload failed: %s", cudaGetErrorString(g_tab_err));
+  return 0;
+}
+
+template <int MODE>
+static int launch_spec(const float* audio, int64_t audio_stride, const int32_t* d_n, int B, float* out,
+                       int64_t out_stride, float* mean_std, double* partials, int n_partials, int tiles, int center,
+                       int normalize, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DSB_CUDA(cudaFuncSetAttribute(spectrogram_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(SpecSmem)));
+    attr_set = true;
+  }
+  dim3 grid(tiles, B);
+  spectrogram_kernel<MODE><<<grid, kWarps * 32, sizeof(SpecSmem), st>>>(audio, audio_stride, d_n, out, out_stride,
+                                                                      mean_std, partials, n_partials, center,
+                                                                      normalize);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace dsb
+
+using namespace dsb;
+
+extern "C" int dsb_spectrogram_num_frames(int n_samples) { return 1 + n_samples / kHop; }
+extern "C" int dsb_spectrogram_partials(int max_frames) { return cdiv(max_frames > 0 ? max_frames : 1, kFT); }
+
+
+extern "C" int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int B,
+                                   int max_samples, float* out, int64_t out_stride, float* mean_std,
+                                   double* partials, int normalize, void* stream) {
+  DSB_REQUIRE(audio && n_samples && out && partials && B > 0, "dsb_spectrogram_f32: null argument or B <= 0");
+  DSB_REQUIRE(max_samples >= 2 && max_samples <= audio_stride, "dsb_spectrogram_f32: max_samples %d out of range",
+              max_samples);
+  if (int e = ensure_tables()) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int max_frames = 1 + max_samples / kHop;
+  DSB_REQUIRE(out_stride >= max_frames, "dsb_spectrogram_f32: out_stride %lld < frames %d", (long long)out_stride,
+              max_frames);
+  const int n_partials = dsb_spectrogram_partials((int)out_stride);
+  const int tiles_valid = cdiv(max_frames, kFT);
+  const int tiles_all = cdiv((int)out_stride, kFT);
+  if (normalize) {
+    if (int e = launch_spec<MODE_STATS>(audio, audio_stride, n_samples, B, out, out_stride, mean_std, partials,
+                                        n_partials, tiles_valid, 1, 1, st))
+      return e;
+  }
+  return launch_spec<MODE_NORM>(audio, audio_stride, n_samples, B, out, out_stride, mean_std, partials, n_partials,
+                                tiles_all, 1, normalize, st);
+}
+
+extern "C" int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int S,
+                                          int max_samples, float* out, int64_t out_stride, double* stats,
+                                          double* partials, void* stream) {
+  DSB_REQUIRE(audio && n_samples && out && partials && stats && S > 0, "dsb_spectrogram_stream_f32: null argument");
+  DSB_REQUIRE(max_samples >= kNfft && max_samples <= audio_stride,
+              "dsb_spectrogram_stream_f32: max_samples %d out of range", max_samples);
+  if (int e = ensure_tables()) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int max_frames = 1 + (max_samples - kNfft) / kHop;
+  DSB_REQUIRE(out_stride >= max_frames, "dsb_spectrogram_stream_f32: out_stride too small");
+  const int n_partials = dsb_spectrogram_partials((int)out_stride);
+  if (int e = launch_spec<MODE_RAW>(audio, audio_stride, n_samples, S, out, out_stride, nullptr, partials,
+                                    n_partials, cdiv((int)out_stride, kFT), 0, 0, st))
+    return e;
+  stream_stats_kernel<<<cdiv(S, 128), 128, 0, st>>>(partials, n_partials, n_samples, stats, S);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dsb_spectrogram_stream_normalize(float* spect, int64_t out_stride, const int32_t* n_frames, int S,
+                                                const float* mean_std, void* stream) {
+  DSB_REQUIRE(spect && n_frames && mean_std && S > 0, "dsb_spectrogram_stream_normalize: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)kBins * out_stride;
+  int64_t gx = cdiv64(total, 256); if (gx > 64) gx = 64;
+  dim3 grid((unsigned)gx, S);
+  stream_normalize_kernel<<<grid, 256, 0, st>>>(spect, out_stride, n_frames, mean_std);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}

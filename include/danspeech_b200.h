@@ -1,0 +1,169 @@
+/*
+ * danspeech_b200 -- C ABI of the B200-native DanSpeech inference hot path.
+ *
+ * Boundary: plain pointers and sizes only (no torch / C++ types).  Every
+ * pointer documented as "device" must be a CUDA device pointer on the current
+ * device; "host" pointers are ordinary host memory.  `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  All functions return 0 on
+ * success and a negative dsb_status on failure; dsb_last_error() returns a
+ * thread-local message for the last failure.  Nothing here allocates behind the
+ * caller's back on the hot path: outputs and workspaces are caller-provided.
+ *
+ * Each entry point names the reference interface it replaces
+ * (paths relative to the reference checkout, danspeech/danspeech).
+ */
+#ifndef DANSPEECH_B200_H
+#define DANSPEECH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  DSB_OK = 0,
+  DSB_ERR_INVALID = -1,   /* bad argument */
+  DSB_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+  DSB_ERR_STATE = -3,     /* call order violated (e.g. forward before finalize) */
+  DSB_ERR_WORKSPACE = -4, /* caller workspace too small */
+  DSB_ERR_UNSUPPORTED = -5,
+  DSB_ERR_IO = -6         /* LM file unreadable / malformed */
+} dsb_status;
+
+const char* dsb_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int dsb_abi_version(void);
+/* Number of kernels launched by this library since process start (bench.py "gpu_launches"). */
+uint64_t dsb_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Spectrogram (replaces danspeech/audio/parsers.py:50-72,
+ * SpectrogramAudioParser.parse_audio: librosa.stft(n_fft=320, hop=160, symmetric
+ * Hamming, center/reflect) -> |.| -> log1p -> (S-mean)/unbiased-std per utterance).
+ *
+ *   audio          device f32 [B, audio_stride]; utterance b occupies samples [0, n_samples[b])
+ *   n_samples      device i32 [B];  max_samples = max over b (host scalar, sizes the grid)
+ *   out            device f32 [B, n_freq=161, out_stride]; frames t >= 1+n/160 are written as 0
+ *   mean_std       device f32 [B, 2] (mean, std actually applied)  -- may be NULL
+ *   partials       device f64 [B, dsb_spectrogram_partials(max_frames), 2] scratch
+ *   normalize      audio_conf["normalize"] (parsers.py:25)
+ * ------------------------------------------------------------------------- */
+int dsb_spectrogram_num_frames(int n_samples);                 /* 1 + n/160 */
+int dsb_spectrogram_partials(int max_frames);                  /* scratch rows per utterance */
+int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int B,
+                        int max_samples, float* out, int64_t out_stride, float* mean_std, double* partials,
+                        int normalize, void* stream);
+
+/* Streaming spectrogram (replaces parsers.py:101-163, InferenceSpectrogramAudioParser:
+ * center=False STFT of an already assembled chunk, log1p, BIASED mean/std of the chunk
+ * returned to the host, which owns the running-statistics recurrence; then
+ * dsb_spectrogram_stream_normalize applies (S-mean)/std with the blended values).
+ *   audio     device f32 [S, audio_stride] chunk per stream (carry-over already prepended)
+ *   n_samples device i32 [S] (multiple of 160, >= 320); max_samples host scalar
+ *   out       device f32 [S, 161, out_stride]   un-normalised log1p|STFT|
+ *   stats     device f64 [S, 2]  (mean, biased std) of each chunk
+ */
+int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int S,
+                               int max_samples, float* out, int64_t out_stride, double* stats, double* partials,
+                               void* stream);
+int dsb_spectrogram_stream_normalize(float* spect, int64_t out_stride, const int32_t* n_frames /* device */, int S,
+                                     const float* mean_std /* device f32 [S,2] */, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Acoustic model (replaces danspeech/deepspeech/model.py: DeepSpeech.__init__ :293-425,
+ * forward :496-515, get_seq_lens :540-551, MaskConv :65-81, BatchRNN :114-122,
+ * Lookahead :143-148, SequenceWise fc :414-420, InferenceBatchSoftmax :89-93,
+ * and the streaming twins :156-284, :517-537).
+ * ------------------------------------------------------------------------- */
+typedef struct dsb_model dsb_model;
+
+typedef enum { DSB_RNN_GRU = 0, DSB_RNN_LSTM = 1, DSB_RNN_TANH = 2 } dsb_rnn_type;
+typedef enum { DSB_PREC_FP32 = 0, DSB_PREC_BF16 = 1 } dsb_precision;
+
+typedef struct {
+  int32_t conv_layers;     /* 1..3            (model.py:344-348 raises ConvError otherwise) */
+  int32_t rnn_layers;
+  int32_t rnn_hidden_size;
+  int32_t rnn_type;        /* dsb_rnn_type    (supported_rnns, model.py:14-19) */
+  int32_t bidirectional;
+  int32_t context;         /* lookahead context, uni-directional models only */
+  int32_t num_classes;     /* len(labels) */
+  int32_t streaming;       /* streaming_inference_model (model.py:350-351) */
+} dsb_model_desc;
+
+int dsb_model_create(const dsb_model_desc* desc, dsb_model** out);
+void dsb_model_destroy(dsb_model* m);
+/* Hand one state-dict tensor (reference names, e.g. "rnns.3.rnn.weight_hh_l0_reverse",
+ * SURVEY A.6) to the model.  `data` is a device f32 pointer that must stay valid until
+ * dsb_model_finalize returns; it is not retained afterwards. */
+int dsb_model_set_tensor(dsb_model* m, const char* name, const float* data, int64_t numel);
+/* Folds eval-mode BatchNorm into the adjacent weights, packs kernel layouts. */
+int dsb_model_finalize(dsb_model* m, int precision, void* stream);
+int dsb_model_precision(const dsb_model* m);
+
+/* get_seq_lens (model.py:540-551): T' = (T-1)/2 + 1 for every supported conv stack. */
+int dsb_model_out_frames(const dsb_model* m, int T);
+size_t dsb_forward_workspace_bytes(const dsb_model* m, int B, int T);
+/* DeepSpeech.forward.
+ *   spect       device f32 [B, 161, T]  zero-padded after normalisation
+ *   lengths     host   i32 [B]          spectrogram frames per utterance; sorted descending
+ *                                       (pack_padded_sequence contract, model.py:117) -> DSB_ERR_INVALID otherwise
+ *   probs       device f32 [B, T', C]   softmax rows (rows t >= T'_b hold a valid softmax row, as upstream)
+ *   out_lengths host   i32 [B]
+ *   argmax      device i32 [B, T'] or NULL: fused argmax of each row (torch.max(probs,2), decoder.py:195)
+ */
+int dsb_forward(dsb_model* m, const float* spect, const int32_t* lengths, int B, int T,
+                float* probs, int32_t* out_lengths, int32_t* argmax,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Streaming (model.py:517-537 and the *Stream modules): S lock-step streams. */
+typedef struct dsb_stream_state dsb_stream_state;
+int dsb_stream_state_create(dsb_model* m, int n_streams, int max_chunk_frames, dsb_stream_state** out);
+void dsb_stream_state_destroy(dsb_stream_state* s);
+/* chunk device f32 [S,161,k]; probs device f32 [S, k_out_max, C]; *k_out receives the
+ * number of frames emitted (0 when the lookahead layer is still buffering, i.e. the
+ * reference returns None, model.py:529-530). */
+int dsb_stream_max_out_frames(const dsb_stream_state* s, int k);
+int dsb_streaming_forward(dsb_model* m, dsb_stream_state* s, const float* chunk, int k,
+                          int is_first, int is_last, float* probs, int32_t* k_out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Greedy CTC (replaces danspeech/deepspeech/decoder.py:151-198, GreedyDecoder:
+ * argmax -> drop blanks -> drop a symbol equal to the previous frame's symbol).
+ *   probs    device f32 [B,T,C] (or NULL when `argmax` device i32 [B,T] is given)
+ *   sizes    device i32 [B] or NULL (= T for every row, decoder.py:156)
+ *   tokens   device i32 [B,T]  label indices kept;  offsets device i32 [B,T] their frame index
+ *   out_len  device i32 [B]
+ * ------------------------------------------------------------------------- */
+int dsb_greedy_decode(const float* probs, const int32_t* argmax, const int32_t* sizes, int B, int T, int C,
+                      int blank, int32_t* tokens, int32_t* offsets, int32_t* out_len, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Beam CTC decoder (replaces the ctcdecode.CTCBeamDecoder object built at
+ * decoder.py:99-100 and called at decoder.py:140; argument order as upstream).
+ *   labels_utf8  n_labels NUL-separated UTF-8 strings, one per class
+ *   lm_path      ARPA text LM path or NULL (no LM)
+ * dsb_beam_decode: probs device f32 [B,T,C]; seq_lens host i32 [B];
+ *   out_tokens/out_timesteps device i32 [B,beam,T]; out_scores device f32 [B,beam]
+ *   (positive: -log p, lower is better); out_lens device i32 [B,beam].
+ * ------------------------------------------------------------------------- */
+typedef struct dsb_beam dsb_beam;
+int dsb_beam_create(const char* labels_utf8, int n_labels, const char* lm_path, float alpha, float beta,
+                    int cutoff_top_n, float cutoff_prob, int beam_width, int blank_id, int log_probs_input,
+                    dsb_beam** out);
+void dsb_beam_destroy(dsb_beam* d);
+size_t dsb_beam_workspace_bytes(const dsb_beam* d, int B, int T);
+int dsb_beam_decode(dsb_beam* d, const float* probs, const int32_t* seq_lens, int B, int T, int C,
+                    int32_t* out_tokens, int32_t* out_timesteps, float* out_scores, int32_t* out_lens,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* LM introspection used by the host wrapper and tests. */
+int dsb_beam_lm_order(const dsb_beam* d);
+int dsb_beam_lm_is_char_based(const dsb_beam* d);
+int64_t dsb_beam_lm_num_ngrams(const dsb_beam* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DANSPEECH_B200_H */
