@@ -170,11 +170,17 @@ class DanSpeechRecognizer(object):
 
     def transcribe_batch(self, recordings, show_all=False):
         """Batched ``transcribe``: sorts by length (pack_padded_sequence contract), restores input order."""
-        order = sorted(range(len(recordings)), key=lambda i: -len(recordings[i]))
-        spect, input_sizes = self.audio_parser.parse_batch([recordings[i] for i in order])
+        if isinstance(recordings, tuple):
+            # (host float32 tensor [B, stride] (ideally pinned), n_samples) already sorted by length descending
+            host_audio, n_samples = recordings
+            order = list(range(len(n_samples)))
+            spect, input_sizes = self.audio_parser.parse_packed(host_audio, n_samples)
+        else:
+            order = sorted(range(len(recordings)), key=lambda i: -len(recordings[i]))
+            spect, input_sizes = self.audio_parser.parse_batch([recordings[i] for i in order])
         out, output_sizes = self.model(spect, input_sizes)
         decoded_output, _ = self.decoder.decode(out, output_sizes)
-        results = [None] * len(recordings)
+        results = [None] * len(order)
         for pos, i in enumerate(order):
             results[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
         return results

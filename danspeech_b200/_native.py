@@ -26,6 +26,9 @@ _SIGS = {
     "dsb_last_error": (c_char_p, []),
     "dsb_abi_version": (c_int, []),
     "dsb_kernel_launch_count": (c_uint64, []),
+    "dsb_profile_enable": (None, [c_int]),
+    "dsb_profile_reset": (None, []),
+    "dsb_profile_read": (c_int, [c_int, POINTER(c_double), POINTER(c_int)]),
     "dsb_spectrogram_num_frames": (c_int, [c_int]),
     "dsb_spectrogram_partials": (c_int, [c_int]),
     "dsb_spectrogram_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p,
@@ -92,6 +95,19 @@ def check(code, what=""):
 
 def launch_count():
     return int(lib().dsb_kernel_launch_count())
+
+
+STAGES = ("spectrogram", "conv", "rnn_input_proj", "rnn_recurrence", "tail", "greedy", "beam")
+
+
+def profile_read():
+    """{stage: (total_ms, spans)} since the last dsb_profile_reset()."""
+    out = {}
+    for i, name in enumerate(STAGES):
+        ms, n = c_double(0), c_int(0)
+        check(lib().dsb_profile_read(i, ms, n), "dsb_profile_read")
+        out[name] = (ms.value, n.value)
+    return out
 
 
 def ptr(t):

@@ -88,6 +88,18 @@ class SpectrogramAudioParser(AudioParser):
         lengths = torch.IntTensor([1 + n // self.hop_length for n in ns])
         return out.view(len(arrs), 1, 161, out.shape[2]), lengths
 
+    def parse_packed(self, host_audio, n_samples):
+        """host_audio: (pinned) CPU f32 tensor [B, stride] already sorted by length descending."""
+        dev = self._dev()
+        if host_audio.dtype != torch.float32 or host_audio.dim() != 2:
+            raise ValueError("parse_packed expects a 2-D float32 tensor")
+        ns = [int(v) for v in n_samples]
+        audio = host_audio.to(dev, non_blocking=True)
+        n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
+        out, _ = self.parse_device(audio, n_dev, max(ns))
+        lengths = torch.IntTensor([1 + n // self.hop_length for n in ns])
+        return out.view(len(ns), 1, 161, out.shape[2]), lengths
+
     def parse_audio(self, recording):
         """1-D numpy array at raw int16 sample scale -> FloatTensor[161, 1 + n//160] (on the CUDA device)."""
         spect, _ = self.parse_batch([recording])

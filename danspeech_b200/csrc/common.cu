@@ -1,4 +1,6 @@
 #include "common.cuh"
+#include <mutex>
+#include <vector>
 
 namespace dsb {
 thread_local char g_err[512] = {0};
@@ -11,7 +13,65 @@ int set_error(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+// ---- stage timers ----
+struct Span { cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+static std::vector<Span> g_spans[ST_COUNT];
+static std::vector<Span> g_pool;
+static Span g_open[ST_COUNT];
+static bool g_is_open[ST_COUNT] = {false};
+
+void prof_begin(int stage, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  Span s;
+  if (!g_pool.empty()) {
+    s = g_pool.back();
+    g_pool.pop_back();
+  } else {
+    cudaEventCreate(&s.a);
+    cudaEventCreate(&s.b);
+  }
+  cudaEventRecord(s.a, st);
+  g_open[stage] = s;
+  g_is_open[stage] = true;
+}
+void prof_end(int stage, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_is_open[stage]) return;
+  cudaEventRecord(g_open[stage].b, st);
+  g_spans[stage].push_back(g_open[stage]);
+  g_is_open[stage] = false;
+}
 }  // namespace dsb
+
+extern "C" void dsb_profile_enable(int on) { dsb::g_prof_on = on != 0; }
+extern "C" void dsb_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(dsb::g_prof_mu);
+  for (int i = 0; i < dsb::ST_COUNT; ++i) {
+    for (auto& s : dsb::g_spans[i]) dsb::g_pool.push_back(s);
+    dsb::g_spans[i].clear();
+  }
+}
+extern "C" int dsb_profile_read(int stage, double* total_ms, int* spans) {
+  if (stage < 0 || stage >= dsb::ST_COUNT || !total_ms || !spans)
+    return dsb::set_error(DSB_ERR_INVALID, "dsb_profile_read: bad argument");
+  std::lock_guard<std::mutex> lk(dsb::g_prof_mu);
+  double t = 0.0;
+  for (auto& s : dsb::g_spans[stage]) {
+    cudaError_t e = cudaEventSynchronize(s.b);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.a, s.b);
+    if (e != cudaSuccess) return dsb::set_error(DSB_ERR_CUDA, "dsb_profile_read: %s", cudaGetErrorString(e));
+    t += ms;
+  }
+  *total_ms = t;
+  *spans = (int)dsb::g_spans[stage].size();
+  return 0;
+}
 
 extern "C" const char* dsb_last_error(void) { return dsb::g_err; }
 extern "C" int dsb_abi_version(void) { return 1; }

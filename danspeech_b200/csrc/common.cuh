@@ -39,6 +39,17 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     if (!(cond)) return dsb::set_error(DSB_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
+// Stage timers (CUDA events on the launching stream), enabled by dsb_profile_enable().
+enum Stage { ST_SPECT = 0, ST_CONV, ST_PROJ, ST_RNN, ST_TAIL, ST_GREEDY, ST_BEAM, ST_COUNT };
+void prof_begin(int stage, cudaStream_t st);
+void prof_end(int stage, cudaStream_t st);
+struct ProfScope {
+  int stage;
+  cudaStream_t st;
+  ProfScope(int s, cudaStream_t t) : stage(s), st(t) { prof_begin(stage, st); }
+  ~ProfScope() { prof_end(stage, st); }
+};
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -354,6 +354,7 @@ extern "C" int dsb_forward(dsb_model* m, const float* spect, const int32_t* leng
   // MaskConv stack; the last block writes the [T', B, C*D] layout the RNN consumes (model.py:501-503)
   const float* x = spect;
   int cur = 0, cin = 1, din = kFreqBins, tin = T;
+  prof_begin(ST_CONV, st);
   for (size_t i = 0; i < m->convs.size(); ++i) {
     const bool last = i + 1 == m->convs.size();
     if (int e = conv2d_bn_htanh_f32(x, B, cin, din, tin, m->convs[i], ws.d_len, ws.act[cur], Tp, last, st)) return e;
@@ -363,17 +364,23 @@ extern "C" int dsb_forward(dsb_model* m, const float* spect, const int32_t* leng
     din = m->convs[i].dout;
     tin = Tp;
   }
+  prof_end(ST_CONV, st);
   const int Tmax = out_lengths[0];
   for (size_t l = 0; l < m->rnns.size(); ++l) {
     const RnnLayer& R = m->rnns[l];
     const int N = R.dirs * R.gates * R.H;
+    prof_begin(ST_PROJ, st);
     if (int e = gemm_bias_f32(x, R.w_ih, R.b_ih, ws.gates, (int64_t)Tp * B, N, R.in_size, st)) return e;
+    prof_end(ST_PROJ, st);
+    prof_begin(ST_RNN, st);
     // y rows t in [Tmax, Tp) must be zero as well: rnn_layer_f32 zeroes Tp rows
     if (int e = rnn_layer_f32(m, R, ws.gates, ws.d_len, B, Tmax, Tp, ws.act[cur], ws.hstate, ws.cstate, st))
       return e;
+    prof_end(ST_RNN, st);
     x = ws.act[cur];
     cur ^= 1;
   }
+  ProfScope tail_scope(ST_TAIL, st);
   if (!d.bidirectional) {
     if (int e = lookahead_htanh_f32(x, m->lookahead_w, ws.act[cur], Tp, B, H, d.context, st)) return e;
     x = ws.act[cur];

@@ -367,6 +367,7 @@ extern "C" int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, con
   const int n_partials = dsb_spectrogram_partials((int)out_stride);
   const int tiles_valid = cdiv(max_frames, kFT);
   const int tiles_all = cdiv((int)out_stride, kFT);
+  ProfScope scope(ST_SPECT, st);
   if (normalize) {
     if (int e = launch_spec<MODE_STATS>(audio, audio_stride, n_samples, B, out, out_stride, mean_std, partials,
                                         n_partials, tiles_valid, 1, 1, st))

@@ -121,6 +121,7 @@ extern "C" int dsb_greedy_decode(const float* probs, const int32_t* argmax, cons
   DSB_REQUIRE((probs || argmax) && tokens && offsets && out_len, "dsb_greedy_decode: null argument");
   DSB_REQUIRE(B > 0 && T >= 0 && C > 0, "dsb_greedy_decode: bad shape B=%d T=%d C=%d", B, T, C);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope scope(ST_GREEDY, st);
   greedy_kernel<<<cdiv(B, 4), 128, 0, st>>>(probs, argmax, sizes, B, T, C, blank, tokens, offsets, out_len);
   DSB_CHECK_LAUNCH();
   return 0;

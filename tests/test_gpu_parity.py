@@ -1,0 +1,164 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star): spectrograms and probabilities within 1e-4 relative in fp32
+mode (max|a-b|/max|b|), greedy transcripts bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import BATCH_CASES, BATCH_LENS, batch_inputs, case_config, rel_err
+from oracle import greedy as og
+from oracle import model as om
+from oracle import spectrogram as osp
+from danspeech_b200.utils import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+
+
+def _model(name, kw, seed, precision="fp32"):
+    from danspeech_b200.pretrained_models import build_model
+    kw = dict(kw)
+    rt = kw.pop("rnn_type", "gru")
+    m = build_model(name, seed=seed, rnn_type=rt, **kw).cuda().eval()
+    m.set_precision(precision)
+    return m
+
+
+# ------------------------------------------------------------------ spectrogram
+def test_spectrogram_matches_golden(golden):
+    from danspeech_b200.audio.parsers import SpectrogramAudioParser
+    p = SpectrogramAudioParser()
+    for name in ("u0013002", "u0042018"):
+        s = p.parse_audio(golden["wav_" + name].astype(np.float64))
+        assert s.is_cuda and tuple(s.shape) == golden["spect_" + name].shape
+        assert rel_err(s.cpu().numpy(), golden["spect_" + name]) < FP32_TOL
+    for i, n in enumerate((161, 1000, 16000, 40001)):
+        s = p.parse_audio(syn.synthetic_audio(n, seed=100 + i))
+        assert rel_err(s.cpu().numpy(), golden["spect_syn%d" % n]) < FP32_TOL
+
+
+def test_spectrogram_ragged_batch_zero_padded():
+    from danspeech_b200.audio.parsers import SpectrogramAudioParser
+    p = SpectrogramAudioParser()
+    auds, x_ref, xl = batch_inputs()
+    x, lens = p.parse_batch(auds)
+    assert lens.tolist() == xl.tolist()
+    assert rel_err(x.cpu().numpy(), x_ref.numpy()) < FP32_TOL
+    for b, L in enumerate(lens.tolist()):
+        assert float(x[b, 0, :, L:].abs().max() if L < x.shape[3] else 0.0) == 0.0
+
+
+def test_spectrogram_full_size_properties():
+    """BASELINE config-2 size (64 x 15 s): per-utterance mean 0 / unbiased std 1, batch == single."""
+    from danspeech_b200.audio.parsers import SpectrogramAudioParser
+    p = SpectrogramAudioParser()
+    auds = [syn.synthetic_audio(240000, seed=i) for i in range(64)]
+    x, lens = p.parse_batch(auds)
+    assert tuple(x.shape) == (64, 1, 161, 1501) and set(lens.tolist()) == {1501}
+    flat = x.view(64, -1).double()
+    assert float(flat.mean(1).abs().max()) < 1e-5
+    assert float((flat.std(1) - 1).abs().max()) < 1e-5
+    single = p.parse_audio(auds[17])
+    assert torch.equal(single, x[17, 0])
+    ref = osp.SpectrogramOracle().parse_audio(auds[17]).numpy()
+    assert rel_err(single.cpu().numpy(), ref) < FP32_TOL
+
+
+def test_streaming_spectrogram_matches_golden(golden):
+    from danspeech_b200.audio.parsers import InferenceSpectrogramAudioParser
+    a = golden["wav_u0013002"].astype(np.float64)
+    chunks = [a[:8640]] + [a[8640 + 6240 * i: 8640 + 6240 * (i + 1)] for i in range(12)]
+    chunks = [c for c in chunks if len(c) > 0]
+    sp = InferenceSpectrogramAudioParser()
+    for i, c in enumerate(chunks):
+        s = sp.parse_audio(c, is_last=(i == len(chunks) - 1))
+        ref = golden["stream_spect_%d" % i]
+        if ref.size == 0:
+            assert len(s) == 0
+        else:
+            assert rel_err(s.cpu().numpy(), ref) < FP32_TOL
+
+
+# ------------------------------------------------------------------ acoustic model, fp32 mode
+def test_forward_config1_matches_golden(golden):
+    m = _model("TestModel", {}, seed=0)
+    sp = torch.from_numpy(golden["spect_u0013002"]).cuda()
+    probs, sizes = m(sp.view(1, 1, 161, -1), torch.IntTensor([sp.size(1)]))
+    assert tuple(probs.shape) == (1, 210, 33)
+    assert sizes.tolist() == golden["cfg1_sizes"].tolist()
+    assert rel_err(probs.cpu().numpy(), golden["cfg1_probs"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("tag,name,kw", BATCH_CASES, ids=[c[0] for c in BATCH_CASES])
+def test_forward_ragged_batch_matches_golden(golden, tag, name, kw):
+    from danspeech_b200.deepspeech.decoder import GreedyDecoder
+    m = _model(name, kw, seed=3)
+    _, x, xl = batch_inputs()
+    probs, sizes = m(x.cuda(), xl)
+    ref = golden["batch_%s_probs" % tag]
+    assert tuple(probs.shape) == ref.shape
+    assert sizes.tolist() == golden["batch_%s_sizes" % tag].tolist()
+    # rows t >= size hold unspecified-but-normalised softmax rows upstream too; compare valid rows
+    for b, L in enumerate(sizes.tolist()):
+        assert rel_err(probs[b, :L].cpu().numpy(), ref[b, :L]) < FP32_TOL
+    strings, offs = GreedyDecoder(syn.LABELS, blank_index=0).decode(probs, sizes)
+    assert [s[0] for s in strings] == [str(s) for s in golden["batch_%s_text" % tag]]
+    assert np.array_equal(np.concatenate([o[0].numpy() for o in offs]), golden["batch_%s_offs" % tag])
+
+
+def test_forward_batch_invariance():
+    """MaskConv + packed sequences make a padded batch equal to single-utterance runs (model.py:57-58)."""
+    m = _model("TestModel", dict(rnn_hidden_size=96, rnn_layers=3), seed=3)
+    _, x, xl = batch_inputs()
+    probs, sizes = m(x.cuda(), xl)
+    for b in range(3):
+        L = int(xl[b])
+        p1, s1 = m(x[b:b + 1, :, :, :L].cuda(), xl[b:b + 1])
+        assert int(s1[0]) == int(sizes[b])
+        assert rel_err(p1[0].cpu().numpy(), probs[b, : int(sizes[b])].cpu().numpy()) < 1e-5
+
+
+def test_forward_rejects_unsorted_lengths():
+    m = _model("TestModel", dict(rnn_hidden_size=64, rnn_layers=1), seed=1)
+    x = torch.zeros(2, 1, 161, 50).cuda()
+    with pytest.raises(RuntimeError):
+        m(x, torch.IntTensor([40, 50]))
+
+
+# ------------------------------------------------------------------ greedy decoder
+def test_greedy_kernel_bit_exact_random():
+    from danspeech_b200.deepspeech.decoder import GreedyDecoder
+    rng = np.random.default_rng(0)
+    B, T, C = 7, 333, 33
+    # sticky random paths so repeats / blanks / spaces all occur
+    probs = np.full((B, T, C), 1e-3, dtype=np.float32)
+    for b in range(B):
+        s = 0
+        for t in range(T):
+            if rng.random() < 0.4:
+                s = int(rng.integers(0, C)) if rng.random() < 0.7 else 0
+            probs[b, t, s] = 0.9
+    sizes = [333, 300, 32, 31, 1, 0, 64]
+    ref_s, ref_o = og.greedy_decode(probs, sizes, syn.LABELS)
+    dec = GreedyDecoder(syn.LABELS, blank_index=0)
+    got_s, got_o = dec.decode(torch.from_numpy(probs).cuda(), torch.IntTensor(sizes))
+    assert got_s == ref_s
+    for b in range(B):
+        assert got_o[b][0].tolist() == ref_o[b][0].tolist()
+    got_s2, _ = dec.decode(torch.from_numpy(probs).cuda())           # sizes=None -> full T (decoder.py:156)
+    assert got_s2 == og.greedy_decode(probs, None, syn.LABELS)[0]
+
+
+# ------------------------------------------------------------------ end to end through the Recognizer API
+def test_recognizer_config1_end_to_end(golden):
+    """BASELINE config 1: TestModel-shaped weights, u0013002.wav, greedy -- transcript bit-exact."""
+    from danspeech_b200 import Recognizer
+    from danspeech_b200.pretrained_models import TestModel
+    r = Recognizer(model=TestModel(seed=0).set_precision("fp32"))
+    text = r.recognize(golden["wav_u0013002"].astype(np.float64))
+    assert text == str(golden["cfg1_text"])
+    batch = r.recognize_batch([golden["wav_u0042018"].astype(np.float64), golden["wav_u0013002"].astype(np.float64)])
+    assert batch[1] == text
