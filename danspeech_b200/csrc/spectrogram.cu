@@ -31,11 +31,15 @@ constexpr int kWarps = 8;
 
 enum { MODE_STATS = 0, MODE_NORM = 1, MODE_RAW = 2 };
 
+// The reference STFT runs in float64 (librosa on a float64 signal) and int16-scale audio has ~1e6:1
+// dynamic range between strong and weak bins, so an fp32 FFT leaves ~1e-3 errors in the weak bins
+// after log1p.  The transform therefore runs in fp64 (B200 FP64 is half the FP32 rate; the kernel
+// stays far from the FP64 roof); only log1p and the normalisation are fp32, as upstream.
 struct SpecTables {
-  float window[kNfft];      // symmetric Hamming
-  float2 tw160[5][32];      // W160^(lane*k1)
-  float2 tw32[4][32];       // radix-2 DIF stage twiddles, halves 16, 8, 4, 2
-  float2 tw320[kBins + 3];  // W320^k, k = 0..160
+  double window[kNfft];      // symmetric Hamming
+  double2 tw160[5][32];      // W160^(lane*k1)
+  double2 tw32[4][32];       // radix-2 DIF stage twiddles, halves 16, 8, 4, 2
+  double2 tw320[kBins + 3];  // W320^k, k = 0..160
 };
 __device__ SpecTables g_tab;
 
@@ -45,29 +49,31 @@ static cudaError_t g_tab_err = cudaSuccess;
 static void init_tables() {
   static SpecTables h;
   const double PI = 3.14159265358979323846;
-  for (int k = 0; k < kNfft; ++k) h.window[k] = (float)(0.54 - 0.46 * cos(2.0 * PI * k / (kNfft - 1)));
+  for (int k = 0; k < kNfft; ++k) h.window[k] = 0.54 - 0.46 * cos(2.0 * PI * k / (kNfft - 1));
   for (int k1 = 0; k1 < 5; ++k1)
     for (int l = 0; l < 32; ++l) {
       double a = -2.0 * PI * (double)(l * k1) / 160.0;
-      h.tw160[k1][l] = make_float2((float)cos(a), (float)sin(a));
+      h.tw160[k1][l] = make_double2(cos(a), sin(a));
     }
   const int halves[4] = {16, 8, 4, 2};
   for (int s = 0; s < 4; ++s)
     for (int l = 0; l < 32; ++l) {
       int hh = halves[s];
       double a = -2.0 * PI * (double)(l & (hh - 1)) / (double)(2 * hh);
-      h.tw32[s][l] = make_float2((float)cos(a), (float)sin(a));
+      h.tw32[s][l] = make_double2(cos(a), sin(a));
     }
   for (int k = 0; k < kBins + 3; ++k) {
     double a = -2.0 * PI * (double)k / 320.0;
-    h.tw320[k] = make_float2((float)cos(a), (float)sin(a));
+    h.tw320[k] = make_double2(cos(a), sin(a));
   }
   g_tab_err = cudaMemcpyToSymbol(g_tab, &h, sizeof(h));
 }
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
 // numpy 'reflect' padding index (periodic extension with period 2(n-1), no edge repeat).
 __device__ __forceinline__ int reflect_index(int j, int n) {
@@ -80,12 +86,12 @@ __device__ __forceinline__ int reflect_index(int j, int n) {
 }
 
 struct SpecSmem {
-  float samples[kTileSamples];
-  float2 z[kWarps][160];
-  float tile[kBins][kFT + 1];
-  float window[kNfft];
-  float2 tw320[kBins + 3];
-  double red[kWarps][2];
+  alignas(16) float samples[kTileSamples];   // read as float2 / written as float4
+  alignas(16) double window[kNfft];          // read as double2
+  alignas(16) double2 z[kWarps][160];
+  alignas(16) double2 tw320[kBins + 3];
+  alignas(16) double red[kWarps][2];
+  alignas(16) float tile[kBins][kFT + 1];
   float mean_std[2];
 };
 
@@ -156,7 +162,7 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
     for (int i = tid; i < kBins + 3; i += kWarps * 32) sm.tw320[i] = g_tab.tw320[i];
   }
   // per-lane twiddles (registers)
-  float2 tw160[5], tw32[4];
+  double2 tw160[5], tw32[4];
 #pragma unroll
   for (int k1 = 0; k1 < 5; ++k1) tw160[k1] = g_tab.tw160[k1][lane];
 #pragma unroll
@@ -164,36 +170,34 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
   __syncthreads();
 
   double dsum = 0.0, dsq = 0.0;
-  const float C1 = 0.30901699437494742f, C2 = -0.80901699437494742f;
-  const float S1 = 0.95105651629515357f, S2 = 0.58778525229247313f;
+  const double C1 = 0.30901699437494742, C2 = -0.80901699437494742;
+  const double S1 = 0.95105651629515357, S2 = 0.58778525229247313;
   const int rlane = __brev((unsigned)lane) >> 27;
 
   for (int f = warp; f < frames_here; f += kWarps) {
     const float* s = sm.samples + f * kHop;
-    float2 z[5];
+    double2 z[5];
 #pragma unroll
     for (int n1 = 0; n1 < 5; ++n1) {
       int idx = 2 * (32 * n1 + lane);
       float2 v = *reinterpret_cast<const float2*>(s + idx);
-      float2 w = *reinterpret_cast<const float2*>(sm.window + idx);
-      z[n1] = make_float2(v.x * w.x, v.y * w.y);
+      double2 w = *reinterpret_cast<const double2*>(sm.window + idx);
+      z[n1] = make_double2((double)v.x * w.x, (double)v.y * w.y);
     }
     // radix-5 over n1
-    float2 a1 = make_float2(z[1].x + z[4].x, z[1].y + z[4].y);
-    float2 a2 = make_float2(z[2].x + z[3].x, z[2].y + z[3].y);
-    float2 b1 = make_float2(z[1].x - z[4].x, z[1].y - z[4].y);
-    float2 b2 = make_float2(z[2].x - z[3].x, z[2].y - z[3].y);
-    float2 Y[5];
-    Y[0] = make_float2(z[0].x + a1.x + a2.x, z[0].y + a1.y + a2.y);
-    float2 p1 = make_float2(z[0].x + C1 * a1.x + C2 * a2.x, z[0].y + C1 * a1.y + C2 * a2.y);
-    float2 p2 = make_float2(z[0].x + C2 * a1.x + C1 * a2.x, z[0].y + C2 * a1.y + C1 * a2.y);
-    float2 q1 = make_float2(S1 * b1.x + S2 * b2.x, S1 * b1.y + S2 * b2.y);
-    float2 q2 = make_float2(S2 * b1.x - S1 * b2.x, S2 * b1.y - S1 * b2.y);
+    double2 a1 = cadd(z[1], z[4]), a2 = cadd(z[2], z[3]);
+    double2 b1 = csub(z[1], z[4]), b2 = csub(z[2], z[3]);
+    double2 Y[5];
+    Y[0] = make_double2(z[0].x + a1.x + a2.x, z[0].y + a1.y + a2.y);
+    double2 p1 = make_double2(z[0].x + C1 * a1.x + C2 * a2.x, z[0].y + C1 * a1.y + C2 * a2.y);
+    double2 p2 = make_double2(z[0].x + C2 * a1.x + C1 * a2.x, z[0].y + C2 * a1.y + C1 * a2.y);
+    double2 q1 = make_double2(S1 * b1.x + S2 * b2.x, S1 * b1.y + S2 * b2.y);
+    double2 q2 = make_double2(S2 * b1.x - S1 * b2.x, S2 * b1.y - S1 * b2.y);
     // -i*q = (q.y, -q.x)
-    Y[1] = make_float2(p1.x + q1.y, p1.y - q1.x);
-    Y[4] = make_float2(p1.x - q1.y, p1.y + q1.x);
-    Y[2] = make_float2(p2.x + q2.y, p2.y - q2.x);
-    Y[3] = make_float2(p2.x - q2.y, p2.y + q2.x);
+    Y[1] = make_double2(p1.x + q1.y, p1.y - q1.x);
+    Y[4] = make_double2(p1.x - q1.y, p1.y + q1.x);
+    Y[2] = make_double2(p2.x + q2.y, p2.y - q2.x);
+    Y[3] = make_double2(p2.x - q2.y, p2.y + q2.x);
 #pragma unroll
     for (int k1 = 1; k1 < 5; ++k1) Y[k1] = cmul(Y[k1], tw160[k1]);
     // five interleaved 32-point DIF FFTs across the lanes
@@ -203,12 +207,12 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
       const bool upper = (lane & half) != 0;
 #pragma unroll
       for (int k1 = 0; k1 < 5; ++k1) {
-        float px = __shfl_xor_sync(0xffffffffu, Y[k1].x, half);
-        float py = __shfl_xor_sync(0xffffffffu, Y[k1].y, half);
+        double px = __shfl_xor_sync(0xffffffffu, Y[k1].x, half);
+        double py = __shfl_xor_sync(0xffffffffu, Y[k1].y, half);
         if (!upper) {
-          Y[k1] = make_float2(Y[k1].x + px, Y[k1].y + py);
+          Y[k1] = make_double2(Y[k1].x + px, Y[k1].y + py);
         } else {
-          float2 d = make_float2(px - Y[k1].x, py - Y[k1].y);
+          double2 d = make_double2(px - Y[k1].x, py - Y[k1].y);
           Y[k1] = (st < 4) ? cmul(d, tw32[st < 4 ? st : 0]) : d;
         }
       }
@@ -223,16 +227,16 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
     for (int j = 0; j < 6; ++j) {
       int k = lane + 32 * j;
       if (k <= 160) {
-        float2 zk = sm.z[warp][k == 160 ? 0 : k];
-        float2 zn = sm.z[warp][k == 0 || k == 160 ? 0 : 160 - k];
+        double2 zk = sm.z[warp][k == 160 ? 0 : k];
+        double2 zn = sm.z[warp][k == 0 || k == 160 ? 0 : 160 - k];
         zn.y = -zn.y;
-        float2 e = make_float2(zk.x + zn.x, zk.y + zn.y);
-        float2 o = make_float2(zk.x - zn.x, zk.y - zn.y);
-        float2 wo = cmul(sm.tw320[k], o);
-        // -i*wo = (wo.y, -wo.x)
-        float re = 0.5f * (e.x + wo.y);
-        float im = 0.5f * (e.y - wo.x);
-        float mag = sqrtf(re * re + im * im);
+        double2 e = cadd(zk, zn);
+        double2 o = csub(zk, zn);
+        double2 wo = cmul(sm.tw320[k], o);
+        // -i*wo = (wo.y, -wo.x); complex64 storage of D upstream -> round the parts to fp32
+        float re = (float)(0.5 * (e.x + wo.y));
+        float im = (float)(0.5 * (e.y - wo.x));
+        float mag = (float)sqrt((double)re * (double)re + (double)im * (double)im);
         float v = log1pf(mag);
         if (MODE != MODE_NORM) {
           dsum += (double)v;

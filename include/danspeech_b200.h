@@ -126,6 +126,13 @@ int dsb_forward(dsb_model* m, const float* spect, const int32_t* lengths, int B,
                 float* probs, int32_t* out_lengths, int32_t* argmax,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* Tensor-core GEMM building block of the model path (also exported for diagnostics and tests):
+ * C[M,N] (f32, row stride ldc) = A[M,K] (bf16, row stride lda) * W[N,K]^T (bf16, row stride ldw) + bias[N].
+ * lda/ldw must be multiples of 8 elements and the operands 16-byte aligned (TMA requirements).
+ * This is the BatchRNN input projection (the x_t*W_ih^T half of nn.GRU/LSTM/RNN, model.py:107-108). */
+int dsb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* C,
+                  int64_t ldc, int M, int N, int K, void* stream);
+
 /* Streaming (model.py:517-537 and the *Stream modules): S lock-step streams. */
 typedef struct dsb_stream_state dsb_stream_state;
 int dsb_stream_state_create(dsb_model* m, int n_streams, int max_chunk_frames, dsb_stream_state** out);

@@ -1,15 +1,19 @@
 #!/bin/bash
-# One gpurun session: parity tests, bench, launch list.  Every leg has its own timeout and log.
+# One gpurun session: parity tests, kernel tests, bench, launch list.  Every leg has its own timeout and log.
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-echo "== pytest" ; timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest.log
-tail -15 gpurun_out/pytest.log
-echo "== bench" ; timeout 600 python bench.py --steps ${BENCH_STEPS:-2} --warmup 3 --precision ${PRECISION:-fp32} > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
+echo "== pytest parity" ; timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py -q -m gpu ${PYTEST_ARGS:-} > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest.log
+grep -E "passed|failed|Error|error" gpurun_out/pytest.log | tail -15
+echo "== pytest kernels" ; timeout -s KILL 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu > gpurun_out/pytest_kernels.log 2>&1; echo "pytest kernels rc=$?" | tee -a gpurun_out/pytest_kernels.log
+grep -E "passed|failed|Error|error|assert" gpurun_out/pytest_kernels.log | tail -15
+if [ "${BENCH:-1}" = "1" ]; then
+echo "== bench" ; timeout -s KILL 900 python bench.py --steps ${BENCH_STEPS:-2} --warmup 3 --precision ${PRECISION:-fp32} > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
+fi
 if [ "${NCU:-1}" = "1" ]; then
   echo "== ncu launch list"
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-400} --csv --log-file gpurun_out/launches.csv \
+  timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-400} --csv --log-file gpurun_out/launches.csv \
      python scripts/ncu_target.py > gpurun_out/ncu_target.log 2>&1; echo "ncu rc=$?"
   tail -3 gpurun_out/ncu_target.log
 fi

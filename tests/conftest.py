@@ -25,6 +25,18 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def logit_rel_err(p, ref, floor=1e-20):
+    """Relative error in the logit domain: log-probabilities are the logits up to one additive constant
+    per row, so max|log p - log ref| / (spread of the reference log-probabilities) is the "logits within
+    1e-4 relative" bar of the north star.  Entries whose reference probability underflows are skipped."""
+    p = np.asarray(p, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    m = (ref > floor) & (p > 0)
+    assert m.mean() > 0.3
+    lp, lr = np.log(p[m]), np.log(ref[m])
+    return float(np.abs(lp - lr).max() / np.abs(lr).max())
+
+
 BATCH_CASES = [
     ("gru_bi_c2", "TestModel", dict(rnn_type="gru", rnn_hidden_size=96, rnn_layers=3)),
     ("gru_bi_c3", "DanSpeechPrimary", dict(rnn_type="gru", rnn_hidden_size=80, rnn_layers=2)),
