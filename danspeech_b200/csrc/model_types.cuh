@@ -26,8 +26,13 @@ struct RnnLayer {
   float* b_ih = nullptr;   // [dirs*gates*H]
   float* w_hh = nullptr;   // [dirs][gates*H][H]
   float* b_hh = nullptr;   // [dirs][gates*H]
-  __nv_bfloat16* w_ih_tc = nullptr;   // bf16 copy of w_ih
-  __nv_bfloat16* w_hh_tc = nullptr;   // bf16 copy of w_hh
+  // bf16 tensor-core path
+  __nv_bfloat16* w_ih_tc = nullptr;   // [dirs*gates*H, in_ld] bf16 copy of w_ih
+  int in_ld = 0;                      // row stride of w_ih_tc / of the activation operand (multiple of 8)
+  float* b_ih_tc = nullptr;           // b_ih + b_hh for every gate except the GRU n-gate
+  float* b_hn = nullptr;              // [dirs][H] GRU n-gate hidden bias
+  __nv_bfloat16* w_hh_pack = nullptr; // per-CTA W_hh slices for the persistent recurrence (rnn_tc.cu)
+  bool tc_recurrence = false;
 };
 
 struct HostTensor {
@@ -64,6 +69,14 @@ int lookahead_htanh_f32(const float* x, const float* w, float* y, int T, int B, 
 int softmax_argmax_f32(const float* logits, float* probs, int32_t* argmax, int T, int B, int C, cudaStream_t st);
 
 // ---- bf16 tensor-core path (tcgen05 / TMEM / TMA) ----
+int gemm_bias_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
+                 float* C, int64_t ldc, int M, int N, int K, cudaStream_t st);
+bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* launches_out);
+int pack_whh_tc(const RnnLayer& L, __nv_bfloat16* out, cudaStream_t st);
+int combine_dirs_tc(const float* y, int dirs, int T, int B, int H, const int32_t* d_len, __nv_bfloat16* xb, int ldx,
+                    float* xf, cudaStream_t st);
+int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
+                 __nv_bfloat16* hbuf, unsigned int* sync_words, cudaStream_t st);
 int finalize_tc(dsb_model* m, cudaStream_t st);
 size_t forward_tc_workspace_bytes(const dsb_model* m, int B, int T);
 int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B, int T, float* probs,

@@ -1,0 +1,380 @@
+// Persistent tensor-core recurrence for BatchRNN (GRU / LSTM / tanh-RNN) on sm_100a.
+//
+// Replaces the sequential half of torch.nn.GRU/LSTM/RNN inside BatchRNN.forward
+// (danspeech/deepspeech/model.py:114-122) with packed-sequence semantics: sequence b runs
+// t = 0..len_b-1 forwards and len_b-1..0 backwards from its own end; both directions run
+// concurrently in one cooperative launch.
+//
+// Decomposition: a CTA owns U hidden units of ONE direction (all gates: N = 64 rows of W_hh) for
+// the whole layer.  Its W_hh slice (bf16, K padded to a multiple of 64) is loaded ONCE by TMA into
+// 128B-swizzled shared memory and stays resident for all T steps.  Per step:
+//   producer warp : waits for the direction-wide step barrier, then TMA-streams h_{t-1} (bf16,
+//                   [B, H]) through a 3-stage mbarrier ring in K-chunks of 64,
+//   MMA warp      : tcgen05.mma  D[batch(128 lanes), 64 gate columns] += h_chunk * W_chunk^T, fp32 in TMEM,
+//   8 epilogue warps: prefetch the input-projection pre-activations of the step while the MMAs run,
+//                   tcgen05.ld the accumulators, apply the gate non-linearities with the fp32 hidden
+//                   state kept in registers, store h_t (bf16, for the next step's MMA) and y_t (fp32),
+//                   then arrive on the direction-wide barrier (one atomicAdd per CTA per step).
+// The step is latency-bound (grid barrier + L2 round trips), not tensor-bound: algorithmic work is
+// 2*B*3H*H flop per step per direction and is reported against the tensor roof.
+//
+// Every wait is bounded: a stuck barrier sets an abort flag instead of hanging the GPU.
+#include "tc_common.cuh"
+#include "model_types.cuh"
+
+namespace dsb {
+namespace tc {
+
+constexpr int RT_STAGES = 3;
+constexpr int RT_BK = 64;
+constexpr int RT_N = 64;                       // W_hh rows per CTA = 2 halves x 32 columns
+constexpr int RT_A_BYTES = 128 * RT_BK * 2;    // A stage (128 MMA rows x 64 k), only BP rows are loaded
+constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk
+constexpr int RT_THREADS = 64 + 256;
+constexpr long long RT_TIMEOUT_CYCLES = 4000000000LL;
+
+struct RnnTcParams {
+  const float* gx;          // [T*B][dirs*G*H]
+  const float* b_hn;        // [dirs][H] GRU n-gate hidden bias (else nullptr)
+  float* y;                 // [dirs][T][B][H]
+  __nv_bfloat16* hbuf;      // [2][dirs][BP][HP]
+  const int32_t* lens;      // [B]
+  unsigned int* counters;   // [dirs]
+  int* abort_flag;
+  int B, H, HP, BP, T, Tmax;
+  int dirs;   // directions in gx / y / hbuf / counters
+  int dir0;   // first direction handled by this launch
+  int cpd;    // CTAs per direction
+  int U;      // hidden units per CTA (2 * units per half)
+  int nkc;    // K chunks of 64 (HP / 64)
+};
+
+__device__ __forceinline__ bool wait_abortable(uint64_t* bar, uint32_t parity, int* abort_flag) {
+  long long t0 = 0;
+  unsigned n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++n & 0xFF) == 0) {
+      if (*(volatile int*)abort_flag) return false;
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > RT_TIMEOUT_CYCLES) {
+        atomicExch(abort_flag, 1);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ bool bar_red_and(bool pred, int id, int nthreads) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %1, 0;\n\t"
+      "barrier.cta.red.and.pred p, %2, %3, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"((uint32_t)pred), "r"(id), "r"(nthreads)
+      : "memory");
+  return r != 0;
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int GATES>
+__global__ void __launch_bounds__(RT_THREADS, 1)
+rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
+              const RnnTcParams p) {
+  constexpr int UH = 32 / GATES;   // units per 32-column half
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sW = smem;
+  unsigned char* sA = smem + (size_t)p.nkc * RT_W_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + RT_STAGES * RT_A_BYTES);
+  uint64_t* empty = full + RT_STAGES;
+  uint64_t* wbar = empty + RT_STAGES;
+  uint64_t* dfull = wbar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dir_local = blockIdx.x / p.cpd;
+  const int dir = p.dir0 + dir_local;
+  const int c = blockIdx.x % p.cpd;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_h);
+    for (int i = 0; i < RT_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(wbar, 1);
+    mbar_init(dfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<64>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident W_hh slice, loaded once
+      mbar_arrive_expect_tx(wbar, (uint32_t)p.nkc * RT_W_BYTES);
+      for (int kc = 0; kc < p.nkc; ++kc)
+        tma_load_2d(sW + (size_t)kc * RT_W_BYTES, &tmap_w, wbar, kc * RT_BK, (dir * p.cpd + c) * RT_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      volatile unsigned int* ctr = p.counters + dir;
+      for (int s = 0; s < p.Tmax && ok; ++s) {
+        if (s > 0) {
+          // direction-wide barrier: every CTA of this direction has published h_{s-1}
+          const unsigned target = (unsigned)p.cpd * (unsigned)s;
+          long long t0 = 0;
+          unsigned n = 0;
+          while (*ctr < target) {
+            if ((++n & 0x3F) == 0) {
+              if (*(volatile int*)p.abort_flag) { ok = false; break; }
+              long long now = clock64();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > RT_TIMEOUT_CYCLES) { atomicExch(p.abort_flag, 1); ok = false; break; }
+            }
+          }
+          if (!ok) break;
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
+        }
+        const int row0 = ((s & 1) * p.dirs + dir) * p.BP;
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          if (!wait_abortable(&empty[stage], phase ^ 1, p.abort_flag)) { ok = false; break; }
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)p.BP * RT_BK * 2);
+          tma_load_2d(sA + stage * RT_A_BYTES, &tmap_h, &full[stage], kc * RT_BK, row0);
+          if (++stage == RT_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, RT_N);
+      bool ok = wait_abortable(wbar, 0, p.abort_flag);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < p.Tmax && ok; ++s) {
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          if (!wait_abortable(&full[stage], phase, p.abort_flag)) { ok = false; break; }
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * RT_A_BYTES), 16, 1024, 2);
+          const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)kc * RT_W_BYTES), 16, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < RT_BK / 16; ++k)
+            umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == RT_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (ok) umma_commit(dfull);
+      }
+    }
+  } else {
+    const int q = warp & 3;              // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;    // which 32-column half
+    const int b = q * 32 + lane;
+    const bool row_ok = b < p.B;
+    const int len = row_ok ? p.lens[b] : 0;
+    const int j0 = c * p.U + half * UH;
+    const int ncol = p.dirs * GATES * p.H;
+    float hprev[UH], cst[UH], bhn[UH];
+#pragma unroll
+    for (int u = 0; u < UH; ++u) {
+      hprev[u] = 0.f;
+      cst[u] = 0.f;
+      bhn[u] = (GATES == 3 && p.b_hn && j0 + u < p.H) ? p.b_hn[(size_t)dir * p.H + j0 + u] : 0.f;
+    }
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+    for (int s = 0; s < p.Tmax; ++s) {
+      const bool active = row_ok && s < len;
+      const int t = dir == 0 ? s : len - 1 - s;
+      float gxv[GATES][UH];
+      if (active) {
+        const float* gp = p.gx + ((size_t)t * p.B + b) * ncol + (size_t)dir * GATES * p.H + j0;
+#pragma unroll
+        for (int g = 0; g < GATES; ++g)
+#pragma unroll
+          for (int u = 0; u < UH; ++u) gxv[g][u] = (j0 + u < p.H) ? __ldg(gp + (size_t)g * p.H + u) : 0.f;
+      }
+      const bool ok = wait_abortable(dfull, (uint32_t)(s & 1), p.abort_flag);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(t_addr, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (ok && active) {
+        float* yo = p.y + (((size_t)dir * p.T + t) * p.B + b) * p.H + j0;
+        __nv_bfloat16* ho = p.hbuf + ((size_t)(((s + 1) & 1) * p.dirs + dir) * p.BP + b) * p.HP + j0;
+#pragma unroll
+        for (int u = 0; u < UH; ++u) {
+          if (j0 + u < p.H) {
+            float hn;
+            if (GATES == 3) {
+              const float rg = fast_sigmoid(gxv[0][u] + __uint_as_float(r[u * GATES + 0]));
+              const float zg = fast_sigmoid(gxv[1 % GATES][u] + __uint_as_float(r[u * GATES + (1 % GATES)]));
+              const float ng = fast_tanh(gxv[2 % GATES][u] + rg * (__uint_as_float(r[u * GATES + (2 % GATES)]) + bhn[u]));
+              hn = (1.0f - zg) * ng + zg * hprev[u];
+            } else if (GATES == 4) {
+              const float ig = fast_sigmoid(gxv[0][u] + __uint_as_float(r[u * GATES + 0]));
+              const float fg = fast_sigmoid(gxv[1 % GATES][u] + __uint_as_float(r[u * GATES + (1 % GATES)]));
+              const float gg = fast_tanh(gxv[2 % GATES][u] + __uint_as_float(r[u * GATES + (2 % GATES)]));
+              const float og = fast_sigmoid(gxv[3 % GATES][u] + __uint_as_float(r[u * GATES + (3 % GATES)]));
+              cst[u] = fg * cst[u] + ig * gg;
+              hn = og * fast_tanh(cst[u]);
+            } else {
+              hn = fast_tanh(gxv[0][u] + __uint_as_float(r[u]));
+            }
+            hprev[u] = hn;
+            yo[u] = hn;
+            ho[u] = __float2bfloat16_rn(hn);
+          }
+        }
+      }
+      const bool all_ok = bar_red_and(ok, 1, 256);
+      if (!all_ok) break;
+      if (threadIdx.x == 64) {
+        __threadfence();
+        atomicAdd(p.counters + dir, 1u);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<64>(tmem_base);
+  }
+}
+
+
+// W_hh [dirs][G*H][H] fp32 -> per-CTA slices [dirs][cpd][64 rows][HP] bf16.  Row n of a slice:
+// half = n/32, r = n%32, u = r/G, g = r%G  <->  W_hh[g*H + c*U + half*UH + u][:]  (zero rows/cols beyond H).
+__global__ void pack_whh_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int dirs, int cpd,
+                                int G, int H, int HP, int U) {
+  const int UH = 32 / G;
+  const int64_t total = (int64_t)dirs * cpd * RT_N * HP;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % HP);
+    int64_t rr = i / HP;
+    const int n = (int)(rr % RT_N);
+    rr /= RT_N;
+    const int c = (int)(rr % cpd);
+    const int d = (int)(rr / cpd);
+    const int half = n / 32, r = n % 32, u = r / G, g = r % G;
+    const int j = c * U + half * UH + u;
+    float v = 0.f;
+    if (u < UH && j < H && k < H) v = w[((int64_t)d * G * H + (int64_t)g * H + j) * H + k];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// next-layer operand: x[t*B+b][j] = bf16(y_fwd + y_bwd) for t < len_b, else 0; optional fp32 copy
+__global__ void combine_dirs_kernel(const float* __restrict__ y, int dirs, int T, int B, int H,
+                                    const int32_t* __restrict__ lens, __nv_bfloat16* __restrict__ xb, int ldx,
+                                    float* __restrict__ xf) {
+  const int64_t total = (int64_t)T * B * H;
+  const int64_t dstride = total;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % H);
+    const int64_t tb = i / H;
+    const int b = (int)(tb % B), t = (int)(tb / B);
+    float v = 0.f;
+    if (t < lens[b]) {
+      v = y[i];
+      if (dirs == 2) v += y[i + dstride];
+    }
+    if (xb) xb[tb * ldx + j] = __float2bfloat16_rn(v);
+    if (xf) xf[i] = v;
+  }
+}
+
+}  // namespace tc
+
+bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* launches_out) {
+  const int UH = 32 / L.gates, U = 2 * UH;
+  const int cpd = cdiv(L.H, U);
+  const int HP = (L.H + 63) / 64 * 64;
+  const size_t smem = (size_t)(HP / 64) * tc::RT_W_BYTES + tc::RT_STAGES * tc::RT_A_BYTES + 256 + 1024;
+  if (B > 128 || smem > 227 * 1024 || cpd > sms) return false;
+  if (cpd_out) *cpd_out = cpd;
+  if (launches_out) *launches_out = (L.dirs * cpd <= sms) ? 1 : L.dirs;
+  return true;
+}
+
+int pack_whh_tc(const RnnLayer& L, __nv_bfloat16* out, cudaStream_t st) {
+  const int U = 2 * (32 / L.gates), cpd = cdiv(L.H, U), HP = (L.H + 63) / 64 * 64;
+  const int64_t total = (int64_t)L.dirs * cpd * tc::RT_N * HP;
+  tc::pack_whh_kernel<<<(int)(cdiv64(total, 256) < 2048 ? cdiv64(total, 256) : 2048), 256, 0, st>>>(
+      L.w_hh, out, L.dirs, cpd, L.gates, L.H, HP, U);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
+int combine_dirs_tc(const float* y, int dirs, int T, int B, int H, const int32_t* d_len, __nv_bfloat16* xb, int ldx,
+                    float* xf, cudaStream_t st) {
+  const int64_t total = (int64_t)T * B * H;
+  tc::combine_dirs_kernel<<<(int)(cdiv64(total, 256) < 148 * 16 ? cdiv64(total, 256) : 148 * 16), 256, 0, st>>>(
+      y, dirs, T, B, H, d_len, xb, ldx, xf);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
+// One BatchRNN layer.  gx [T*B][dirs*G*H] fp32, y [dirs][T][B][H] fp32 (rows t >= len_b are NOT written),
+// hbuf [2][dirs][BP][HP] bf16, sync = {counters[dirs] u32, abort i32} (device).
+int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
+                 __nv_bfloat16* hbuf, unsigned int* sync_words, cudaStream_t st) {
+  using namespace tc;
+  int dev = 0, sms = 148, cpd = 0, launches = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (!rnn_tc_supported(L, B, sms, &cpd, &launches))
+    return set_error(DSB_ERR_UNSUPPORTED, "rnn_layer_tc: shape H=%d B=%d not supported", L.H, B);
+  const int HP = (L.H + 63) / 64 * 64, BP = B <= 64 ? 64 : 128, nkc = HP / 64;
+  DSB_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(__nv_bfloat16) * 2 * (size_t)L.dirs * BP * HP, st));
+  DSB_CUDA(cudaMemsetAsync(sync_words, 0, sizeof(unsigned int) * 2, st));   // step counters only; abort flag is sticky
+
+  CUtensorMap tw, th;
+  uint64_t dw[2] = {(uint64_t)HP, (uint64_t)L.dirs * cpd * RT_N}, sw[2] = {2, (uint64_t)HP * 2};
+  uint32_t bw[2] = {RT_BK, RT_N};
+  if (int e = make_tmap_bf16(&tw, L.w_hh_pack, 2, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  uint64_t dh[2] = {(uint64_t)HP, (uint64_t)2 * L.dirs * BP}, sh[2] = {2, (uint64_t)HP * 2};
+  uint32_t bh[2] = {RT_BK, (uint32_t)BP};
+  if (int e = make_tmap_bf16(&th, hbuf, 2, dh, sh, bh, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+
+  RnnTcParams p{};
+  p.gx = gx;
+  p.b_hn = L.b_hn;
+  p.y = y;
+  p.hbuf = hbuf;
+  p.lens = d_len;
+  p.counters = sync_words;
+  p.abort_flag = reinterpret_cast<int*>(sync_words + 2);
+  p.B = B; p.H = L.H; p.HP = HP; p.BP = BP; p.T = T; p.Tmax = Tmax;
+  p.dirs = L.dirs; p.cpd = cpd; p.U = 2 * (32 / L.gates); p.nkc = nkc;
+  const size_t smem = (size_t)nkc * RT_W_BYTES + RT_STAGES * RT_A_BYTES + 256 + 1024;
+  const void* fn = L.gates == 3 ? (const void*)rnn_tc_kernel<3>
+                   : L.gates == 4 ? (const void*)rnn_tc_kernel<4> : (const void*)rnn_tc_kernel<1>;
+  DSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int dirs_per_launch = L.dirs / launches;
+  for (int l = 0; l < launches; ++l) {
+    p.dir0 = l * dirs_per_launch;
+    void* args[] = {(void*)&tw, (void*)&th, (void*)&p};
+    DSB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(dirs_per_launch * cpd), dim3(RT_THREADS), args, smem, st));
+    count_launch();
+  }
+  return 0;
+}
+
+}  // namespace dsb

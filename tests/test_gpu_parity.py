@@ -165,3 +165,55 @@ def test_recognizer_config1_end_to_end(golden):
     assert text == str(golden["cfg1_text"])
     batch = r.recognize_batch([golden["wav_u0042018"].astype(np.float64), golden["wav_u0013002"].astype(np.float64)])
     assert batch[1] == text
+
+
+# ------------------------------------------------------------------ acoustic model, bf16 tensor-core mode
+BF16_TOL = 2e-2       # north star: logits within 2e-2 relative in bf16 mode
+
+
+def test_forward_bf16_config1_matches_golden(golden):
+    m = _model("TestModel", {}, seed=0, precision="bf16")
+    sp = torch.from_numpy(golden["spect_u0013002"]).cuda()
+    probs, sizes = m(sp.view(1, 1, 161, -1), torch.IntTensor([sp.size(1)]))
+    assert sizes.tolist() == golden["cfg1_sizes"].tolist()
+    assert logit_rel_err(probs.cpu().numpy(), golden["cfg1_probs"]) < BF16_TOL
+
+
+@pytest.mark.parametrize("tag,name,kw", BATCH_CASES, ids=[c[0] for c in BATCH_CASES])
+def test_forward_bf16_ragged_batch_matches_golden(golden, tag, name, kw):
+    m = _model(name, kw, seed=3, precision="bf16")
+    _, x, xl = batch_inputs()
+    probs, sizes = m(x.cuda(), xl)
+    ref = golden["batch_%s_probs" % tag]
+    assert sizes.tolist() == golden["batch_%s_sizes" % tag].tolist()
+    for b, L in enumerate(sizes.tolist()):
+        assert logit_rel_err(probs[b, :L].cpu().numpy(), ref[b, :L]) < BF16_TOL
+
+
+def test_primary_shape_bf16_vs_fp32_and_oracle():
+    """DanSpeechPrimary-shaped weights (3 conv, 9 x 1200 bi-GRU), small ragged batch: fp32 mode vs the CPU
+    oracle (1e-4), bf16 mode vs fp32 mode (2e-2), greedy transcripts of fp32 mode bit-exact vs the oracle."""
+    from danspeech_b200.deepspeech.decoder import GreedyDecoder
+    from danspeech_b200.audio.parsers import SpectrogramAudioParser
+    lens = [48000, 40000, 16000, 8000]
+    auds = [syn.synthetic_audio(n, seed=50 + i) for i, n in enumerate(lens)]
+    x, xl = SpectrogramAudioParser().parse_batch(auds)
+    m = _model("DanSpeechPrimary", {}, seed=0, precision="fp32")
+    p32, sizes = m(x, xl)
+    cfg = case_config("DanSpeechPrimary", {})
+    sd = syn.make_state_dict(seed=0, **cfg)
+    ref, rs = om.forward(sd, x.cpu(), xl, cfg["conv_layers"], cfg["rnn_layers"])
+    assert sizes.tolist() == rs.tolist()
+    dec = GreedyDecoder(syn.LABELS, blank_index=0)
+    ref_text = og.greedy_decode(ref.numpy(), rs.numpy())[0]
+    for b, L in enumerate(sizes.tolist()):
+        assert logit_rel_err(p32[b, :L].cpu().numpy(), ref[b, :L].numpy()) < FP32_TOL
+    assert dec.decode(p32, sizes)[0] == ref_text
+    m.set_precision("bf16")
+    p16, s16 = m(x, xl)
+    assert s16.tolist() == sizes.tolist()
+    for b, L in enumerate(sizes.tolist()):
+        assert logit_rel_err(p16[b, :L].cpu().numpy(), ref[b, :L].numpy()) < BF16_TOL
+    got = dec.decode(p16, s16)[0]
+    same = sum(int(a == b) for a, b in zip(got, ref_text))
+    print("bf16 greedy transcripts identical to the oracle: %d / %d" % (same, len(ref_text)))
