@@ -25,11 +25,17 @@
 namespace dsb {
 namespace tc {
 
-constexpr int RT_STAGES = 3;
 constexpr int RT_BK = 64;
 constexpr int RT_N = 64;                       // W_hh rows per CTA = 2 halves x 32 columns
-constexpr int RT_A_BYTES = 128 * RT_BK * 2;    // A stage (128 MMA rows x 64 k), only BP rows are loaded
 constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk
+// A (h) ring: the MMA is M=128 but only BP batch rows carry data.  For BP = 64 the stages are spaced
+// 8 KB apart, so the unused upper 64 rows of a stage alias the next stage (their products land in TMEM
+// lanes 64..127, which nobody reads); one spare 8 KB slot keeps the last stage's upper half in bounds.
+// 8 stages x 8 KB keep ~64 KB of h in flight per SM, which is what hides the L2 latency of the step.
+__host__ __device__ constexpr int rt_stages(int BP) { return BP == 64 ? 8 : 4; }
+__host__ __device__ constexpr int rt_stage_bytes(int BP) { return BP * RT_BK * 2; }
+__host__ __device__ constexpr int rt_ring_bytes(int BP) { return BP == 64 ? 9 * 8192 : 4 * 16384; }
+constexpr int RT_MAX_STAGES = 8;
 constexpr int RT_THREADS = 64 + 256;
 constexpr long long RT_TIMEOUT_CYCLES = 4000000000LL;
 
@@ -80,11 +86,9 @@ __device__ __forceinline__ bool bar_red_and(bool pred, int id, int nthreads) {
 }
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
+// tanh.approx.f32 is only good to ~5e-4 absolute, which is visible after 9 recurrent layers; the
+// exp-based form below is accurate to ~1e-6 and still a handful of instructions.
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
 template <int GATES>
 __global__ void __launch_bounds__(RT_THREADS, 1)
@@ -95,9 +99,11 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* sW = smem;
   unsigned char* sA = smem + (size_t)p.nkc * RT_W_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sA + RT_STAGES * RT_A_BYTES);
-  uint64_t* empty = full + RT_STAGES;
-  uint64_t* wbar = empty + RT_STAGES;
+  const int RT_STAGES = rt_stages(p.BP);
+  const int RT_A_BYTES = rt_stage_bytes(p.BP);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + rt_ring_bytes(p.BP));
+  uint64_t* empty = full + RT_MAX_STAGES;
+  uint64_t* wbar = empty + RT_MAX_STAGES;
   uint64_t* dfull = wbar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
 
@@ -306,7 +312,7 @@ bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* laun
   const int UH = 32 / L.gates, U = 2 * UH;
   const int cpd = cdiv(L.H, U);
   const int HP = (L.H + 63) / 64 * 64;
-  const size_t smem = (size_t)(HP / 64) * tc::RT_W_BYTES + tc::RT_STAGES * tc::RT_A_BYTES + 256 + 1024;
+  const size_t smem = (size_t)(HP / 64) * tc::RT_W_BYTES + tc::rt_ring_bytes(B <= 64 ? 64 : 128) + 256 + 1024;
   if (B > 128 || smem > 227 * 1024 || cpd > sms) return false;
   if (cpd_out) *cpd_out = cpd;
   if (launches_out) *launches_out = (L.dirs * cpd <= sms) ? 1 : L.dirs;
@@ -363,7 +369,7 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.abort_flag = reinterpret_cast<int*>(sync_words + 2);
   p.B = B; p.H = L.H; p.HP = HP; p.BP = BP; p.T = T; p.Tmax = Tmax;
   p.dirs = L.dirs; p.cpd = cpd; p.U = 2 * (32 / L.gates); p.nkc = nkc;
-  const size_t smem = (size_t)nkc * RT_W_BYTES + RT_STAGES * RT_A_BYTES + 256 + 1024;
+  const size_t smem = (size_t)nkc * RT_W_BYTES + rt_ring_bytes(BP) + 256 + 1024;
   const void* fn = L.gates == 3 ? (const void*)rnn_tc_kernel<3>
                    : L.gates == 4 ? (const void*)rnn_tc_kernel<4> : (const void*)rnn_tc_kernel<1>;
   DSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

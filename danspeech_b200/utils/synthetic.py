@@ -43,8 +43,8 @@ def _bn(rng, n, prefix, sd):
 
 
 def make_state_dict(conv_layers=2, rnn_layers=5, rnn_hidden_size=400, bidirectional=True, rnn_type="gru", context=20,
-                    streaming_inference_model=False, num_classes=len(LABELS), seed=0, fc_scale=20.0,
-                    ih_scale=8.0):
+                    streaming_inference_model=False, num_classes=len(LABELS), seed=0, fc_scale=10.0,
+                    ih_scale=4.0):
     """State dict with the reference's names and shapes, float32 torch tensors."""
     rng = np.random.default_rng(seed)
     sd = OrderedDict()
@@ -68,8 +68,9 @@ def make_state_dict(conv_layers=2, rnn_layers=5, rnn_hidden_size=400, bidirectio
             _bn(rng, isz, "rnns.%d.batch_norm.module" % l, sd)
         for d in range(dirs):
             sfx = "_reverse" if d == 1 else ""
-            # strong input drive: a random GRU stack otherwise forgets its input and the argmax path
-            # degenerates to one symbol (nothing to decode)
+            # input drive x4: a random GRU stack otherwise forgets its input and the argmax path degenerates
+            # to one symbol (nothing to decode); much larger gains make the random network chaotic, so that
+            # bf16 rounding alone (emulated on the CPU) already exceeds the 2e-2 bar
             sd["rnns.%d.rnn.weight_ih_l0%s" % (l, sfx)] = rng.uniform(-bound, bound, (G * H, isz)) * ih_scale
             sd["rnns.%d.rnn.weight_hh_l0%s" % (l, sfx)] = rng.uniform(-bound, bound, (G * H, H))
             sd["rnns.%d.rnn.bias_ih_l0%s" % (l, sfx)] = rng.uniform(-bound, bound, G * H)
