@@ -21,23 +21,40 @@
 // Every wait is bounded: a stuck barrier sets an abort flag instead of hanging the GPU.
 #include "tc_common.cuh"
 #include "model_types.cuh"
+#include <cstdlib>
 
 namespace dsb {
 namespace tc {
 
 constexpr int RT_BK = 64;
 constexpr int RT_N = 64;                       // W_hh rows per CTA = 2 halves x 32 columns
-constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk
-// A (h) ring: the MMA is M=128 but only BP batch rows carry data.  For BP = 64 the stages are spaced
-// 8 KB apart, so the unused upper 64 rows of a stage alias the next stage (their products land in TMEM
-// lanes 64..127, which nobody reads); one spare 8 KB slot keeps the last stage's upper half in bounds.
-// 8 stages x 8 KB keep ~64 KB of h in flight per SM, which is what hides the L2 latency of the step.
-__host__ __device__ constexpr int rt_stages(int BP) { return BP == 64 ? 8 : 4; }
-__host__ __device__ constexpr int rt_stage_bytes(int BP) { return BP * RT_BK * 2; }
-__host__ __device__ constexpr int rt_ring_bytes(int BP) { return BP == 64 ? 9 * 8192 : 4 * 16384; }
+constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk (8 KB)
 constexpr int RT_MAX_STAGES = 8;
 constexpr int RT_THREADS = 64 + 256;
 constexpr long long RT_TIMEOUT_CYCLES = 4000000000LL;
+constexpr int RT_SMEM_LIMIT = 227 * 1024;
+
+// Shared-memory plan: [W slice: nkc x 8 KB][h ring: stages x BP*128 B][store staging][barriers].
+// The MMA is M = BP (64 or 128 batch rows): with M = 64 only the 64 valid rows are read from shared
+// memory, which matters because the SS-mode MMA is shared-memory-bandwidth bound at N = 64.
+struct RtPlan {
+  int stages, stage_bytes, stage_off, stg_off, bar_off, total;
+};
+__host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U) {
+  RtPlan pl;
+  pl.stage_bytes = BP * RT_BK * 2;
+  const int w_bytes = nkc * RT_W_BYTES;
+  const int stg = 2 * BP * U * (2 + 4);          // double-buffered h (bf16) + y (fp32) staging
+  const int stg_al = (stg + 1023) / 1024 * 1024;
+  int stages = (RT_SMEM_LIMIT - 2048 - 256 - w_bytes - stg_al) / pl.stage_bytes;   // 1 KB align slack + 1 KB static
+  if (stages > RT_MAX_STAGES) stages = RT_MAX_STAGES;
+  pl.stages = stages;
+  pl.stage_off = w_bytes;
+  pl.stg_off = w_bytes + stages * pl.stage_bytes;
+  pl.bar_off = pl.stg_off + stg_al;
+  pl.total = pl.bar_off + 256 + 1024;
+  return pl;
+}
 
 struct RnnTcParams {
   const float* gx;          // [T*B][dirs*G*H]
@@ -53,6 +70,7 @@ struct RnnTcParams {
   int cpd;    // CTAs per direction
   int U;      // hidden units per CTA (2 * units per half)
   int nkc;    // K chunks of 64 (HP / 64)
+  unsigned long long* dbg;   // optional [grid][16] cycle counters (DSB_RNN_DEBUG=1)
 };
 
 __device__ __forceinline__ bool wait_abortable(uint64_t* bar, uint32_t parity, int* abort_flag) {
@@ -84,6 +102,17 @@ __device__ __forceinline__ bool bar_red_and(bool pred, int id, int nthreads) {
       : "memory");
   return r != 0;
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // tanh.approx.f32 is only good to ~5e-4 absolute, which is visible after 9 recurrent layers; the
@@ -95,27 +124,32 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
 rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
               const RnnTcParams p) {
   constexpr int UH = 32 / GATES;   // units per 32-column half
+  constexpr int U = 2 * UH;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const RtPlan pl = rt_plan(p.nkc, p.BP, U);
   unsigned char* sW = smem;
-  unsigned char* sA = smem + (size_t)p.nkc * RT_W_BYTES;
-  const int RT_STAGES = rt_stages(p.BP);
-  const int RT_A_BYTES = rt_stage_bytes(p.BP);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sA + rt_ring_bytes(p.BP));
+  unsigned char* sA = smem + pl.stage_off;
+  unsigned char* sStg = smem + pl.stg_off;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
   uint64_t* empty = full + RT_MAX_STAGES;
   uint64_t* wbar = empty + RT_MAX_STAGES;
   uint64_t* dfull = wbar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
+  const int n_stages = pl.stages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dir_local = blockIdx.x / p.cpd;
   const int dir = p.dir0 + dir_local;
   const int c = blockIdx.x % p.cpd;
+  // every CTA walks the K chunks in its own rotation so that the 60 CTAs of a direction do not all hit
+  // the same L2 lines of h at the same instant
+  const int kc_rot = (int)(((long long)c * p.nkc) / p.cpd);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_h);
-    for (int i = 0; i < RT_STAGES; ++i) {
+    for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -138,14 +172,16 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      volatile unsigned int* ctr = p.counters + dir;
+      const unsigned* ctr = p.counters + dir;
+      unsigned long long d_spin = 0, d_fence = 0, d_issue = 0;
       for (int s = 0; s < p.Tmax && ok; ++s) {
+        long long c0 = clock64();
         if (s > 0) {
           // direction-wide barrier: every CTA of this direction has published h_{s-1}
           const unsigned target = (unsigned)p.cpd * (unsigned)s;
           long long t0 = 0;
           unsigned n = 0;
-          while (*ctr < target) {
+          while (ld_acquire_gpu(ctr) < target) {
             if ((++n & 0x3F) == 0) {
               if (*(volatile int*)p.abort_flag) { ok = false; break; }
               long long now = clock64();
@@ -154,46 +190,71 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             }
           }
           if (!ok) break;
-          __threadfence();
+          long long c1 = clock64();
           asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
+          d_spin += c1 - c0;
+          d_fence += clock64() - c1;
         }
+        long long c2 = clock64();
         const int row0 = ((s & 1) * p.dirs + dir) * p.BP;
-        for (int kc = 0; kc < p.nkc; ++kc) {
+        for (int i = 0; i < p.nkc; ++i) {
+          int kc = i + kc_rot;
+          if (kc >= p.nkc) kc -= p.nkc;
           if (!wait_abortable(&empty[stage], phase ^ 1, p.abort_flag)) { ok = false; break; }
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)p.BP * RT_BK * 2);
-          tma_load_2d(sA + stage * RT_A_BYTES, &tmap_h, &full[stage], kc * RT_BK, row0);
-          if (++stage == RT_STAGES) { stage = 0; phase ^= 1; }
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)pl.stage_bytes);
+          tma_load_2d(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0);
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
+        d_issue += clock64() - c2;
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 16 + 0] = d_spin;
+        p.dbg[blockIdx.x * 16 + 1] = d_fence;
+        p.dbg[blockIdx.x * 16 + 2] = d_issue;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, RT_N);
+      const uint32_t idesc = make_idesc_bf16(p.BP, RT_N);
       bool ok = wait_abortable(wbar, 0, p.abort_flag);
       int stage = 0;
       uint32_t phase = 0;
+      unsigned long long d_wait0 = 0, d_rest = 0;
       for (int s = 0; s < p.Tmax && ok; ++s) {
-        for (int kc = 0; kc < p.nkc; ++kc) {
+        long long m0 = clock64();
+        for (int i = 0; i < p.nkc; ++i) {
+          int kc = i + kc_rot;
+          if (kc >= p.nkc) kc -= p.nkc;
           if (!wait_abortable(&full[stage], phase, p.abort_flag)) { ok = false; break; }
+          if (i == 0) { long long m1 = clock64(); d_wait0 += m1 - m0; m0 = m1; }
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * RT_A_BYTES), 16, 1024, 2);
+          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * pl.stage_bytes), 16, 1024, 2);
           const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)kc * RT_W_BYTES), 16, 1024, 2);
 #pragma unroll
           for (int k = 0; k < RT_BK / 16; ++k)
-            umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+            umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) != 0);
           umma_commit(&empty[stage]);
-          if (++stage == RT_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         if (ok) umma_commit(dfull);
+        d_rest += clock64() - m0;
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 16 + 3] = d_wait0;
+        p.dbg[blockIdx.x * 16 + 4] = d_rest;
       }
     }
   } else {
-    const int q = warp & 3;              // TMEM lane quarter of this warp
-    const int half = (warp - 2) >> 2;    // which 32-column half
-    const int b = q * 32 + lane;
-    const bool row_ok = b < p.B;
+    // ---- epilogue: 8 warps.  TMEM lane quarter q = warp % 4 holds batch rows [q*rpq, (q+1)*rpq)
+    //      (rpq = 16 for the M = 64 MMA, 32 for M = 128); the two warps of a quarter split the columns.
+    const int et = threadIdx.x - 64;     // 0..255
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int rpq = p.BP >> 2;
+    const int b = q * rpq + lane;
+    const bool row_ok = lane < rpq && b < p.B;
     const int len = row_ok ? p.lens[b] : 0;
-    const int j0 = c * p.U + half * UH;
+    const int j0 = c * U + half * UH;
     const int ncol = p.dirs * GATES * p.H;
     float hprev[UH], cst[UH], bhn[UH];
 #pragma unroll
@@ -203,57 +264,125 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       bhn[u] = (GATES == 3 && p.b_hn && j0 + u < p.H) ? p.b_hn[(size_t)dir * p.H + j0 + u] : 0.f;
     }
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+    // store staging (double buffered by step parity): sH [2][BP][U] bf16, sY [2][BP][U] fp32, sT [2][BP] int
+    __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(sStg);
+    float* sY = reinterpret_cast<float*>(sStg + 2 * p.BP * U * 2);
+    __shared__ int sT[2][128];
+    const bool vec2 = ((p.H & 1) == 0) && ((UH & 1) == 0);
+    unsigned long long e_load = 0, e_wait = 0, e_math = 0, e_bar = 0, e_pub = 0;
     for (int s = 0; s < p.Tmax; ++s) {
+      long long e0 = clock64();
       const bool active = row_ok && s < len;
       const int t = dir == 0 ? s : len - 1 - s;
+      const int par = s & 1;
       float gxv[GATES][UH];
       if (active) {
         const float* gp = p.gx + ((size_t)t * p.B + b) * ncol + (size_t)dir * GATES * p.H + j0;
+        if (vec2 && j0 + UH <= p.H) {
 #pragma unroll
-        for (int g = 0; g < GATES; ++g)
+          for (int g = 0; g < GATES; ++g)
 #pragma unroll
-          for (int u = 0; u < UH; ++u) gxv[g][u] = (j0 + u < p.H) ? __ldg(gp + (size_t)g * p.H + u) : 0.f;
+            for (int u = 0; u < UH; u += 2) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(gp + (size_t)g * p.H + u));
+              gxv[g][u] = v.x;
+              gxv[g][u + 1 < UH ? u + 1 : u] = v.y;
+            }
+        } else {
+#pragma unroll
+          for (int g = 0; g < GATES; ++g)
+#pragma unroll
+            for (int u = 0; u < UH; ++u) gxv[g][u] = (j0 + u < p.H) ? __ldg(gp + (size_t)g * p.H + u) : 0.f;
+        }
       }
+      if (half == 0 && lane < rpq) sT[par][q * rpq + lane] = active ? t : -1;
+      long long e1 = clock64();
       const bool ok = wait_abortable(dfull, (uint32_t)(s & 1), p.abort_flag);
+      long long e2 = clock64();
       tc_fence_after();
       uint32_t r[32];
       tmem_ld32(t_addr, r);
       tmem_ld_wait();
       tc_fence_before();
       if (ok && active) {
-        float* yo = p.y + (((size_t)dir * p.T + t) * p.B + b) * p.H + j0;
-        __nv_bfloat16* ho = p.hbuf + ((size_t)(((s + 1) & 1) * p.dirs + dir) * p.BP + b) * p.HP + j0;
+        __nv_bfloat16* sh = sH + ((size_t)par * p.BP + b) * U + half * UH;
+        float* sy = sY + ((size_t)par * p.BP + b) * U + half * UH;
 #pragma unroll
         for (int u = 0; u < UH; ++u) {
-          if (j0 + u < p.H) {
-            float hn;
-            if (GATES == 3) {
-              const float rg = fast_sigmoid(gxv[0][u] + __uint_as_float(r[u * GATES + 0]));
-              const float zg = fast_sigmoid(gxv[1 % GATES][u] + __uint_as_float(r[u * GATES + (1 % GATES)]));
-              const float ng = fast_tanh(gxv[2 % GATES][u] + rg * (__uint_as_float(r[u * GATES + (2 % GATES)]) + bhn[u]));
-              hn = (1.0f - zg) * ng + zg * hprev[u];
-            } else if (GATES == 4) {
-              const float ig = fast_sigmoid(gxv[0][u] + __uint_as_float(r[u * GATES + 0]));
-              const float fg = fast_sigmoid(gxv[1 % GATES][u] + __uint_as_float(r[u * GATES + (1 % GATES)]));
-              const float gg = fast_tanh(gxv[2 % GATES][u] + __uint_as_float(r[u * GATES + (2 % GATES)]));
-              const float og = fast_sigmoid(gxv[3 % GATES][u] + __uint_as_float(r[u * GATES + (3 % GATES)]));
-              cst[u] = fg * cst[u] + ig * gg;
-              hn = og * fast_tanh(cst[u]);
-            } else {
-              hn = fast_tanh(gxv[0][u] + __uint_as_float(r[u]));
-            }
-            hprev[u] = hn;
-            yo[u] = hn;
-            ho[u] = __float2bfloat16_rn(hn);
+          float hn;
+          if (GATES == 3) {
+            const float rg = fast_sigmoid(gxv[0][u] + __uint_as_float(r[u * GATES + 0]));
+            const float zg = fast_sigmoid(gxv[1 % GATES][u] + __uint_as_float(r[u * GATES + (1 % GATES)]));
+            const float ng = fast_tanh(gxv[2 % GATES][u] + rg * (__uint_as_float(r[u * GATES + (2 % GATES)]) + bhn[u]));
+            hn = (1.0f - zg) * ng + zg * hprev[u];
+          } else if (GATES == 4) {
+            const float ig = fast_sigmoid(gxv[0][u] + __uint_as_float(r[u * GATES + 0]));
+            const float fg = fast_sigmoid(gxv[1 % GATES][u] + __uint_as_float(r[u * GATES + (1 % GATES)]));
+            const float gg = fast_tanh(gxv[2 % GATES][u] + __uint_as_float(r[u * GATES + (2 % GATES)]));
+            const float og = fast_sigmoid(gxv[3 % GATES][u] + __uint_as_float(r[u * GATES + (3 % GATES)]));
+            cst[u] = fg * cst[u] + ig * gg;
+            hn = og * fast_tanh(cst[u]);
+          } else {
+            hn = fast_tanh(gxv[0][u] + __uint_as_float(r[u]));
+          }
+          hprev[u] = hn;
+          sy[u] = hn;
+          sh[u] = __float2bfloat16_rn(hn);
+        }
+      }
+      long long e3 = clock64();
+      const bool all_ok = bar_red_and(ok, 1, 256);     // staging complete (and uniform abort decision)
+      if (!all_ok) break;
+      // h_t -> global (bf16), coalesced: each row contributes U contiguous values
+      {
+        const int n_valid = min(U, p.H - c * U);       // units of this CTA inside H
+        __nv_bfloat16* hrow0 = p.hbuf + ((size_t)(((s + 1) & 1) * p.dirs + dir) * p.BP) * p.HP + c * U;
+        if ((U & 3) == 0 && n_valid == U && (p.HP & 3) == 0) {
+          const int per_row = U / 4;                   // 8-byte pieces
+          for (int i = et; i < p.BP * per_row; i += 256) {
+            const int row = i / per_row, part = i - row * per_row;
+            if (sT[par][row] >= 0)
+              *reinterpret_cast<uint2*>(hrow0 + (size_t)row * p.HP + part * 4) =
+                  *reinterpret_cast<const uint2*>(sH + ((size_t)par * p.BP + row) * U + part * 4);
+          }
+        } else {
+          for (int i = et; i < p.BP * U; i += 256) {
+            const int row = i / U, u = i - row * U;
+            if (sT[par][row] >= 0 && u < n_valid) hrow0[(size_t)row * p.HP + u] = sH[((size_t)par * p.BP + row) * U + u];
           }
         }
       }
-      const bool all_ok = bar_red_and(ok, 1, 256);
-      if (!all_ok) break;
-      if (threadIdx.x == 64) {
-        __threadfence();
-        atomicAdd(p.counters + dir, 1u);
+      named_bar_sync(2, 256);                          // all h stores issued
+      long long e4 = clock64();
+      if (et == 0) red_release_gpu_add(p.counters + dir, 1u);   // publish h_t (release: cumulative over the CTA)
+      // y_t -> global (fp32) after the publish: nobody waits on these stores
+      {
+        const int n_valid = min(U, p.H - c * U);
+        float* ybase = p.y + (size_t)dir * p.T * p.B * p.H + c * U;
+        if ((U & 3) == 0 && n_valid == U && (p.H & 3) == 0) {
+          const int per_row = U / 4;                   // float4 pieces
+          for (int i = et; i < p.BP * per_row; i += 256) {
+            const int row = i / per_row, part = i - row * per_row;
+            const int tt = sT[par][row];
+            if (tt >= 0)
+              *reinterpret_cast<float4*>(ybase + ((size_t)tt * p.B + row) * p.H + part * 4) =
+                  *reinterpret_cast<const float4*>(sY + ((size_t)par * p.BP + row) * U + part * 4);
+          }
+        } else {
+          for (int i = et; i < p.BP * U; i += 256) {
+            const int row = i / U, u = i - row * U;
+            const int tt = sT[par][row];
+            if (tt >= 0 && u < n_valid) ybase[((size_t)tt * p.B + row) * p.H + u] = sY[((size_t)par * p.BP + row) * U + u];
+          }
+        }
       }
+      e_load += e1 - e0; e_wait += e2 - e1; e_math += e3 - e2; e_bar += e4 - e3; e_pub += clock64() - e4;
+    }
+    if (p.dbg && et == 64) {   // warp 4: quarter 0, an active row
+      p.dbg[blockIdx.x * 16 + 5] = e_load;
+      p.dbg[blockIdx.x * 16 + 6] = e_wait;
+      p.dbg[blockIdx.x * 16 + 7] = e_math;
+      p.dbg[blockIdx.x * 16 + 8] = e_bar;
+      p.dbg[blockIdx.x * 16 + 9] = e_pub;
     }
   }
   tc_fence_before();
@@ -263,7 +392,6 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     tmem_dealloc<64>(tmem_base);
   }
 }
-
 
 // W_hh [dirs][G*H][H] fp32 -> per-CTA slices [dirs][cpd][64 rows][HP] bf16.  Row n of a slice:
 // half = n/32, r = n%32, u = r/G, g = r%G  <->  W_hh[g*H + c*U + half*UH + u][:]  (zero rows/cols beyond H).
@@ -312,8 +440,8 @@ bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* laun
   const int UH = 32 / L.gates, U = 2 * UH;
   const int cpd = cdiv(L.H, U);
   const int HP = (L.H + 63) / 64 * 64;
-  const size_t smem = (size_t)(HP / 64) * tc::RT_W_BYTES + tc::rt_ring_bytes(B <= 64 ? 64 : 128) + 256 + 1024;
-  if (B > 128 || smem > 227 * 1024 || cpd > sms) return false;
+  const tc::RtPlan pl = tc::rt_plan(HP / 64, B <= 64 ? 64 : 128, U);
+  if (B > 128 || pl.stages < 2 || pl.total > tc::RT_SMEM_LIMIT || cpd > sms) return false;
   if (cpd_out) *cpd_out = cpd;
   if (launches_out) *launches_out = (L.dirs * cpd <= sms) ? 1 : L.dirs;
   return true;
@@ -369,16 +497,38 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.abort_flag = reinterpret_cast<int*>(sync_words + 2);
   p.B = B; p.H = L.H; p.HP = HP; p.BP = BP; p.T = T; p.Tmax = Tmax;
   p.dirs = L.dirs; p.cpd = cpd; p.U = 2 * (32 / L.gates); p.nkc = nkc;
-  const size_t smem = (size_t)nkc * RT_W_BYTES + rt_ring_bytes(BP) + 256 + 1024;
+  const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates)).total;
   const void* fn = L.gates == 3 ? (const void*)rnn_tc_kernel<3>
                    : L.gates == 4 ? (const void*)rnn_tc_kernel<4> : (const void*)rnn_tc_kernel<1>;
   DSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int dirs_per_launch = L.dirs / launches;
+  static const bool debug = getenv("DSB_RNN_DEBUG") != nullptr;
+  unsigned long long* dbg = nullptr;
+  const int grid = dirs_per_launch * cpd;
+  if (debug) {
+    DSB_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * 16 * grid));
+    DSB_CUDA(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 16 * grid, st));
+  }
+  p.dbg = dbg;
   for (int l = 0; l < launches; ++l) {
     p.dir0 = l * dirs_per_launch;
     void* args[] = {(void*)&tw, (void*)&th, (void*)&p};
-    DSB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(dirs_per_launch * cpd), dim3(RT_THREADS), args, smem, st));
+    DSB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RT_THREADS), args, smem, st));
     count_launch();
+  }
+  if (debug) {
+    std::vector<unsigned long long> h(16 * grid);
+    DSB_CUDA(cudaStreamSynchronize(st));
+    DSB_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * 16 * grid, cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    const char* names[10] = {"prod.spin", "prod.fence", "prod.issue", "mma.wait_first", "mma.rest", "epi.gload",
+                             "epi.wait_mma", "epi.math_store", "epi.bar", "epi.publish"};
+    fprintf(stderr, "[rnn_tc debug] H=%d B=%d Tmax=%d grid=%d  cycles/step (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid);
+    for (int k = 0; k < 10; ++k) {
+      double sum = 0, mx = 0;
+      for (int c = 0; c < grid; ++c) { double v = (double)h[c * 16 + k] / Tmax; sum += v; mx = v > mx ? v : mx; }
+      fprintf(stderr, "   %-16s %9.0f | %9.0f\n", names[k], sum / grid, mx);
+    }
   }
   return 0;
 }
