@@ -1,15 +1,745 @@
-// Beam CTC decoder (placeholder; implemented after the offline path is green on the GPU).
+// GPU CTC prefix beam search with a device-resident n-gram LM and dictionary.
+//
+// Replaces the ctcdecode.CTCBeamDecoder object the reference builds at
+// danspeech/deepspeech/decoder.py:99-100 and calls at decoder.py:140 (third-party parlance/ctcdecode:
+// prefix beam search + KenLM + dictionary FST on 6 host threads, DanSpeechRecognizer.py:89-92).
+// Semantics follow SURVEY.md appendix B: blank / repeat / extend updates per prefix, LM applied at
+// word boundaries (word LM, with the vocabulary trie as dictionary) or at every symbol (character LM),
+// log(p + FLT_MIN) scores, prefix_compare ordering (score desc, then smaller last symbol), OOV = -1000,
+// final partial-word scoring, reported score = -(score - len*beta - alpha*sentence_log_prob).
+//
+// Mapping: one CTA per utterance (utterances are independent; a batch of 64 occupies 64 SMs).  The live
+// beam (<= 128 prefixes) and the step's candidates (beam x C) live in shared memory; a step is
+//   log-probs -> candidate scores (one thread per (prefix, symbol), LM probes into a device hash table)
+//   -> merge children that are already in the beam -> compaction -> bitonic sort by prefix_compare
+//   -> materialise the surviving prefixes in a per-utterance node arena (parent / symbol / timestep).
+// The work is latency / random-access bound, reported as utterances/s and steps/s.
 #include "model_types.cuh"
+#include <float.h>
+#include <math.h>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+
+namespace dsb {
+
+constexpr int BM_MAXW = 128;       // max beam width
+constexpr int BM_MAXC = 64;        // max classes
+constexpr int BM_HIST = 4;         // max LM order - 1
+constexpr int BM_THREADS = 256;
+constexpr float BM_NEG = -FLT_MAX;
+constexpr float BM_OOV = -1000.0f;
+constexpr float BM_LOGE = 0.4342944819f;
+
+struct LmEntry {
+  uint64_t k0, k1;
+  float prob, backoff;
+  uint32_t used, pad;
+};
+
+struct BeamTables {
+  const int32_t* trans;      // [n_states][C] dictionary arcs (-1 = none; final states map to 0)
+  const int32_t* word_at;    // [n_states] vocabulary id of the word spelled by the state (-1 = not a word)
+  const int32_t* char_word;  // [C] vocabulary id of each single-symbol token (character LM)
+  const LmEntry* lm;
+  uint32_t lm_mask;
+  int order, id_bos, id_eos;
+  int has_lm, char_based;
+  float alpha, beta, unk_prob;
+};
+
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+__host__ __device__ inline void pack_key(const int* ids, int n, uint64_t& k0, uint64_t& k1) {
+  k0 = (uint64_t)n;
+  k1 = 0;
+  for (int i = 0; i < n; ++i) {
+    if (i < 3) k0 |= (uint64_t)(ids[i] & 0xFFFFF) << (3 + 20 * i);
+    else k1 |= (uint64_t)(ids[i] & 0xFFFFF) << (20 * (i - 3));
+  }
+}
+__host__ __device__ inline uint32_t key_hash(uint64_t k0, uint64_t k1) { return (uint32_t)mix64(k0 ^ mix64(k1 + 0x9e3779b97f4a7c15ULL)); }
+
+__device__ __forceinline__ bool lm_find(const BeamTables& T, const int* ids, int n, float& prob, float& backoff) {
+  uint64_t k0, k1;
+  pack_key(ids, n, k0, k1);
+  uint32_t h = key_hash(k0, k1) & T.lm_mask;
+  for (;;) {
+    const LmEntry e = T.lm[h];
+    if (!e.used) return false;
+    if (e.k0 == k0 && e.k1 == k1) {
+      prob = e.prob;
+      backoff = e.backoff;
+      return true;
+    }
+    h = (h + 1) & T.lm_mask;
+  }
+}
+
+// Scorer::get_log_cond_prob: natural-log P(words[n-1] | words[0..n-2]) with KenLM back-off; OOV anywhere -> -1000
+__device__ float lm_log_cond_prob(const BeamTables& T, const int* words, int n) {
+  for (int i = 0; i < n; ++i)
+    if (words[i] == 0) return BM_OOV;
+  int first = n > T.order ? n - T.order : 0;   // keep order-1 context words
+  float bo = 0.f;
+  for (int start = first; start < n; ++start) {
+    float pr, b;
+    if (lm_find(T, words + start, n - start, pr, b)) return (bo + pr) / BM_LOGE;
+    if (start < n - 1 && lm_find(T, words + start, n - 1 - start, pr, b)) bo += b;
+  }
+  return (bo + T.unk_prob) / BM_LOGE;
+}
+
+__device__ __forceinline__ float lse2(float x, float y) {
+  if (x <= BM_NEG) return y;
+  if (y <= BM_NEG) return x;
+  const float m = fmaxf(x, y);
+  return logf(expf(x - m) + expf(y - m)) + m;
+}
+__device__ __forceinline__ uint32_t f2o_desc(float f) {
+  uint32_t u = __float_as_uint(f);
+  u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;   // ascending order
+  return ~u;                                    // descending
+}
+
+struct BeamState {   // one live-beam buffer (shared memory)
+  int node[BM_MAXW], parent[BM_MAXW], ch[BM_MAXW], dstate[BM_MAXW], ts[BM_MAXW];
+  int hist[BM_MAXW][BM_HIST];
+  float bprev[BM_MAXW], nbprev[BM_MAXW], score[BM_MAXW], lpc[BM_MAXW];
+};
+
+struct BeamSmem {
+  BeamState st[2];
+  float lp[BM_MAXC];
+  int allowed[BM_MAXC];
+  float selfb[BM_MAXW], selfnb[BM_MAXW], selfscore[BM_MAXW];
+  int pidx[BM_MAXW];
+  int count, arena_count;
+  float lpb_raw;
+};
+
+struct BeamParams {
+  const float* probs;        // [B,T,C]
+  const int32_t* seq_lens;   // [B] device
+  int B, T, C, W, blank, space, cutoff_top_n;
+  float cutoff_prob;
+  // arena [B][max_nodes]
+  int32_t* a_parent;
+  int32_t* a_info;           // ch | timestep << 8
+  int32_t* a_wid;            // word id completed at this node (space nodes), else -1
+  int max_nodes;
+  float* cand;               // [B][W*C] child candidate scores
+  int32_t* cand_aux;         // [B][W*C][2] next dictionary state, completed word id
+  int32_t* words;            // [B][W][T+2] scratch for the sentence score
+  int32_t* out_tokens;
+  int32_t* out_ts;
+  float* out_scores;
+  int32_t* out_lens;
+  BeamTables tab;
+};
+
+__global__ void __launch_bounds__(BM_THREADS)
+beam_kernel(const BeamParams p) {
+  extern __shared__ __align__(16) unsigned char bsm_raw[];
+  BeamSmem& sm = *reinterpret_cast<BeamSmem*>(bsm_raw);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(bsm_raw + ((sizeof(BeamSmem) + 15) & ~(size_t)15));
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int C = p.C, W = p.W;
+  const BeamTables& T = p.tab;
+  const int HN = T.order > 1 ? T.order - 1 : 0;
+  const int len = min(p.seq_lens ? p.seq_lens[b] : p.T, p.T);
+  int32_t* a_parent = p.a_parent + (size_t)b * p.max_nodes;
+  int32_t* a_info = p.a_info + (size_t)b * p.max_nodes;
+  int32_t* a_wid = p.a_wid + (size_t)b * p.max_nodes;
+  float* cand = p.cand + (size_t)b * W * C;
+  int32_t* cand_aux = p.cand_aux + (size_t)b * W * C * 2;
+
+  int cur = 0, n_active = 1;
+  if (tid == 0) {
+    BeamState& s = sm.st[0];
+    s.node[0] = 0; s.parent[0] = -1; s.ch[0] = -1; s.dstate[0] = 0; s.ts[0] = 0;
+    for (int h = 0; h < BM_HIST; ++h) s.hist[0][h] = T.id_bos;
+    s.bprev[0] = 0.f; s.nbprev[0] = BM_NEG; s.score[0] = 0.f; s.lpc[0] = BM_NEG;
+    a_parent[0] = -1; a_info[0] = 0xFF; a_wid[0] = -1;
+    sm.arena_count = 1;
+  }
+  __syncthreads();
+
+  for (int t = 0; t < len; ++t) {
+    BeamState& S = sm.st[cur];
+    BeamState& Nx = sm.st[cur ^ 1];
+    const float* pr = p.probs + ((size_t)b * p.T + t) * C;
+    // ---- phase 0: log-probabilities, vocabulary pruning (get_pruned_log_probs) ----
+    if (tid < C) {
+      const float pv = pr[tid];
+      sm.lp[tid] = (float)log((double)pv + (double)FLT_MIN);
+      if (tid == p.blank) sm.lpb_raw = (float)log((double)pv);
+      int allowed = 1;
+      if (p.cutoff_prob < 1.0f || p.cutoff_top_n < C) {
+        int rank = 0;
+        for (int c2 = 0; c2 < C; ++c2) {
+          const float q = pr[c2];
+          rank += (q > pv) || (q == pv && c2 < tid);
+        }
+        int cutoff_len = C;
+        if (p.cutoff_prob < 1.0f) {
+          // upstream accumulates log_sum_exp(cum, log p) from cum = 0.0 and stops at cum >= cutoff_prob
+          // (i.e. log(1 + sum p) >= cutoff_prob); reproduce on the sorted order
+          double sum_before = 0.0;   // sum of probabilities ranked strictly before this symbol, plus own
+          for (int c2 = 0; c2 < C; ++c2) {
+            const float q = pr[c2];
+            if ((q > pv) || (q == pv && c2 <= tid)) sum_before += (double)q;
+          }
+          // symbol with rank r is kept iff the stop condition was not met at any earlier rank:
+          // cum after rank r-1 = log(1 + sum_{rank<r}) < cutoff
+          const double prev = sum_before - (double)pv;
+          allowed = (rank == 0) || (log(1.0 + prev) < (double)p.cutoff_prob);
+          (void)cutoff_len;
+        }
+        if (rank >= p.cutoff_top_n) allowed = 0;
+      }
+      sm.allowed[tid] = allowed;
+    }
+    for (int k = tid; k < n_active; k += BM_THREADS) {
+      sm.pidx[k] = -1;
+      sm.selfnb[k] = BM_NEG;
+      sm.selfb[k] = BM_NEG;
+    }
+    if (tid == 0) sm.count = 0;
+    __syncthreads();
+    const bool full_beam = T.has_lm && n_active == W;
+    const float min_cutoff = T.has_lm ? S.score[n_active - 1] + sm.lpb_raw - fmaxf(0.f, T.beta) : BM_NEG;
+
+    // ---- phase 2: which live prefixes are children of other live prefixes ----
+    for (int pair = tid; pair < n_active * n_active; pair += BM_THREADS) {
+      const int k = pair / n_active, i = pair - k * n_active;
+      if (S.parent[k] == S.node[i] && k != i) sm.pidx[k] = i;
+    }
+    // ---- phase 3: candidate scores, one thread per (prefix, symbol) ----
+    for (int idx = tid; idx < n_active * C; idx += BM_THREADS) {
+      const int i = idx / C, c = idx - i * C;
+      const float lpc = sm.lp[c];
+      const float sc = S.score[i];
+      const bool pass = sm.allowed[c] && !(full_beam && lpc + sc < min_cutoff);
+      float v = BM_NEG;
+      int next_state = 0, wid = -1;
+      if (c == p.blank) {
+        if (pass) sm.selfb[i] = lpc + sc;
+      } else if (pass) {
+        if (c == S.ch[i]) sm.selfnb[i] = lpc + S.nbprev[i];   // repeated symbol without a blank
+        bool ok = true;
+        if (T.has_lm && !T.char_based) {
+          next_state = T.trans[(size_t)S.dstate[i] * C + c];
+          ok = next_state >= 0;
+        }
+        if (ok) {
+          float log_p = BM_NEG;
+          if (c == S.ch[i]) {
+            if (S.bprev[i] > BM_NEG) log_p = lpc + S.bprev[i];
+          } else {
+            log_p = lpc + sc;
+          }
+          if (T.has_lm && (c == p.space || T.char_based)) {
+            int words[BM_HIST + 1];
+            for (int h = 0; h < HN; ++h) words[h] = S.hist[i][h];
+            wid = T.char_based ? T.char_word[c] : T.word_at[S.dstate[i]];
+            words[HN] = wid < 0 ? 0 : wid;
+            const float lm = lm_log_cond_prob(T, words, HN + 1) * T.alpha;
+            log_p += lm;
+            log_p += T.beta;
+          }
+          v = log_p;
+          if (!(v > BM_NEG)) v = BM_NEG;
+        }
+      }
+      if (c != p.blank) {
+        cand[idx] = v;
+        cand_aux[idx * 2 + 0] = next_state;
+        cand_aux[idx * 2 + 1] = wid;
+      }
+    }
+    __syncthreads();
+    // ---- phase 3b: a child that is already in the beam absorbs its parent's extension ----
+    for (int k = tid; k < n_active; k += BM_THREADS) {
+      const int i = sm.pidx[k];
+      float nb = sm.selfnb[k];
+      if (i >= 0) {
+        const int c = S.ch[k];
+        const float lpc = sm.lp[c];
+        const bool pass = sm.allowed[c] && !(full_beam && lpc + S.score[i] < min_cutoff);
+        if (pass) {
+          nb = lse2(nb, cand[i * C + c]);
+          cand[i * C + c] = BM_NEG;
+          if (S.lpc[k] < lpc) {   // PathTrie::get_path_trie keeps the time step of the best symbol probability
+            S.lpc[k] = lpc;
+            S.ts[k] = t;
+            a_info[S.node[k]] = (c & 0xFF) | (t << 8);
+          }
+        }
+      }
+      sm.selfnb[k] = nb;
+      sm.selfscore[k] = lse2(sm.selfb[k], nb);
+    }
+    __syncthreads();
+    // ---- phase 4: compaction of the valid candidates + bitonic sort by prefix_compare ----
+    for (int k = tid; k < n_active; k += BM_THREADS) {
+      if (sm.selfscore[k] > BM_NEG) {
+        const int slot = atomicAdd(&sm.count, 1);
+        keys[slot] = ((uint64_t)f2o_desc(sm.selfscore[k]) << 32) | ((uint64_t)((S.ch[k] + 1) & 0xFF) << 16) | (uint64_t)k;
+      }
+    }
+    for (int idx = tid; idx < n_active * C; idx += BM_THREADS) {
+      const int c = idx % C;
+      if (c == p.blank) continue;
+      const float v = cand[idx];
+      if (v > BM_NEG) {
+        const int slot = atomicAdd(&sm.count, 1);
+        keys[slot] = ((uint64_t)f2o_desc(v) << 32) | ((uint64_t)((c + 1) & 0xFF) << 16) | (uint64_t)(BM_MAXW + idx);
+      }
+    }
+    __syncthreads();
+    const int count = sm.count;
+    int n2 = 64;
+    while (n2 < count) n2 <<= 1;
+    for (int i = count + tid; i < n2; i += BM_THREADS) keys[i] = ~0ULL;
+    __syncthreads();
+    for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < n2; i += BM_THREADS) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const uint64_t a = keys[i], bb = keys[ixj];
+            const bool up = (i & k2) == 0;
+            if ((a > bb) == up) {
+              keys[i] = bb;
+              keys[ixj] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- phase 5: the new live beam ----
+    const int m = min(W, count);
+    for (int r = tid; r < m; r += BM_THREADS) {
+      const uint64_t key = keys[r];
+      const int code = (int)(key & 0xFFFF);
+      if (code < BM_MAXW) {   // surviving prefix
+        const int k = code;
+        Nx.node[r] = S.node[k]; Nx.parent[r] = S.parent[k]; Nx.ch[r] = S.ch[k]; Nx.dstate[r] = S.dstate[k];
+        Nx.ts[r] = S.ts[k]; Nx.lpc[r] = S.lpc[k];
+        for (int h = 0; h < BM_HIST; ++h) Nx.hist[r][h] = S.hist[k][h];
+        Nx.bprev[r] = sm.selfb[k]; Nx.nbprev[r] = sm.selfnb[k]; Nx.score[r] = sm.selfscore[k];
+      } else {                // new prefix: parent i extended by symbol c
+        const int idx = code - BM_MAXW;
+        const int i = idx / C, c = idx - i * C;
+        const int id = atomicAdd(&sm.arena_count, 1);
+        const float v = cand[idx];
+        const int wid = cand_aux[idx * 2 + 1];
+        Nx.node[r] = id; Nx.parent[r] = S.node[i]; Nx.ch[r] = c; Nx.ts[r] = t; Nx.lpc[r] = sm.lp[c];
+        Nx.dstate[r] = cand_aux[idx * 2 + 0];
+        const bool shift = T.has_lm && (T.char_based || c == p.space);
+        for (int h = 0; h < BM_HIST; ++h) {
+          int hv = S.hist[i][h];
+          if (shift && HN > 0) hv = (h + 1 < HN) ? S.hist[i][h + 1] : (h == HN - 1 ? (wid < 0 ? 0 : wid) : hv);
+          Nx.hist[r][h] = hv;
+        }
+        Nx.bprev[r] = BM_NEG; Nx.nbprev[r] = v; Nx.score[r] = v;
+        if (id < p.max_nodes) {
+          a_parent[id] = S.node[i];
+          a_info[id] = (c & 0xFF) | (t << 8);
+          a_wid[id] = (T.has_lm && !T.char_based && c == p.space) ? (wid < 0 ? 0 : wid) : -1;
+        }
+      }
+    }
+    __syncthreads();
+    n_active = m;
+    cur ^= 1;
+    if (n_active == 0) break;
+  }
+
+  // ---- final: score the unfinished last word (word LM), order, approximate CTC score, back-trace ----
+  BeamState& S = sm.st[cur];
+  if (T.has_lm && !T.char_based) {
+    for (int k = tid; k < n_active; k += BM_THREADS) {
+      if (S.ch[k] >= 0 && S.ch[k] != p.space) {
+        int words[BM_HIST + 1];
+        for (int h = 0; h < HN; ++h) words[h] = S.hist[k][h];
+        const int wid = T.word_at[S.dstate[k]];
+        words[HN] = wid < 0 ? 0 : wid;
+        float sc = lm_log_cond_prob(T, words, HN + 1) * T.alpha;
+        sc += T.beta;
+        S.score[k] += sc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int k = tid; k < n_active; k += BM_THREADS)
+    keys[k] = ((uint64_t)f2o_desc(S.score[k]) << 32) | ((uint64_t)((S.ch[k] + 1) & 0xFF) << 16) | (uint64_t)k;
+  int n2 = 64;
+  while (n2 < n_active) n2 <<= 1;
+  for (int i = n_active + tid; i < n2; i += BM_THREADS) keys[i] = ~0ULL;
+  __syncthreads();
+  for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n2; i += BM_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = keys[i], bb = keys[ixj];
+          const bool up = (i & k2) == 0;
+          if ((a > bb) == up) { keys[i] = bb; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = tid; r < W; r += BM_THREADS) {
+    int32_t* otok = p.out_tokens + ((size_t)b * W + r) * p.T;
+    int32_t* ots = p.out_ts + ((size_t)b * W + r) * p.T;
+    if (r >= n_active) {
+      p.out_scores[(size_t)b * W + r] = 0.f;
+      p.out_lens[(size_t)b * W + r] = 0;
+      continue;
+    }
+    const int k = (int)(keys[r] & 0xFFFF);
+    // path length
+    int n = 0;
+    for (int node = S.node[k]; node > 0; node = a_parent[node]) ++n;
+    n = min(n, p.T);
+    int pos = n - 1;
+    int32_t* wbuf = p.words + ((size_t)b * W + r) * (p.T + 2);
+    int nwords = 0;   // collected backwards
+    for (int node = S.node[k]; node > 0 && pos >= 0; node = a_parent[node], --pos) {
+      const int info = a_info[node];
+      const int c = info & 0xFF;
+      otok[pos] = c;
+      ots[pos] = info >> 8;
+      if (T.has_lm) {
+        if (T.char_based) wbuf[nwords++] = T.char_word[c];
+        else if (c == p.space && a_wid[node] >= 0) wbuf[nwords++] = a_wid[node];
+      }
+    }
+    double approx = (double)S.score[k];
+    if (T.has_lm) {
+      // words are stored newest-first in wbuf[0..nwords); a trailing partial word comes first
+      int total = nwords;
+      int trailing = -1;
+      if (!T.char_based && S.ch[k] >= 0 && S.ch[k] != p.space) {
+        const int wid = T.word_at[S.dstate[k]];
+        trailing = wid < 0 ? 0 : wid;
+        total += 1;
+      }
+      auto word_at_pos = [&](int i) -> int {   // i-th word of the sentence, oldest first
+        if (trailing >= 0 && i == total - 1) return trailing;
+        const int from_end = (trailing >= 0) ? (total - 2 - i) : (total - 1 - i);
+        return wbuf[from_end];
+      };
+      const int order = T.order;
+      const int pad = total == 0 ? order : order - 1;
+      const int slen = pad + total + 1;
+      double sent = 0.0;
+      for (int i = 0; i + order <= slen; ++i) {
+        int win[BM_HIST + 1];
+        for (int j = 0; j < order; ++j) {
+          const int q = i + j;
+          win[j] = q < pad ? T.id_bos : (q < pad + total ? word_at_pos(q - pad) : T.id_eos);
+        }
+        sent += (double)lm_log_cond_prob(T, win, order);
+      }
+      approx = approx - (double)n * (double)T.beta - sent * (double)T.alpha;
+    }
+    p.out_scores[(size_t)b * W + r] = (float)(-(double)(float)approx);
+    p.out_lens[(size_t)b * W + r] = n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+struct HostLm {
+  int order = 0;
+  std::unordered_map<std::string, int> vocab;
+  std::vector<std::string> words;
+  struct Gram { std::vector<int> ids; float prob, backoff; };
+  std::vector<Gram> grams;
+  float unk_prob = -100.f;
+  int index(const std::string& w) const {
+    auto it = vocab.find(w);
+    return it == vocab.end() ? 0 : it->second;
+  }
+};
+
+static int load_arpa(const char* path, HostLm& lm) {
+  std::ifstream f(path);
+  if (!f) return set_error(DSB_ERR_IO, "dsb_beam_create: cannot open language model '%s'", path);
+  lm.vocab["<unk>"] = 0;
+  lm.words.push_back("<unk>");
+  std::string line;
+  int cur = 0;
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) continue;
+    if (line[0] == '\\') {
+      if (line.find("-grams:") != std::string::npos) {
+        cur = atoi(line.c_str() + 1);
+        if (cur > lm.order) lm.order = cur;
+      } else if (line == "\\end\\") {
+        break;
+      }
+      continue;
+    }
+    if (cur == 0) continue;
+    std::vector<std::string> tok;
+    std::stringstream ss(line);
+    std::string t;
+    while (ss >> t) tok.push_back(t);
+    if ((int)tok.size() < cur + 1) continue;
+    HostLm::Gram g;
+    g.prob = (float)atof(tok[0].c_str());
+    g.backoff = (int)tok.size() > cur + 1 ? (float)atof(tok[cur + 1].c_str()) : 0.f;
+    for (int i = 0; i < cur; ++i) {
+      const std::string& w = tok[1 + i];
+      int id;
+      if (cur == 1 && w != "<unk>") {
+        auto it = lm.vocab.find(w);
+        if (it == lm.vocab.end()) {
+          id = (int)lm.words.size();
+          lm.vocab[w] = id;
+          lm.words.push_back(w);
+        } else {
+          id = it->second;
+        }
+      } else {
+        id = lm.index(w);
+      }
+      g.ids.push_back(id);
+    }
+    if (cur == 1 && g.ids[0] == 0) lm.unk_prob = g.prob;
+    lm.grams.push_back(g);
+  }
+  if (lm.order == 0) return set_error(DSB_ERR_IO, "dsb_beam_create: '%s' is not an ARPA language model", path);
+  if (lm.order > BM_HIST + 1)
+    return set_error(DSB_ERR_UNSUPPORTED, "dsb_beam_create: LM order %d > %d", lm.order, BM_HIST + 1);
+  if (lm.words.size() >= (1u << 20)) return set_error(DSB_ERR_UNSUPPORTED, "dsb_beam_create: vocabulary too large");
+  return 0;
+}
+
+static std::vector<std::string> utf8_split(const std::string& s) {
+  std::vector<std::string> out;
+  for (size_t i = 0; i < s.size();) {
+    unsigned char c = (unsigned char)s[i];
+    size_t n = c < 0x80 ? 1 : (c >> 5) == 0x6 ? 2 : (c >> 4) == 0xE ? 3 : (c >> 3) == 0x1E ? 4 : 1;
+    out.push_back(s.substr(i, n));
+    i += n;
+  }
+  return out;
+}
+
+}  // namespace dsb
+
+struct dsb_beam {
+  int C = 0, W = 0, blank = 0, space = -1, cutoff_top_n = 40;
+  float cutoff_prob = 1.f;
+  dsb::BeamTables tab{};
+  int64_t n_ngrams = 0;
+  std::vector<void*> owned;
+};
+
 using namespace dsb;
-extern "C" int dsb_beam_create(const char*, int, const char*, float, float, int, float, int, int, int, dsb_beam**) {
-  return set_error(DSB_ERR_UNSUPPORTED, "beam decoder not built yet");
+
+template <typename T>
+static int beam_upload(dsb_beam* d, const std::vector<T>& h, const T** out) {
+  void* q = nullptr;
+  DSB_CUDA(cudaMalloc(&q, sizeof(T) * (h.empty() ? 1 : h.size())));
+  d->owned.push_back(q);
+  if (!h.empty()) DSB_CUDA(cudaMemcpy(q, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<const T*>(q);
+  return 0;
 }
-extern "C" void dsb_beam_destroy(dsb_beam*) {}
-extern "C" size_t dsb_beam_workspace_bytes(const dsb_beam*, int, int) { return 0; }
-extern "C" int dsb_beam_decode(dsb_beam*, const float*, const int32_t*, int, int, int, int32_t*, int32_t*, float*,
-                               int32_t*, void*, size_t, void*) {
-  return set_error(DSB_ERR_UNSUPPORTED, "beam decoder not built yet");
+
+extern "C" int dsb_beam_create(const char* labels_utf8, int n_labels, const char* lm_path, float alpha, float beta,
+                               int cutoff_top_n, float cutoff_prob, int beam_width, int blank_id,
+                               int log_probs_input, dsb_beam** out) {
+  DSB_REQUIRE(labels_utf8 && out && n_labels >= 2 && n_labels <= BM_MAXC, "dsb_beam_create: bad labels (n=%d)", n_labels);
+  DSB_REQUIRE(beam_width >= 1 && beam_width <= BM_MAXW, "dsb_beam_create: beam_width %d not in [1,%d]", beam_width,
+              BM_MAXW);
+  DSB_REQUIRE(blank_id >= 0 && blank_id < n_labels, "dsb_beam_create: blank_id out of range");
+  if (log_probs_input) return set_error(DSB_ERR_UNSUPPORTED, "dsb_beam_create: log_probs_input is not supported");
+  std::vector<std::string> labels;
+  const char* p = labels_utf8;
+  for (int i = 0; i < n_labels; ++i) {
+    labels.emplace_back(p);
+    p += labels.back().size() + 1;
+  }
+  dsb_beam* d = new dsb_beam();
+  d->C = n_labels;
+  d->W = beam_width;
+  d->blank = blank_id;
+  d->cutoff_top_n = cutoff_top_n;
+  d->cutoff_prob = cutoff_prob;
+  for (int i = 0; i < n_labels; ++i)
+    if (labels[i] == " ") d->space = i;
+  BeamTables& T = d->tab;
+  T.alpha = alpha;
+  T.beta = beta;
+  T.order = 1;
+  T.unk_prob = -100.f;
+  auto fail = [&](int e) {
+    for (void* q : d->owned) cudaFree(q);
+    delete d;
+    return e;
+  };
+  if (lm_path && lm_path[0]) {
+    HostLm lm;
+    if (int e = load_arpa(lm_path, lm)) return fail(e);
+    T.has_lm = 1;
+    T.order = lm.order;
+    T.unk_prob = lm.unk_prob;
+    T.id_bos = lm.index("<s>");
+    T.id_eos = lm.index("</s>");
+    T.char_based = 1;
+    for (const std::string& w : lm.words)
+      if (w != "<unk>" && w != "<s>" && w != "</s>" && utf8_split(w).size() > 1) T.char_based = 0;
+    // n-gram hash table
+    size_t cap = 64;
+    while (cap < lm.grams.size() * 2) cap <<= 1;
+    std::vector<LmEntry> table(cap);
+    memset(table.data(), 0, sizeof(LmEntry) * cap);
+    for (const HostLm::Gram& g : lm.grams) {
+      uint64_t k0, k1;
+      pack_key(g.ids.data(), (int)g.ids.size(), k0, k1);
+      uint32_t h = key_hash(k0, k1) & (uint32_t)(cap - 1);
+      while (table[h].used && !(table[h].k0 == k0 && table[h].k1 == k1)) h = (h + 1) & (uint32_t)(cap - 1);
+      table[h].k0 = k0; table[h].k1 = k1; table[h].prob = g.prob; table[h].backoff = g.backoff; table[h].used = 1;
+    }
+    d->n_ngrams = (int64_t)lm.grams.size();
+    T.lm_mask = (uint32_t)(cap - 1);
+    if (int e = beam_upload(d, table, &T.lm)) return fail(e);
+    std::unordered_map<std::string, int> char_map;
+    for (int i = 0; i < n_labels; ++i) char_map[labels[i]] = i;
+    std::vector<int32_t> char_word(n_labels, 0);
+    for (int i = 0; i < n_labels; ++i) char_word[i] = lm.index(labels[i]);
+    if (int e = beam_upload(d, char_word, &T.char_word)) return fail(e);
+    // dictionary trie over (word + ' '), final states folded back to the root
+    std::vector<int32_t> trans(n_labels, -1), word_at(1, -1);
+    if (!T.char_based) {
+      if (d->space < 0) return fail(set_error(DSB_ERR_INVALID, "dsb_beam_create: word LM needs a space label"));
+      for (size_t wi = 0; wi < lm.words.size(); ++wi) {
+        const std::string& w = lm.words[wi];
+        std::vector<int> ids;
+        bool ok = true;
+        for (const std::string& c : utf8_split(w)) {
+          auto it = char_map.find(c);
+          if (it == char_map.end() || it->second == d->space) { ok = false; break; }
+          ids.push_back(it->second);
+        }
+        if (!ok || ids.empty()) continue;
+        int s = 0;
+        for (int c : ids) {
+          int nx = trans[(size_t)s * n_labels + c];
+          if (nx < 0) {
+            nx = (int)word_at.size();
+            word_at.push_back(-1);
+            trans.resize(trans.size() + n_labels, -1);
+            trans[(size_t)s * n_labels + c] = nx;
+          }
+          s = nx;
+        }
+        word_at[s] = (int)wi;
+        trans[(size_t)s * n_labels + d->space] = 0;   // word + ' ' is final -> back to the start state
+      }
+    }
+    if (int e = beam_upload(d, trans, &T.trans)) return fail(e);
+    if (int e = beam_upload(d, word_at, &T.word_at)) return fail(e);
+  }
+  *out = d;
+  return 0;
 }
-extern "C" int dsb_beam_lm_order(const dsb_beam*) { return 0; }
-extern "C" int dsb_beam_lm_is_char_based(const dsb_beam*) { return 0; }
-extern "C" int64_t dsb_beam_lm_num_ngrams(const dsb_beam*) { return 0; }
+
+extern "C" void dsb_beam_destroy(dsb_beam* d) {
+  if (!d) return;
+  for (void* q : d->owned) cudaFree(q);
+  delete d;
+}
+
+extern "C" int dsb_beam_lm_order(const dsb_beam* d) { return d && d->tab.has_lm ? d->tab.order : 0; }
+extern "C" int dsb_beam_lm_is_char_based(const dsb_beam* d) { return d && d->tab.has_lm ? d->tab.char_based : -1; }
+extern "C" int64_t dsb_beam_lm_num_ngrams(const dsb_beam* d) { return d ? d->n_ngrams : 0; }
+
+namespace {
+struct BeamWs {
+  size_t o_len, o_parent, o_info, o_wid, o_cand, o_aux, o_words, total;
+  int max_nodes;
+};
+BeamWs beam_ws(const dsb_beam* d, int B, int T) {
+  BeamWs w{};
+  w.max_nodes = 1 + d->W * T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += dsb::align_up(bytes, 256);
+    return o;
+  };
+  w.o_len = take(sizeof(int32_t) * B);
+  w.o_parent = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
+  w.o_info = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
+  w.o_wid = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
+  w.o_cand = take(sizeof(float) * (size_t)B * d->W * d->C);
+  w.o_aux = take(sizeof(int32_t) * (size_t)B * d->W * d->C * 2);
+  w.o_words = take(sizeof(int32_t) * (size_t)B * d->W * (T + 2));
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t dsb_beam_workspace_bytes(const dsb_beam* d, int B, int T) {
+  if (!d || B <= 0 || T <= 0) return 0;
+  return beam_ws(d, B, T).total;
+}
+
+extern "C" int dsb_beam_decode(dsb_beam* d, const float* probs, const int32_t* seq_lens, int B, int T, int C,
+                               int32_t* out_tokens, int32_t* out_timesteps, float* out_scores, int32_t* out_lens,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  DSB_REQUIRE(d && probs && seq_lens && out_tokens && out_timesteps && out_scores && out_lens && workspace,
+              "dsb_beam_decode: null argument");
+  DSB_REQUIRE(B > 0 && T > 0 && C == d->C, "dsb_beam_decode: bad shape B=%d T=%d C=%d (decoder has %d labels)", B, T, C,
+              d->C);
+  const BeamWs w = beam_ws(d, B, T);
+  if (workspace_bytes < w.total)
+    return set_error(DSB_ERR_WORKSPACE, "dsb_beam_decode: workspace %zu < required %zu", workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope scope(ST_BEAM, st);
+  char* base = reinterpret_cast<char*>(workspace);
+  int32_t* d_len = reinterpret_cast<int32_t*>(base + w.o_len);
+  DSB_CUDA(cudaMemcpyAsync(d_len, seq_lens, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+  BeamParams p{};
+  p.probs = probs;
+  p.seq_lens = d_len;
+  p.B = B; p.T = T; p.C = C; p.W = d->W; p.blank = d->blank; p.space = d->space;
+  p.cutoff_top_n = d->cutoff_top_n;
+  p.cutoff_prob = d->cutoff_prob;
+  p.a_parent = reinterpret_cast<int32_t*>(base + w.o_parent);
+  p.a_info = reinterpret_cast<int32_t*>(base + w.o_info);
+  p.a_wid = reinterpret_cast<int32_t*>(base + w.o_wid);
+  p.max_nodes = w.max_nodes;
+  p.cand = reinterpret_cast<float*>(base + w.o_cand);
+  p.cand_aux = reinterpret_cast<int32_t*>(base + w.o_aux);
+  p.words = reinterpret_cast<int32_t*>(base + w.o_words);
+  p.out_tokens = out_tokens;
+  p.out_ts = out_timesteps;
+  p.out_scores = out_scores;
+  p.out_lens = out_lens;
+  p.tab = d->tab;
+  int n2 = 64;
+  while (n2 < d->W * C + d->W) n2 <<= 1;
+  const size_t smem = ((sizeof(BeamSmem) + 15) & ~(size_t)15) + sizeof(uint64_t) * n2;
+  DSB_CUDA(cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DSB_CUDA(cudaMemsetAsync(out_tokens, 0, sizeof(int32_t) * (size_t)B * d->W * T, st));
+  DSB_CUDA(cudaMemsetAsync(out_timesteps, 0, sizeof(int32_t) * (size_t)B * d->W * T, st));
+  beam_kernel<<<B, BM_THREADS, smem, st>>>(p);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}

@@ -30,6 +30,10 @@ constexpr int RT_BK = 64;
 constexpr int RT_N = 64;                       // W_hh rows per CTA = 2 halves x 32 columns
 constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk (8 KB)
 constexpr int RT_MAX_STAGES = 8;
+// Consecutive tcgen05.mma into the SAME accumulator serialise on the accumulate dependency (~100 cycles
+// each, measured), which dwarfs the 32 cycles of work of a 64x64x16 MMA.  The four K=16 slices of a chunk
+// therefore go to four independent TMEM accumulators that the epilogue adds up.
+constexpr int RT_ACC = 1;   // measured: 4 accumulators do not help, the MMA is bound by shared-memory operand bandwidth (~64 B/clk), not by the accumulate dependency
 constexpr int RT_THREADS = 64 + 256;
 constexpr long long RT_TIMEOUT_CYCLES = 4000000000LL;
 constexpr int RT_SMEM_LIMIT = 227 * 1024;
@@ -157,7 +161,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     mbar_init(dfull, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<64>(tmem_slot);
+  if (warp == 1) tmem_alloc<RT_ACC * RT_N>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -173,7 +177,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       uint32_t phase = 0;
       bool ok = true;
       const unsigned* ctr = p.counters + dir;
-      unsigned long long d_spin = 0, d_fence = 0, d_issue = 0;
+      unsigned long long d_spin = 0, d_fence = 0, d_issue = 0, d_empty = 0;
       for (int s = 0; s < p.Tmax && ok; ++s) {
         long long c0 = clock64();
         if (s > 0) {
@@ -191,7 +195,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           }
           if (!ok) break;
           long long c1 = clock64();
-          asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
+          asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
           d_spin += c1 - c0;
           d_fence += clock64() - c1;
         }
@@ -200,7 +204,9 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         for (int i = 0; i < p.nkc; ++i) {
           int kc = i + kc_rot;
           if (kc >= p.nkc) kc -= p.nkc;
+          long long w0 = clock64();
           if (!wait_abortable(&empty[stage], phase ^ 1, p.abort_flag)) { ok = false; break; }
+          d_empty += clock64() - w0;
           mbar_arrive_expect_tx(&full[stage], (uint32_t)pl.stage_bytes);
           tma_load_2d(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0);
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -211,6 +217,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         p.dbg[blockIdx.x * 16 + 0] = d_spin;
         p.dbg[blockIdx.x * 16 + 1] = d_fence;
         p.dbg[blockIdx.x * 16 + 2] = d_issue;
+        p.dbg[blockIdx.x * 16 + 11] = d_empty;
       }
     }
   } else if (warp == 1) {
@@ -219,20 +226,23 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       bool ok = wait_abortable(wbar, 0, p.abort_flag);
       int stage = 0;
       uint32_t phase = 0;
-      unsigned long long d_wait0 = 0, d_rest = 0;
+      unsigned long long d_wait0 = 0, d_rest = 0, d_waitn = 0;
       for (int s = 0; s < p.Tmax && ok; ++s) {
         long long m0 = clock64();
         for (int i = 0; i < p.nkc; ++i) {
           int kc = i + kc_rot;
           if (kc >= p.nkc) kc -= p.nkc;
+          long long w0 = clock64();
           if (!wait_abortable(&full[stage], phase, p.abort_flag)) { ok = false; break; }
           if (i == 0) { long long m1 = clock64(); d_wait0 += m1 - m0; m0 = m1; }
+          else d_waitn += clock64() - w0;
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * pl.stage_bytes), 16, 1024, 2);
           const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)kc * RT_W_BYTES), 16, 1024, 2);
 #pragma unroll
           for (int k = 0; k < RT_BK / 16; ++k)
-            umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) != 0);
+            umma_bf16(tmem_base + (uint32_t)((k % RT_ACC) * RT_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
+                      idesc, i != 0);
           umma_commit(&empty[stage]);
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
@@ -242,6 +252,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       if (p.dbg) {
         p.dbg[blockIdx.x * 16 + 3] = d_wait0;
         p.dbg[blockIdx.x * 16 + 4] = d_rest;
+        p.dbg[blockIdx.x * 16 + 10] = d_waitn;
       }
     }
   } else {
@@ -302,6 +313,14 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       uint32_t r[32];
       tmem_ld32(t_addr, r);
       tmem_ld_wait();
+#pragma unroll
+      for (int a = 1; a < RT_ACC; ++a) {
+        uint32_t r2[32];
+        tmem_ld32(t_addr + (uint32_t)(a * RT_N), r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      }
       tc_fence_before();
       if (ok && active) {
         __nv_bfloat16* sh = sH + ((size_t)par * p.BP + b) * U + half * UH;
@@ -389,7 +408,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<64>(tmem_base);
+    tmem_dealloc<RT_ACC * RT_N>(tmem_base);
   }
 }
 
@@ -521,10 +540,11 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     DSB_CUDA(cudaStreamSynchronize(st));
     DSB_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * 16 * grid, cudaMemcpyDeviceToHost));
     cudaFree(dbg);
-    const char* names[10] = {"prod.spin", "prod.fence", "prod.issue", "mma.wait_first", "mma.rest", "epi.gload",
-                             "epi.wait_mma", "epi.math_store", "epi.bar", "epi.publish"};
+    const char* names[12] = {"prod.spin", "prod.fence", "prod.issue", "mma.wait_first", "mma.rest", "epi.gload",
+                             "epi.wait_mma", "epi.math_store", "epi.bar", "epi.publish", "mma.wait_rest",
+                             "prod.wait_empty"};
     fprintf(stderr, "[rnn_tc debug] H=%d B=%d Tmax=%d grid=%d  cycles/step (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid);
-    for (int k = 0; k < 10; ++k) {
+    for (int k = 0; k < 12; ++k) {
       double sum = 0, mx = 0;
       for (int c = 0; c < grid; ++c) { double v = (double)h[c * 16 + k] / Tmax; sum += v; mx = v > mx ? v : mx; }
       fprintf(stderr, "   %-16s %9.0f | %9.0f\n", names[k], sum / grid, mx);

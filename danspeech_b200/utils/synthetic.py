@@ -44,8 +44,12 @@ def _bn(rng, n, prefix, sd):
 
 def make_state_dict(conv_layers=2, rnn_layers=5, rnn_hidden_size=400, bidirectional=True, rnn_type="gru", context=20,
                     streaming_inference_model=False, num_classes=len(LABELS), seed=0, fc_scale=10.0,
-                    ih_scale=4.0):
+                    ih_scale=None):
     """State dict with the reference's names and shapes, float32 torch tensors."""
+    if ih_scale is None:
+        # deeper random stacks amplify perturbations more: with x4 a 9-layer stack already turns plain bf16
+        # rounding of weights and layer inputs (emulated on the CPU) into ~3e-2 logit error
+        ih_scale = 4.0 if rnn_layers <= 5 else 2.5
     rng = np.random.default_rng(seed)
     sd = OrderedDict()
     H = rnn_hidden_size

@@ -2,6 +2,7 @@
 # One gpurun session: parity tests, kernel tests, bench, launch list.  Every leg has its own timeout and log.
 set -u
 mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== pytest parity" ; timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py -q -m gpu ${PYTEST_ARGS:-} > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest.log
 grep -E "passed|failed|Error|error" gpurun_out/pytest.log | tail -15

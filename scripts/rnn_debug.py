@@ -5,6 +5,8 @@ import sys
 os.environ["DSB_RNN_DEBUG"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
+import __graft_entry__ as _g  # noqa: E402
+_g.build()
 from danspeech_b200 import Recognizer  # noqa: E402
 from danspeech_b200.pretrained_models import build_model  # noqa: E402
 from danspeech_b200.utils import synthetic as syn  # noqa: E402

