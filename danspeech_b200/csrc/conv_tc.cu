@@ -1,0 +1,306 @@
+// bf16 tensor-core MaskConv blocks for sm_100a: implicit-GEMM Conv2d + folded BatchNorm2d +
+// Hardtanh(0,20) + length mask (danspeech/deepspeech/model.py:357-392 and MaskConv.forward :65-81).
+//
+// Activations are channels-last bf16 [B][D][T'][C].  An output tile is 128 consecutive frames of one
+// (utterance, output frequency row) x all output channels:  D[128, Cout] = sum over (kh, kw) of
+// A_{kh,kw}[128, Cin] * W_{kh,kw}[Cout, Cin]^T, where A_{kh,kw} is the TMA box
+// {Cin, 128 frames} at (t0 + kw - 5, 2d + kh - pad, b): the zero padding in time and frequency is the
+// TMA out-of-bounds fill, so there is no im2col buffer and no boundary code.
+// The first block has Cin = 1, which no MMA can use directly; its input is expanded once in time
+// ("x1[b,d,t,j] = spect[b,d,2t+j-5]", 11 taps padded to 16) so that it becomes a kH x 1 convolution
+// over 16 channels with unit time stride, and runs through the same kernel.
+// Warp roles as in gemm_tc.cu: TMA producer / single-thread tcgen05.mma issuer / 4 epilogue warps, with
+// the accumulator double-buffered in TMEM so that the epilogue of a tile overlaps the next tile's MMAs.
+// Bound: the SS-mode MMA operand fetch from shared memory (~64 B/clk/SM measured), i.e. tensor pipe
+// fed at (128 + Cout)/2 + ~30 cycles per K=16 slice; algorithmic flops = 2*T'*Cout*Dout*Cin*kH*kW per utterance.
+#include "tc_common.cuh"
+#include "model_types.cuh"
+
+namespace dsb {
+namespace tc {
+
+constexpr int CV_BM = 128;
+constexpr int CV_STAGES = 8;
+constexpr int CV_THREADS = 192;
+
+struct ConvTcParams {
+  const float* bias;          // [NOUT] folded
+  const int32_t* lens;        // [B] output frames per utterance
+  __nv_bfloat16* out;
+  int B, Tp, Din, Dout, KH, KW, sd, pd, pt;
+  int rnn_layout;             // 0: [B][Dout][Tp][NOUT]   1: [(t*B+b)][Dout*NOUT] (feature = d*NOUT + co)
+  int64_t out_ld;             // row stride of the rnn layout
+};
+
+template <int NOUT, int CIN>
+struct ConvSmem {
+  static constexpr int ROW = CIN * 2;
+  static constexpr int A_BYTES = CV_BM * ROW;
+  static constexpr int B_BYTES = NOUT * ROW;
+  static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;
+  static constexpr int BAR_OFF = CV_STAGES * (A_STRIDE + B_STRIDE);
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int NOUT, int CIN>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+               const ConvTcParams p) {
+  using S = ConvSmem<NOUT, CIN>;
+  constexpr int TMEM_COLS = NOUT <= 32 ? 64 : 256;
+  constexpr int ACC_STRIDE = NOUT <= 32 ? 32 : 128;
+  constexpr uint32_t SWZ = CIN == 32 ? 4u : 6u;          // SWIZZLE_64B : SWIZZLE_32B
+  constexpr uint32_t SBO = 8 * S::ROW;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + CV_STAGES * S::A_STRIDE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty = full + CV_STAGES;
+  uint64_t* tfull = empty + CV_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_blocks = (p.Tp + CV_BM - 1) / CV_BM;
+  const int n_tiles = p.B * p.Dout * t_blocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+    for (int i = 0; i < CV_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (b, d, t0); frames fastest so that neighbouring CTAs share input rows in L2
+  auto decode = [&](int tile, int& b, int& d, int& t0) {
+    const int tb = tile % t_blocks;
+    const int r = tile / t_blocks;
+    d = r % p.Dout;
+    b = r / p.Dout;
+    t0 = tb * CV_BM;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int b, d, t0;
+        decode(tile, b, d, t0);
+        const int kh_lo = max(0, p.pd - p.sd * d), kh_hi = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d);
+        for (int kh = kh_lo; kh <= kh_hi; ++kh) {
+          const int row = p.sd * d + kh - p.pd;
+          for (int kw = 0; kw < p.KW; ++kw) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], S::A_BYTES + S::B_BYTES);
+            tma_load_4d(sA + stage * S::A_STRIDE, &tmap_x, &full[stage], 0, t0 + kw - p.pt, row, b);
+            tma_load_2d(sB + stage * S::B_STRIDE, &tmap_w, &full[stage], 0, (kh * p.KW + kw) * NOUT);
+            if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(CV_BM, NOUT);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int b, d, t0;
+        decode(tile, b, d, t0);
+        const int kh_lo = max(0, p.pd - p.sd * d), kh_hi = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d);
+        const int steps = (kh_hi - kh_lo + 1) * p.KW;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int s = 0; s < steps; ++s) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * S::A_STRIDE), 16, SBO, SWZ);
+          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * S::B_STRIDE), 16, SBO, SWZ);
+#pragma unroll
+          for (int k = 0; k < CIN / 16; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (s | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int b, d, t0;
+      decode(tile, b, d, t0);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int t = t0 + q * 32 + lane;
+      const bool valid = t < p.Tp;
+      const bool live = valid && t < p.lens[b];
+      __nv_bfloat16* dst = nullptr;
+      if (valid)
+        dst = p.rnn_layout ? p.out + ((int64_t)t * p.B + b) * p.out_ld + (int64_t)d * NOUT
+                           : p.out + (((int64_t)b * p.Dout + d) * p.Tp + t) * NOUT;
+      const uint32_t t_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < NOUT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_addr + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              float v0 = 0.f, v1 = 0.f;
+              if (live) {
+                v0 = fminf(fmaxf(__uint_as_float(r[j + 2 * h]) + __ldg(p.bias + c0 + j + 2 * h), 0.f), 20.f);
+                v1 = fminf(fmaxf(__uint_as_float(r[j + 2 * h + 1]) + __ldg(p.bias + c0 + j + 2 * h + 1), 0.f), 20.f);
+              }
+              __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+              w[h] = *reinterpret_cast<uint32_t*>(&pk);
+            }
+            *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// x1[b][d][t][j] = spect[b][d][2t + j - 5] (j < 11, zero outside [0,T) and for j >= 11)
+__global__ void im2col_time_kernel(const float* __restrict__ spect, __nv_bfloat16* __restrict__ x1, int B, int D, int T,
+                                   int Tp) {
+  const int64_t total = (int64_t)B * D * Tp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % Tp);
+    const int64_t bd = i / Tp;
+    const float* src = spect + bd * T;
+    uint32_t w[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const int j0 = 2 * h, j1 = 2 * h + 1;
+      const int s0 = 2 * t + j0 - 5, s1 = 2 * t + j1 - 5;
+      const float v0 = (j0 < kConvKW && s0 >= 0 && s0 < T) ? src[s0] : 0.f;
+      const float v1 = (j1 < kConvKW && s1 >= 0 && s1 < T) ? src[s1] : 0.f;
+      __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+      w[h] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(x1 + i * 16);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// folded fp32 weights [kh][cin][11][cout] -> bf16 [(kh*KW + kw)][cout][cin_pad]
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int KH, int cin,
+                                   int cout, int first) {
+  const int KW = first ? 1 : kConvKW, CP = first ? 16 : cin;
+  const int64_t total = (int64_t)KH * KW * cout * CP;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % CP);
+    int64_t r = i / CP;
+    const int co = (int)(r % cout);
+    r /= cout;
+    const int kw = (int)(r % KW), kh = (int)(r / KW);
+    float v;
+    if (first) v = ci < kConvKW ? w[(((int64_t)kh * cin + 0) * kConvKW + ci) * cout + co] : 0.f;
+    else v = w[(((int64_t)kh * cin + ci) * kConvKW + kw) * cout + co];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+template <int NOUT, int CIN>
+static int launch_conv(const __nv_bfloat16* x, const ConvLayer& L, const ConvTcParams& p, cudaStream_t st) {
+  using S = ConvSmem<NOUT, CIN>;
+  CUtensorMap tx, tw;
+  const CUtensorMapSwizzle swz = CIN == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  uint64_t dx[4] = {(uint64_t)CIN, (uint64_t)p.Tp, (uint64_t)p.Din, (uint64_t)p.B};
+  uint64_t sx[4] = {2, (uint64_t)CIN * 2, (uint64_t)p.Tp * CIN * 2, (uint64_t)p.Din * p.Tp * CIN * 2};
+  uint32_t bx[4] = {CIN, CV_BM, 1, 1};
+  if (int e = make_tmap_bf16(&tx, x, 4, dx, sx, bx, swz)) return e;
+  uint64_t dw[2] = {(uint64_t)CIN, (uint64_t)p.KH * p.KW * NOUT}, sw[2] = {2, (uint64_t)CIN * 2};
+  uint32_t bw[2] = {CIN, NOUT};
+  if (int e = make_tmap_bf16(&tw, L.w_tc, 2, dw, sw, bw, swz)) return e;
+  static bool attr = false;
+  if (!attr) {
+    DSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NOUT, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = p.B * p.Dout * cdiv(p.Tp, CV_BM);
+  conv_tc_kernel<NOUT, CIN><<<tiles < sms ? tiles : sms, CV_THREADS, S::TOTAL, st>>>(tx, tw, p);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace tc
+
+int im2col_time_tc(const float* spect, __nv_bfloat16* x1, int B, int T, int Tp, cudaStream_t st) {
+  const int64_t total = (int64_t)B * kFreqBins * Tp;
+  tc::im2col_time_kernel<<<(int)(cdiv64(total, 256) < 148 * 16 ? cdiv64(total, 256) : 148 * 16), 256, 0, st>>>(
+      spect, x1, B, kFreqBins, T, Tp);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
+int pack_conv_w_tc(const ConvLayer& L, bool first, __nv_bfloat16* out, cudaStream_t st) {
+  const int64_t total = (int64_t)L.kh * (first ? 1 : kConvKW) * L.cout * (first ? 16 : L.cin);
+  tc::pack_conv_w_kernel<<<(int)(cdiv64(total, 256) < 2048 ? cdiv64(total, 256) : 2048), 256, 0, st>>>(
+      L.w, out, L.kh, L.cin, L.cout, first ? 1 : 0);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
+// x: block 0 -> time-expanded spectrogram [B][161][Tp][16]; later blocks -> [B][Din][Tp][32]
+int conv_block_tc(const __nv_bfloat16* x, const ConvLayer& L, bool first, const int32_t* d_len, int B, int Tp,
+                  __nv_bfloat16* out, bool rnn_layout, int64_t out_ld, cudaStream_t st) {
+  tc::ConvTcParams p{};
+  p.bias = L.bias;
+  p.lens = d_len;
+  p.out = out;
+  p.B = B; p.Tp = Tp; p.Din = L.din; p.Dout = L.dout; p.KH = L.kh;
+  p.KW = first ? 1 : kConvKW;
+  p.sd = L.sd; p.pd = L.pd;
+  p.pt = first ? 0 : kConvPT;
+  p.rnn_layout = rnn_layout ? 1 : 0;
+  p.out_ld = out_ld;
+  if (first && L.cout == 32) return tc::launch_conv<32, 16>(x, L, p, st);
+  if (!first && L.cin == 32 && L.cout == 32) return tc::launch_conv<32, 32>(x, L, p, st);
+  if (!first && L.cin == 32 && L.cout == 96) return tc::launch_conv<96, 32>(x, L, p, st);
+  return set_error(DSB_ERR_UNSUPPORTED, "conv_block_tc: unsupported block (cin=%d, cout=%d)", L.cin, L.cout);
+}
+
+}  // namespace dsb

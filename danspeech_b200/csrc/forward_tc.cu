@@ -42,18 +42,47 @@ static int dev_alloc_tc(dsb_model* m, T** p, int64_t n) {
 
 static int conv_grid(int64_t n) { return (int)(cdiv64(n, 256) < 4096 ? cdiv64(n, 256) : 4096); }
 
+// The tensor-core conv stack hands the RNN channels-last features (index d*C + c) instead of the
+// reference's channel-major order (c*D + d, model.py:502); permuting the columns of the first layer's
+// W_ih once makes the projection identical.
+__global__ void permute_w_ih0_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows, int C,
+                                     int D, int ld) {
+  const int64_t total = (int64_t)rows * C * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % (C * D));
+    const int64_t r = i / (C * D);
+    const int d = col / C, c = col - d * C;
+    out[r * ld + col] = __float2bfloat16_rn(w[r * (int64_t)(C * D) + (int64_t)c * D + d]);
+  }
+}
+
 int finalize_tc(dsb_model* m, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  for (size_t i = 0; i < m->convs.size(); ++i) {
+    ConvLayer& L = m->convs[i];
+    const bool first = i == 0;
+    const int64_t n = (int64_t)L.kh * (first ? 1 : kConvKW) * L.cout * (first ? 16 : L.cin);
+    if (int e = dev_alloc_tc(m, &L.w_tc, n)) return e;
+    if (int e = pack_conv_w_tc(L, first, L.w_tc, st)) return e;
+  }
+  bool first_rnn = true;
   for (RnnLayer& R : m->rnns) {
     const int GH = R.gates * R.H, rows = R.dirs * GH;
     R.in_ld = (R.in_size + 7) / 8 * 8;
     if (int e = dev_alloc_tc(m, &R.w_ih_tc, (int64_t)rows * R.in_ld)) return e;
     DSB_CUDA(cudaMemsetAsync(R.w_ih_tc, 0, sizeof(__nv_bfloat16) * (size_t)rows * R.in_ld, st));
-    f32_to_bf16_ld_kernel<<<conv_grid((int64_t)rows * R.in_size), 256, 0, st>>>(R.w_ih, R.w_ih_tc, rows, R.in_size,
-                                                                               R.in_ld);
+    if (first_rnn) {
+      const ConvLayer& LC = m->convs.back();
+      permute_w_ih0_kernel<<<conv_grid((int64_t)rows * R.in_size), 256, 0, st>>>(R.w_ih, R.w_ih_tc, rows, LC.cout,
+                                                                                 LC.dout, R.in_ld);
+    } else {
+      f32_to_bf16_ld_kernel<<<conv_grid((int64_t)rows * R.in_size), 256, 0, st>>>(R.w_ih, R.w_ih_tc, rows, R.in_size,
+                                                                                 R.in_ld);
+    }
     DSB_CHECK_LAUNCH();
+    first_rnn = false;
     if (int e = dev_alloc_tc(m, &R.b_ih_tc, rows)) return e;
     if (int e = dev_alloc_tc(m, &R.b_hn, (int64_t)R.dirs * R.H)) return e;
     fold_rnn_bias_kernel<<<cdiv(rows, 256), 256, 0, st>>>(R.b_ih, R.b_hh, R.dirs, R.gates, R.H, R.b_ih_tc, R.b_hn);
@@ -73,6 +102,7 @@ namespace {
 struct TcWorkspace {
   int32_t* d_len;
   float* act[2];
+  __nv_bfloat16* cb[2];   // channels-last bf16 conv activations (ping-pong)
   __nv_bfloat16* xb;
   float* gates;
   float* ydir;
@@ -91,8 +121,13 @@ TcWorkspace carve_tc(const dsb_model* m, int B, int T, void* base) {
   const dsb_model_desc& d = m->desc;
   const int Tp = dsb_model_out_frames(m, T);
   const int dirs = m->rnns[0].dirs, G = m->rnns[0].gates, H = d.rnn_hidden_size;
-  size_t act_elems = 0;
-  for (const ConvLayer& L : m->convs) act_elems = max(act_elems, (size_t)B * L.cout * L.dout * Tp);
+  const size_t act_elems = (size_t)Tp * B * H;   // fp32 scratch for the lookahead output
+  size_t cb0 = (size_t)B * kFreqBins * Tp * 16, cb1 = 0;
+  for (size_t i = 0; i < m->convs.size(); ++i) {
+    const ConvLayer& L = m->convs[i];
+    const size_t e = (size_t)B * L.dout * Tp * L.cout;
+    if (i % 2 == 0) cb1 = max(cb1, e); else cb0 = max(cb0, e);
+  }
   const int ld = max((m->rnn_input + 7) / 8 * 8, (H + 7) / 8 * 8);
   const int HP = (H + 63) / 64 * 64;
   size_t off = 0;
@@ -106,6 +141,8 @@ TcWorkspace carve_tc(const dsb_model* m, int B, int T, void* base) {
   const size_t o_len = take(sizeof(int32_t) * B);
   const size_t o_a0 = take(sizeof(float) * act_elems);
   const size_t o_a1 = take(sizeof(float) * act_elems);
+  const size_t o_cb0 = take(sizeof(__nv_bfloat16) * cb0);
+  const size_t o_cb1 = take(sizeof(__nv_bfloat16) * cb1);
   const size_t o_xb = take(sizeof(__nv_bfloat16) * (size_t)Tp * B * ld);
   const size_t o_g = take(sizeof(float) * (size_t)Tp * B * dirs * G * H);
   const size_t o_y = take(sizeof(float) * (size_t)dirs * Tp * B * H);
@@ -121,6 +158,8 @@ TcWorkspace carve_tc(const dsb_model* m, int B, int T, void* base) {
     w.d_len = reinterpret_cast<int32_t*>(p + o_len);
     w.act[0] = reinterpret_cast<float*>(p + o_a0);
     w.act[1] = reinterpret_cast<float*>(p + o_a1);
+    w.cb[0] = reinterpret_cast<__nv_bfloat16*>(p + o_cb0);
+    w.cb[1] = reinterpret_cast<__nv_bfloat16*>(p + o_cb1);
     w.xb = reinterpret_cast<__nv_bfloat16*>(p + o_xb);
     w.gates = reinterpret_cast<float*>(p + o_g);
     w.ydir = reinterpret_cast<float*>(p + o_y);
@@ -150,20 +189,17 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
   DSB_CUDA(cudaMemsetAsync(ws.sync_words, 0, 64, st));   // step counters + abort flag
 
   prof_begin(ST_CONV, st);
-  const float* x = spect;
-  int cur = 0, cin = 1, din = kFreqBins, tin = T;
-  for (size_t i = 0; i < m->convs.size(); ++i) {
-    const bool last = i + 1 == m->convs.size();
-    if (int e = conv2d_bn_htanh_f32(x, B, cin, din, tin, m->convs[i], ws.d_len, ws.act[cur], Tp, last, st)) return e;
-    x = ws.act[cur];
-    cur ^= 1;
-    cin = m->convs[i].cout;
-    din = m->convs[i].dout;
-    tin = Tp;
+  if (int e = im2col_time_tc(spect, ws.cb[0], B, T, Tp, st)) return e;
+  {
+    const __nv_bfloat16* x = ws.cb[0];
+    for (size_t i = 0; i < m->convs.size(); ++i) {
+      const ConvLayer& L = m->convs[i];
+      const bool last = i + 1 == m->convs.size();
+      __nv_bfloat16* y = last ? ws.xb : ws.cb[(i + 1) & 1];
+      if (int e = conv_block_tc(x, L, i == 0, ws.d_len, B, Tp, y, last, m->rnns[0].in_ld, st)) return e;
+      x = y;
+    }
   }
-  f32_to_bf16_ld_kernel<<<conv_grid(M * m->rnn_input), 256, 0, st>>>(x, ws.xb, M, m->rnn_input,
-                                                                     m->rnns[0].in_ld);
-  DSB_CHECK_LAUNCH();
   prof_end(ST_CONV, st);
 
   const int Tmax = h_out_len[0];

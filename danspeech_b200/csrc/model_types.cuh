@@ -71,6 +71,10 @@ int softmax_argmax_f32(const float* logits, float* probs, int32_t* argmax, int T
 // ---- bf16 tensor-core path (tcgen05 / TMEM / TMA) ----
 int gemm_bias_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
                  float* C, int64_t ldc, int M, int N, int K, cudaStream_t st);
+int im2col_time_tc(const float* spect, __nv_bfloat16* x1, int B, int T, int Tp, cudaStream_t st);
+int pack_conv_w_tc(const ConvLayer& L, bool first, __nv_bfloat16* out, cudaStream_t st);
+int conv_block_tc(const __nv_bfloat16* x, const ConvLayer& L, bool first, const int32_t* d_len, int B, int Tp,
+                  __nv_bfloat16* out, bool rnn_layout, int64_t out_ld, cudaStream_t st);
 bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* launches_out);
 int pack_whh_tc(const RnnLayer& L, __nv_bfloat16* out, cudaStream_t st);
 int combine_dirs_tc(const float* y, int dirs, int T, int B, int H, const int32_t* d_len, __nv_bfloat16* xb, int ldx,

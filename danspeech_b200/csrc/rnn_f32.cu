@@ -142,4 +142,38 @@ int rnn_layer_f32(const dsb_model* m, const RnnLayer& L, const float* gates_x, c
   return 0;
 }
 
+
+// Uni-directional layer with carried state (BatchRNNStream, model.py:219-237): h_io/c_io [B][H] hold the
+// state between chunks; has_state = false starts from zeros (first chunk of an utterance).
+int rnn_layer_f32_state(const RnnLayer& L, const float* gates_x, const int32_t* d_len, int B, int T, float* y,
+                        float* h_scratch, float* c_scratch, float* h_io, float* c_io, bool has_state, cudaStream_t st) {
+  (void)c_scratch;
+  const int H = L.H;
+  const size_t hbytes = sizeof(float) * (size_t)B * H;
+  if (L.dirs != 1) return set_error(DSB_ERR_UNSUPPORTED, "rnn_layer_f32_state: uni-directional layers only");
+  if (has_state) {
+    DSB_CUDA(cudaMemcpyAsync(h_scratch, h_io, hbytes, cudaMemcpyDeviceToDevice, st));
+  } else {
+    DSB_CUDA(cudaMemsetAsync(h_scratch, 0, hbytes, st));
+    if (L.gates == 4) DSB_CUDA(cudaMemsetAsync(c_io, 0, hbytes, st));
+  }
+  dim3 grid(cdiv(H, RJ), 1, cdiv(B, RB));
+  float* hbuf[2] = {h_scratch, h_scratch + (size_t)B * H};
+  for (int s = 0; s < T; ++s) {
+    const float* hp = hbuf[s & 1];
+    float* hn = hbuf[(s + 1) & 1];
+    if (L.gates == 3)
+      rnn_step_f32_kernel<3><<<grid, 256, 0, st>>>(gates_x, L.w_hh, L.b_hh, hp, hn, c_io, y, d_len, s, B, H, 1);
+    else if (L.gates == 4)
+      rnn_step_f32_kernel<4><<<grid, 256, 0, st>>>(gates_x, L.w_hh, L.b_hh, hp, hn, c_io, y, d_len, s, B, H, 1);
+    else
+      rnn_step_f32_kernel<1><<<grid, 256, 0, st>>>(gates_x, L.w_hh, L.b_hh, hp, hn, c_io, y, d_len, s, B, H, 1);
+    count_launch();
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(DSB_ERR_CUDA, "rnn step launch failed: %s", cudaGetErrorString(e));
+  DSB_CUDA(cudaMemcpyAsync(h_io, hbuf[T & 1], hbytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 }  // namespace dsb

@@ -242,7 +242,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < RT_BK / 16; ++k)
             umma_bf16(tmem_base + (uint32_t)((k % RT_ACC) * RT_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
-                      idesc, i != 0);
+                      idesc, (i != 0) || (k >= RT_ACC));
           umma_commit(&empty[stage]);
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }

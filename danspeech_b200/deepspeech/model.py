@@ -256,14 +256,15 @@ class DeepSpeech(nn.Module):
                 N.check(L.dsb_stream_state_create(h, S, 512, st), "dsb_stream_state_create")
                 self._stream_state, self._stream_key = st, key
             k_max = L.dsb_stream_max_out_frames(self._stream_state, k)
-            probs = torch.empty((S, max(k_max, 1), len(self.labels)), dtype=torch.float32, device=dev)
+            flat = torch.empty((S * max(k_max, 1) * len(self.labels),), dtype=torch.float32, device=dev)
             k_out = N.c_int32(0)
             N.check(L.dsb_streaming_forward(h, self._stream_state, N.ptr(x), k, 1 if is_first else 0,
-                                            1 if is_last else 0, N.ptr(probs), k_out, N.current_stream()),
+                                            1 if is_last else 0, N.ptr(flat), k_out, N.current_stream()),
                     "dsb_streaming_forward")
         if k_out.value == 0:
             return None
-        return probs[:, : k_out.value]
+        C = len(self.labels)
+        return flat[: S * k_out.value * C].view(S, k_out.value, C)
 
     # ------------------------------------------------------------------ (de)serialisation
     @classmethod
