@@ -91,7 +91,7 @@ def main():
             ("gru_bi_c2", "TestModel", dict(rnn_type="gru", rnn_hidden_size=96, rnn_layers=3)),
             ("gru_bi_c3", "DanSpeechPrimary", dict(rnn_type="gru", rnn_hidden_size=80, rnn_layers=2)),
             ("gru_bi_c1", "TestModel", dict(rnn_type="gru", rnn_hidden_size=64, rnn_layers=2, conv_layers=1)),
-            ("lstm_bi_c2", "TestModel", dict(rnn_type="lstm", rnn_hidden_size=72, rnn_layers=2)),
+            ("lstm_bi_c2", "TestModel", dict(rnn_type="lstm", rnn_hidden_size=72, rnn_layers=2, ih_scale=2.5)),
             ("rnn_bi_c2", "TestModel", dict(rnn_type="rnn", rnn_hidden_size=72, rnn_layers=2)),
             ("gru_uni_c2", "TestModel", dict(rnn_type="gru", rnn_hidden_size=96, rnn_layers=2, bidirectional=False,
                                              context=20)),

@@ -217,3 +217,87 @@ def test_primary_shape_bf16_vs_fp32_and_oracle():
     got = dec.decode(p16, s16)[0]
     same = sum(int(a == b) for a, b in zip(got, ref_text))
     print("bf16 greedy transcripts identical to the oracle: %d / %d" % (same, len(ref_text)))
+
+
+# ------------------------------------------------------------------ streaming (BASELINE config 4 path)
+def _stream_chunks(a):
+    # engine chunk schedule: first 8640 samples, then 6240 (Recognizer.py:602-611)
+    chunks = [a[:8640]] + [a[8640 + 6240 * i: 8640 + 6240 * (i + 1)] for i in range(64)]
+    return [c for c in chunks if len(c) > 0]
+
+
+def test_streaming_forward_matches_golden(golden):
+    from danspeech_b200.audio.parsers import InferenceSpectrogramAudioParser
+    m = _model("CPUStreamingRNN", dict(rnn_hidden_size=128, rnn_layers=3), seed=5)
+    a = golden["smodel_audio"].astype(np.float64)
+    chunks = [a[:8640]] + [a[8640 + 6240 * i: 8640 + 6240 * (i + 1)] for i in range(5)]
+    sp = InferenceSpectrogramAudioParser()
+    frames = []
+    for i, c in enumerate(chunks):
+        last = i == len(chunks) - 1
+        s = sp.parse_audio(c, is_last=last)
+        o = m(s.view(1, 1, 161, -1), i == 0, last)
+        ref = golden["smodel_probs_%d" % i]
+        if ref.size == 0:
+            assert o is None
+            frames.append(0)
+        else:
+            assert tuple(o.shape) == ref.shape
+            assert logit_rel_err(o.cpu().numpy(), ref) < FP32_TOL
+            frames.append(o.shape[1])
+    assert frames[:3] == [0, 50, 35]
+
+
+def test_streaming_many_streams_equal_solo_runs():
+    """S lock-step streams with different audio == S solo runs (state is per stream)."""
+    from danspeech_b200.audio.parsers import InferenceSpectrogramAudioParser
+    m = _model("CPUStreamingRNN", dict(rnn_hidden_size=96, rnn_layers=2), seed=6)
+    S = 5
+    auds = [syn.synthetic_audio(8640 + 6240 * 3, seed=70 + i) for i in range(S)]
+    parsers = [InferenceSpectrogramAudioParser() for _ in range(S)]
+    solo = [[] for _ in range(S)]
+    specs = [[] for _ in range(S)]
+    for s in range(S):
+        for i, c in enumerate(_stream_chunks(auds[s])):
+            specs[s].append(parsers[s].parse_audio(c, is_last=(i == 3)))
+    for s in range(S):
+        for i in range(4):
+            o = m(specs[s][i].view(1, 1, 161, -1), i == 0, i == 3)
+            solo[s].append(None if o is None else o.clone())
+    for i in range(4):
+        x = torch.stack([specs[s][i] for s in range(S)]).view(S, 1, 161, -1)
+        o = m(x, i == 0, i == 3)
+        for s in range(S):
+            if solo[s][i] is None:
+                assert o is None
+            else:
+                assert torch.allclose(o[s], solo[s][i][0], rtol=1e-5, atol=1e-7)
+
+
+def test_streaming_transcribe_engine_matches_oracle(golden):
+    from danspeech_b200 import Recognizer
+    from danspeech_b200.pretrained_models import build_model
+    kw = dict(rnn_hidden_size=128, rnn_layers=3)
+    cfg = case_config("CPUStreamingRNN", kw)
+    sd = syn.make_state_dict(seed=5, **cfg)
+    a = golden["smodel_audio"].astype(np.float64)
+    chunks = [a[:8640]] + [a[8640 + 6240 * i: 8640 + 6240 * (i + 1)] for i in range(5)]
+    # oracle pipeline: streaming parser + streaming model + greedy + the reference's stitching rule
+    sp, sm = osp.StreamingSpectrogramOracle(), om.StreamingOracle(sd, cfg["rnn_layers"], context=cfg["context"])
+    expect, it = [], ""
+    for i, c in enumerate(chunks):
+        last = i == len(chunks) - 1
+        o = sm.forward(sp.parse_audio(c, is_last=last).view(1, 1, 161, -1), i == 0, last)
+        part = ""
+        if i > 0:
+            t = og.greedy_decode(o.numpy())[0][0][0]
+            if it and t and it[-1] == t[0]:
+                it, t = it + t[1:], t[1:]
+            else:
+                it += t
+            part = t
+        expect.append(it if last and len(it) > 1 else ("" if last else part))
+    r = Recognizer()
+    r.enable_real_time_streaming(build_model("CPUStreamingRNN", seed=5, **kw).set_precision("fp32"), string_parts=True)
+    got = [r.streaming_transcribe(c, is_last=(i == len(chunks) - 1), is_first=(i == 0)) for i, c in enumerate(chunks)]
+    assert got == expect

@@ -1,0 +1,145 @@
+"""CPU: host-side logic -- state-dict layout, model factories, sharding (incl. a world-size-2 gloo run)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from danspeech_b200 import sharding
+from danspeech_b200.utils import synthetic as syn
+
+
+def test_state_dict_layout_matches_survey_a6():
+    from danspeech_b200.pretrained_models import build_model
+    m = build_model("DanSpeechPrimary", rnn_hidden_size=64)      # narrow: same names / ranks, fast
+    sd = m.state_dict()
+    assert len(sd) == 139                                          # 139 entries for 3 conv + 9 bi-GRU
+    assert tuple(sd["conv.seq_module.0.weight"].shape) == (32, 1, 41, 11)
+    assert tuple(sd["conv.seq_module.3.weight"].shape) == (32, 32, 21, 11)
+    assert tuple(sd["conv.seq_module.6.weight"].shape) == (96, 32, 21, 11)
+    assert tuple(sd["rnns.0.rnn.weight_ih_l0"].shape) == (3 * 64, 2016)
+    assert tuple(sd["rnns.8.rnn.weight_hh_l0_reverse"].shape) == (3 * 64, 64)
+    assert "rnns.0.batch_norm.module.weight" not in sd and "rnns.1.batch_norm.module.running_var" in sd
+    assert tuple(sd["fc.0.module.1.weight"].shape) == (33, 64)
+    full = syn.make_state_dict(**syn.MODEL_SHAPES["TestModel"])
+    assert sum(v.numel() for k, v in full.items() if not k.endswith("num_batches_tracked")
+               and "running" not in k) == 12081168             # SURVEY appendix C parameter count
+
+
+def test_streaming_and_unidirectional_keys():
+    from danspeech_b200.pretrained_models import build_model
+    s = build_model("CPUStreamingRNN", rnn_hidden_size=32, rnn_layers=2)
+    assert "lookahead.conv.weight" in s.state_dict() and s.streaming_model
+    assert tuple(s.state_dict()["rnns.0.rnn.weight_ih_l0"].shape) == (96, 1312)
+    u = build_model("TestModel", rnn_hidden_size=32, rnn_layers=2, bidirectional=False, context=20)
+    assert "lookahead.0.conv.weight" in u.state_dict()
+    assert "rnns.0.rnn.weight_ih_l0_reverse" not in u.state_dict()
+
+
+def test_package_round_trip(tmp_path):
+    from danspeech_b200.deepspeech.model import DeepSpeech
+    from danspeech_b200.pretrained_models import build_model, CustomModel
+    m = build_model("TestModel", rnn_hidden_size=32, rnn_layers=2, seed=4)
+    path = str(tmp_path / "m.pth")
+    torch.save(m.serialize(), path)
+    m2 = CustomModel(path)
+    assert isinstance(m2, DeepSpeech) and m2.rnn_hidden_size == 32 and m2.labels == m.labels
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k])
+
+
+def test_conv_error_and_seq_lens():
+    import torch.nn as nn
+    from danspeech_b200.deepspeech.model import DeepSpeech
+    from danspeech_b200.errors.model_errors import ConvError
+    with pytest.raises(ConvError):
+        DeepSpeech("x", conv_layers=0)
+    with pytest.raises(ConvError):
+        DeepSpeech("x", conv_layers=4)
+    m = DeepSpeech("x", rnn_type=nn.GRU, rnn_hidden_size=16, rnn_layers=1, conv_layers=3)
+    assert m.get_seq_lens(torch.IntTensor([1501, 419, 2, 1])).tolist() == [751, 210, 1, 1]
+
+
+def test_get_model_from_string_quirk():
+    from danspeech_b200 import pretrained_models as pm
+    assert pm.get_model_from_string("nope") is None
+    assert set(syn.MODEL_SHAPES) >= {"DanSpeechPrimary", "TestModel", "Baseline", "CPUStreamingRNN", "GPUStreamingRNN",
+                                     "Folketinget", "TransferLearned", "EnglishLibrispeech"}
+
+
+def test_decoder_helpers_without_gpu():
+    from danspeech_b200.deepspeech.decoder import Decoder
+    d = Decoder(syn.LABELS, blank_index=0)
+    assert d.space_index == 32 and d.int_to_char[27] == "æ"
+    assert d.wer("en to tre", "en tre") == 1 and d.cer("abc", "abd") == 1
+    assert Decoder("_ab").space_index == 3          # out-of-range sentinel (decoder.py:40-43)
+
+
+def test_synthetic_arpa_is_well_formed(tmp_path):
+    p = syn.write_synthetic_arpa(str(tmp_path / "a.arpa"), n_words=50, seed=1, n_bigrams=100, n_trigrams=100)
+    txt = open(p, encoding="utf-8").read()
+    assert txt.startswith("\\data\\") and "\\3-grams:" in txt and txt.rstrip().endswith("\\end\\")
+    assert "ngram 1=53" in txt
+
+
+def test_lpt_shards_and_batches():
+    rng = np.random.default_rng(0)
+    lengths = rng.integers(5 * 16000, 30 * 16000, size=256).tolist()
+    for n in (1, 2, 4, 8):
+        shards = sharding.lpt_shards(lengths, n)
+        assert sorted(i for s in shards for i in s) == list(range(256))
+        loads = [sum(lengths[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(lengths)            # LPT guarantee
+        for s in shards:
+            for b in sharding.make_batches(s, lengths, max_batch=64):
+                assert len(b) <= 64
+                assert all(lengths[b[i]] >= lengths[b[i + 1]] for i in range(len(b) - 1))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(1)
+    recs = [np.zeros(int(n)) for n in rng.integers(100, 3000, size=37)]
+    calls = []
+
+    def fake_recognize(batch):          # stands in for Recognizer.recognize_batch (no GPU here)
+        calls.append(len(batch))
+        assert all(len(batch[i]) >= len(batch[i + 1]) for i in range(len(batch) - 1))
+        return ["len%d" % len(a) for a in batch]
+
+    out = sharding.transcribe_sharded(fake_recognize, recs, rank, world, max_batch=8)
+    q.put((rank, out, sum(calls)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_transcription_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(1)
+    expect = ["len%d" % int(n) for n in rng.integers(100, 3000, size=37)]
+    outs = {r: o for r, o, _ in got}
+    assert outs[0] == expect and outs[1] == expect        # every rank holds the full, ordered result
+    assert sum(n for _, _, n in got) == 37                # disjoint shards covering everything
+    single = sharding.transcribe_sharded(lambda b: ["len%d" % len(a) for a in b],
+                                         [np.zeros(int(n)) for n in np.random.default_rng(1).integers(100, 3000, size=37)])
+    assert single == expect                               # shard invariance: same answer for world size 1
