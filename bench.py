@@ -42,11 +42,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DANSPEECH_B200_PRECISION", "fp32"),
+    ap.add_argument("--precision", default=os.environ.get("DANSPEECH_B200_PRECISION", "bf16"),
                     choices=["fp32", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=1, help="utterances in the cpu_baseline sample")
     ap.add_argument("--ref-batch", type=int, default=8, help="utterances per reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-beam", action="store_true")
     return ap.parse_args()
 
 
@@ -275,6 +276,34 @@ def run_ours(args):
     else:
         n_texts = len(texts)
     e2e_value = audio_s * args.steps / float(te.item())
+
+    # ---- secondary: BASELINE config 3, beam-64 decode with a synthetic 3-gram ARPA LM (utterances/s) ----
+    beam = None
+    if not args.no_beam:
+        import tempfile
+        from danspeech_b200.deepspeech.decoder import BeamCTCDecoder
+        from danspeech_b200.utils import synthetic as syn
+        arpa = os.path.join(tempfile.mkdtemp(prefix="dsb_lm_%d_" % rank), "synthetic3gram.arpa")
+        syn.write_synthetic_arpa(arpa, n_words=2000, seed=0)
+        bdec = BeamCTCDecoder(labels=eng.labels, lm_path=arpa, alpha=1.3, beta=0.2, beam_width=64, num_processes=6,
+                              cutoff_prob=1.0, cutoff_top_n=40, blank_index=eng.labels.index("_"))
+        spect, _ = parser.parse_device(audio_dev, n_dev, n, out=spect_buf)
+        probs, sizes = eng.model(spect.view(BATCH, 1, 161, -1), lengths)
+        bdec.decode_device(probs, sizes)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(args.steps):
+            bdec.decode_device(probs, sizes)
+        b1.record()
+        barrier()
+        tb = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        beam_ms = float(tb.item()) / args.steps
+        beam = {"utt_per_s": BATCH * world / (beam_ms / 1e3), "ms_per_batch": beam_ms, "beam_width": 64,
+                "lm": "synthetic 3-gram ARPA, 2000 words, alpha 1.3, beta 0.2",
+                "rtfx_forward_plus_beam": audio_s / ((ms_max / args.steps + beam_ms) / 1e3)}
     Tp = (1 + n // 160 - 1) // 2 + 1
     d2h = BATCH * (1 + 2 * Tp) * 4
 
@@ -322,7 +351,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": BATCH * n * 4,
                 "d2h_bytes_per_step": d2h, "transcripts": n_texts},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "beam": beam,
     }
     print(json.dumps(line))
     if world > 1:

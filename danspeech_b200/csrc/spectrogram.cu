@@ -11,11 +11,10 @@
 // the lanes with warp shuffles) plus the usual even/odd untangling.  log1p|X| is transposed
 // through shared memory so that global stores are 128-byte rows of the [161, T] output.
 //
-// HBM-bound: algorithmic bytes = 4*n (samples) + 4*161*T (output) per utterance.  The
-// normalisation needs the global mean/std first, so the kernel runs twice: MODE_STATS only
-// reduces (re-reading the audio, which the second pass then finds in L2) and MODE_NORM
-// recomputes and writes the normalised result -- cheaper in DRAM traffic than writing raw
-// values and normalising in place.
+// Algorithmic bytes = 4*n (samples) + 4*161*T (output) per utterance (the HBM roofline the kernel is
+// reported against).  The transform runs in fp64 (see SpecTables) and is instruction-bound, so the FFT
+// is computed exactly once (MODE_RAW writes log1p|X| plus per-tile sum / sum of squares in fp64) and the
+// per-utterance normalisation is a separate elementwise pass over data that is still L2-resident.
 #include "common.cuh"
 #include <math.h>
 #include <mutex>
@@ -292,12 +291,16 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
 }
 
 // mean and biased std per stream from the MODE_RAW partials (numpy np.mean / np.std, parsers.py:148-149)
-__global__ void stream_stats_kernel(const double* __restrict__ partials, int n_partials,
-                                    const int32_t* __restrict__ n_samples, double* __restrict__ stats, int S) {
+// center = 0: streaming chunk (np.mean / biased np.std, parsers.py:148-149) -> stats (f64)
+// center = 1: offline utterance (torch mean / UNBIASED std, parsers.py:66-70) -> f32 (mean, std) stored in the
+//             first 8 bytes of the utterance's partials row (and in mean_std_out when given)
+__global__ void stream_stats_kernel(double* __restrict__ partials, int n_partials,
+                                    const int32_t* __restrict__ n_samples, double* __restrict__ stats, int S,
+                                    int center, int normalize, float* __restrict__ mean_std_out, int64_t audio_stride) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
-  int n = n_samples[s];
-  int n_frames = n >= kNfft ? 1 + (n - kNfft) / kHop : 0;
+  int n = min(n_samples[s], (int)audio_stride);
+  int n_frames = center ? 1 + n / kHop : (n >= kNfft ? 1 + (n - kNfft) / kHop : 0);
   int used = (n_frames + kFT - 1) / kFT;
   double a = 0.0, q = 0.0;
   for (int i = 0; i < used; ++i) {
@@ -306,16 +309,32 @@ __global__ void stream_stats_kernel(const double* __restrict__ partials, int n_p
   }
   double N = (double)n_frames * kBins;
   double mean = N > 0 ? a / N : 0.0;
-  double var = N > 0 ? q / N - mean * mean : 0.0;
-  stats[s * 2 + 0] = mean;
-  stats[s * 2 + 1] = sqrt(var > 0.0 ? var : 0.0);
+  if (!center) {
+    double var = N > 0 ? q / N - mean * mean : 0.0;
+    stats[s * 2 + 0] = mean;
+    stats[s * 2 + 1] = sqrt(var > 0.0 ? var : 0.0);
+  } else {
+    double var = N > 1 ? (q - a * a / N) / (N - 1.0) : 0.0;
+    float m = normalize ? (float)mean : 0.0f;
+    float sd = normalize ? (float)sqrt(var > 0.0 ? var : 0.0) : 1.0f;
+    float* slot = reinterpret_cast<float*>(partials + (int64_t)s * n_partials * 2);
+    slot[0] = m;
+    slot[1] = sd;
+    if (mean_std_out) {
+      mean_std_out[s * 2 + 0] = m;
+      mean_std_out[s * 2 + 1] = sd;
+    }
+  }
 }
 
+// ms_stride: floats between consecutive (mean, std) pairs; frames_from_samples: n_frames holds sample counts
 __global__ void stream_normalize_kernel(float* __restrict__ spect, int64_t out_stride,
-                                        const int32_t* __restrict__ n_frames, const float* __restrict__ mean_std) {
+                                        const int32_t* __restrict__ n_frames, const float* __restrict__ mean_std,
+                                        int64_t ms_stride, int frames_from_samples, int64_t audio_stride) {
   int s = blockIdx.y;
   int nf = n_frames[s];
-  float mean = mean_std[s * 2 + 0], sd = mean_std[s * 2 + 1];
+  if (frames_from_samples) nf = 1 + min(nf, (int)audio_stride) / kHop;
+  float mean = mean_std[s * ms_stride + 0], sd = mean_std[s * ms_stride + 1];
   int64_t total = (int64_t)kBins * out_stride;
   float* p = spect + (int64_t)s * total;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -372,13 +391,25 @@ extern "C" int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, con
   const int tiles_valid = cdiv(max_frames, kFT);
   const int tiles_all = cdiv((int)out_stride, kFT);
   ProfScope scope(ST_SPECT, st);
-  if (normalize) {
-    if (int e = launch_spec<MODE_STATS>(audio, audio_stride, n_samples, B, out, out_stride, mean_std, partials,
-                                        n_partials, tiles_valid, 1, 1, st))
-      return e;
-  }
-  return launch_spec<MODE_NORM>(audio, audio_stride, n_samples, B, out, out_stride, mean_std, partials, n_partials,
-                                tiles_all, 1, normalize, st);
+  (void)tiles_valid;
+  // one fp64 FFT pass writes log1p|X| and per-tile (sum, sum of squares); the normalisation is a cheap
+  // elementwise pass over data that is still in L2 (the FFT is instruction-bound, not HBM-bound, so
+  // recomputing it for the second pass would double the kernel time)
+  if (int e = launch_spec<MODE_RAW>(audio, audio_stride, n_samples, B, out, out_stride, nullptr, partials, n_partials,
+                                    tiles_all, 1, 0, st))
+    return e;
+  if (!normalize) return 0;
+  stream_stats_kernel<<<cdiv(B, 128), 128, 0, st>>>(partials, n_partials, n_samples, nullptr, B, 1, normalize,
+                                                   mean_std, audio_stride);
+  DSB_CHECK_LAUNCH();
+  int64_t total = (int64_t)kBins * out_stride;
+  int64_t gx = cdiv64(total, 1024);
+  if (gx > 256) gx = 256;
+  stream_normalize_kernel<<<dim3((unsigned)gx, B), 256, 0, st>>>(out, out_stride, n_samples,
+                                                                reinterpret_cast<const float*>(partials),
+                                                                (int64_t)n_partials * 4, 1, audio_stride);
+  DSB_CHECK_LAUNCH();
+  return 0;
 }
 
 extern "C" int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int S,
@@ -395,7 +426,8 @@ extern "C" int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stri
   if (int e = launch_spec<MODE_RAW>(audio, audio_stride, n_samples, S, out, out_stride, nullptr, partials,
                                     n_partials, cdiv((int)out_stride, kFT), 0, 0, st))
     return e;
-  stream_stats_kernel<<<cdiv(S, 128), 128, 0, st>>>(partials, n_partials, n_samples, stats, S);
+  stream_stats_kernel<<<cdiv(S, 128), 128, 0, st>>>(partials, n_partials, n_samples, stats, S, 0, 1, nullptr,
+                                                   audio_stride);
   DSB_CHECK_LAUNCH();
   return 0;
 }
@@ -407,7 +439,7 @@ extern "C" int dsb_spectrogram_stream_normalize(float* spect, int64_t out_stride
   int64_t total = (int64_t)kBins * out_stride;
   int64_t gx = cdiv64(total, 256); if (gx > 64) gx = 64;
   dim3 grid((unsigned)gx, S);
-  stream_normalize_kernel<<<grid, 256, 0, st>>>(spect, out_stride, n_frames, mean_std);
+  stream_normalize_kernel<<<grid, 256, 0, st>>>(spect, out_stride, n_frames, mean_std, 2, 0, 0);
   DSB_CHECK_LAUNCH();
   return 0;
 }

@@ -9,7 +9,7 @@ grep -E "passed|failed|Error|error" gpurun_out/pytest.log | tail -15
 echo "== pytest kernels" ; timeout -s KILL 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu > gpurun_out/pytest_kernels.log 2>&1; echo "pytest kernels rc=$?" | tee -a gpurun_out/pytest_kernels.log
 grep -E "passed|failed|Error|error|assert" gpurun_out/pytest_kernels.log | tail -15
 if [ "${BENCH:-1}" = "1" ]; then
-echo "== bench" ; timeout -s KILL 900 python bench.py --steps ${BENCH_STEPS:-2} --warmup 3 --precision ${PRECISION:-fp32} > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
+echo "== bench" ; timeout -s KILL 900 python bench.py --steps ${BENCH_STEPS:-2} --warmup 3 --precision ${PRECISION:-bf16} > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
 fi
 if [ "${NCU:-1}" = "1" ]; then
@@ -17,4 +17,14 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-400} --csv --log-file gpurun_out/launches.csv \
      python scripts/ncu_target.py > gpurun_out/ncu_target.log 2>&1; echo "ncu rc=$?"
   tail -3 gpurun_out/ncu_target.log
+fi
+if [ "${NCU_FULL:-0}" = "1" ]; then
+  echo "== ncu full (top kernels)"
+  timeout -s KILL 900 ncu --set full --clock-control none --import-source on \
+     -k regex:'rnn_tc_kernel|gemm_tc_kernel|conv_tc_kernel|spectrogram_kernel' -c ${NCU_FULL_COUNT:-8} -f -o gpurun_out/prof_top \
+     python scripts/ncu_target.py > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+  tail -2 gpurun_out/ncu_full.log
+fi
+if [ "${SMOKE:-0}" = "1" ]; then
+  echo "== smoke"; timeout -s KILL 300 python __graft_entry__.py smoke 2>&1 | tail -4
 fi
