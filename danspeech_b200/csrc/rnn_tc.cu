@@ -146,16 +146,20 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   const int dir_local = blockIdx.x / p.cpd;
   const int dir = p.dir0 + dir_local;
   const int c = blockIdx.x % p.cpd;
-  // every CTA walks the K chunks in its own rotation so that the 60 CTAs of a direction do not all hit
-  // the same L2 lines of h at the same instant
-  const int kc_rot = (int)(((long long)c * p.nkc) / p.cpd);
+  // Clusters of CL CTAs (same direction) share the h stream: each CTA issues every CL-th chunk as a TMA
+  // multicast into all CL shared memories, which divides the L2 reads of the (hot, 60x re-read) h buffer
+  // and the per-SM TMA issue rate by CL.  Every cluster walks the chunks in its own rotation.
+  const int CL = (int)cluster_nctarank();
+  const int crank = (int)cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  const int kc_rot = (int)(((long long)(c / CL) * p.nkc) / ((p.cpd + CL - 1) / CL));
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_h);
     for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CL);      // one tcgen05.commit from every CTA of the cluster
     }
     mbar_init(wbar, 1);
     mbar_init(dfull, 1);
@@ -164,6 +168,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   if (warp == 1) tmem_alloc<RT_ACC * RT_N>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();    // peers' barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -208,7 +213,10 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           if (!wait_abortable(&empty[stage], phase ^ 1, p.abort_flag)) { ok = false; break; }
           d_empty += clock64() - w0;
           mbar_arrive_expect_tx(&full[stage], (uint32_t)pl.stage_bytes);
-          tma_load_2d(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0);
+          if (CL == 1)
+            tma_load_2d(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0);
+          else if (i % CL == crank)
+            tma_load_2d_mcast(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0, cmask);
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         d_issue += clock64() - c2;
@@ -243,7 +251,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           for (int k = 0; k < RT_BK / 16; ++k)
             umma_bf16(tmem_base + (uint32_t)((k % RT_ACC) * RT_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
                       idesc, (i != 0) || (k >= RT_ACC));
-          umma_commit(&empty[stage]);
+          if (CL == 1) umma_commit(&empty[stage]);
+          else umma_commit_mcast(&empty[stage], cmask);
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         if (ok) umma_commit(dfull);
@@ -406,6 +415,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();    // nobody leaves while a peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<RT_ACC * RT_N>(tmem_base);
@@ -529,10 +539,41 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     DSB_CUDA(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 16 * grid, st));
   }
   p.dbg = dbg;
+  static const int cl_env = getenv("DSB_RNN_CLUSTER") ? atoi(getenv("DSB_RNN_CLUSTER")) : 4;
+  int cl = 1;
+  for (int c2 = cl_env; c2 >= 2; c2 >>= 1)
+    if (cpd % c2 == 0) { cl = c2; break; }
   for (int l = 0; l < launches; ++l) {
     p.dir0 = l * dirs_per_launch;
     void* args[] = {(void*)&tw, (void*)&th, (void*)&p};
-    DSB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RT_THREADS), args, smem, st));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(RT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeCooperative;          // all CTAs co-resident (they spin on each other)
+    attrs[0].val.cooperative = 1;
+    attrs[1].id = cudaLaunchAttributeClusterDimension;
+    attrs[1].val.clusterDim.x = cl;
+    attrs[1].val.clusterDim.y = 1;
+    attrs[1].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = cl > 1 ? 2 : 1;
+    cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
+    if (le != cudaSuccess && cl > 1) {   // cluster + cooperative rejected: fall back to unicast TMA
+      (void)cudaGetLastError();
+      static bool warned = false;
+      if (!warned) {
+        fprintf(stderr, "[danspeech_b200] cluster launch of the recurrence failed (%s); using cluster size 1\n",
+                cudaGetErrorString(le));
+        warned = true;
+      }
+      cfg.numAttrs = 1;
+      le = cudaLaunchKernelExC(&cfg, fn, args);
+    }
+    if (le != cudaSuccess)
+      return set_error(DSB_ERR_CUDA, "rnn_layer_tc: launch failed: %s", cudaGetErrorString(le));
     count_launch();
   }
   if (debug) {
