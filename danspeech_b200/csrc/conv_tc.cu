@@ -83,7 +83,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // tile -> (b, d, t0); frames fastest so that neighbouring CTAs share input rows in L2
   auto decode = [&](int tile, int& b, int& d, int& t0) {
@@ -95,54 +95,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int b, d, t0;
-        decode(tile, b, d, t0);
-        const int kh_lo = max(0, p.pd - p.sd * d), kh_hi = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d);
-        for (int kh = kh_lo; kh <= kh_hi; ++kh) {
-          const int row = p.sd * d + kh - p.pd;
-          for (int kw = 0; kw < p.KW; ++kw) {
-            mbar_wait(&empty[stage], phase ^ 1);
+    // whole warp, warp-uniform control flow; one elected lane issues (see elect_one_sync)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int b, d, t0;
+      decode(tile, b, d, t0);
+      const int kh_lo = max(0, p.pd - p.sd * d), kh_hi = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d);
+      for (int kh = kh_lo; kh <= kh_hi; ++kh) {
+        const int row = p.sd * d + kh - p.pd;
+        for (int kw = 0; kw < p.KW; ++kw) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one_sync()) {
             mbar_arrive_expect_tx(&full[stage], S::A_BYTES + S::B_BYTES);
             tma_load_4d(sA + stage * S::A_STRIDE, &tmap_x, &full[stage], 0, t0 + kw - p.pt, row, b);
             tma_load_2d(sB + stage * S::B_STRIDE, &tmap_w, &full[stage], 0, (kh * p.KW + kw) * NOUT);
-            if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(CV_BM, NOUT);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int b, d, t0;
-        decode(tile, b, d, t0);
-        const int kh_lo = max(0, p.pd - p.sd * d), kh_hi = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d);
-        const int steps = (kh_hi - kh_lo + 1) * p.KW;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = make_idesc_bf16(CV_BM, NOUT);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int b, d, t0;
+      decode(tile, b, d, t0);
+      const int kh_lo = max(0, p.pd - p.sd * d), kh_hi = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d);
+      const int steps = (kh_hi - kh_lo + 1) * p.KW;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+      for (int s = 0; s < steps; ++s) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-        for (int s = 0; s < steps; ++s) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * S::A_STRIDE), 16, SBO, SWZ);
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * S::B_STRIDE), 16, SBO, SWZ);
+        const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * S::A_STRIDE), 16, SBO, SWZ);
+        const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * S::B_STRIDE), 16, SBO, SWZ);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < CIN / 16; ++k)
             umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (s | k) != 0);
           umma_commit(&empty[stage]);
-          if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
+          if (s == steps - 1) umma_commit(&tfull[acc]);
         }
-        umma_commit(&tfull[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     const int q = warp & 3;

@@ -99,56 +99,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    // whole warp, warp-uniform control flow; one elected lane issues (see elect_one_sync)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full[stage], S::A_BYTES + S::B_BYTES);
           tma_load_2d(sA + stage * S::A_BYTES, &tmap_a, &full[stage], kb * BK, m0);
           tma_load_2d(sB + stage * S::B_STRIDE, &tmap_b, &full[stage], kb * BK, n0);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * S::A_BYTES), 16, 1024, 2);
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * S::B_STRIDE), 16, 1024, 2);
+        const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * S::A_BYTES), 16, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * S::B_STRIDE), 16, 1024, 2);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == nkb - 1) umma_commit(&tfull[acc]);
         }
-        umma_commit(&tfull[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else {

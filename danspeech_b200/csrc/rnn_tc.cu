@@ -170,99 +170,113 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   __syncthreads();
   if (CL > 1) cluster_sync_all();    // peers' barriers are initialised before anything arrives on them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ---- TMA producer: whole warp in warp-uniform control flow, one elected lane issues (elect_one_sync) ----
+    if (elect_one_sync()) {
       // resident W_hh slice, loaded once
       mbar_arrive_expect_tx(wbar, (uint32_t)p.nkc * RT_W_BYTES);
       for (int kc = 0; kc < p.nkc; ++kc)
         tma_load_2d(sW + (size_t)kc * RT_W_BYTES, &tmap_w, wbar, kc * RT_BK, (dir * p.cpd + c) * RT_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      const unsigned* ctr = p.counters + dir;
-      unsigned long long d_spin = 0, d_fence = 0, d_issue = 0, d_empty = 0;
-      for (int s = 0; s < p.Tmax && ok; ++s) {
-        long long c0 = clock64();
-        if (s > 0) {
-          // direction-wide barrier: every CTA of this direction has published h_{s-1}
-          const unsigned target = (unsigned)p.cpd * (unsigned)s;
-          long long t0 = 0;
-          unsigned n = 0;
-          while (ld_acquire_gpu(ctr) < target) {
-            if ((++n & 0x3F) == 0) {
-              if (*(volatile int*)p.abort_flag) { ok = false; break; }
-              long long now = clock64();
-              if (t0 == 0) t0 = now;
-              else if (now - t0 > RT_TIMEOUT_CYCLES) { atomicExch(p.abort_flag, 1); ok = false; break; }
-            }
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    bool ok = true;
+    const unsigned* ctr = p.counters + dir;
+    unsigned long long d_spin = 0, d_fence = 0, d_issue = 0, d_empty = 0;
+    for (int s = 0; s < p.Tmax && ok; ++s) {
+      long long c0 = clock64();
+      if (s > 0) {
+        // direction-wide barrier: every CTA of this direction has published h_{s-1}
+        const unsigned target = (unsigned)p.cpd * (unsigned)s;
+        long long t0 = 0;
+        unsigned n = 0;
+        while (ld_acquire_gpu(ctr) < target) {
+          if ((++n & 0x3F) == 0) {
+            if (*(volatile int*)p.abort_flag) { ok = false; break; }
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > RT_TIMEOUT_CYCLES) { atomicExch(p.abort_flag, 1); ok = false; break; }
           }
-          if (!ok) break;
-          long long c1 = clock64();
-          asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
-          d_spin += c1 - c0;
-          d_fence += clock64() - c1;
         }
-        long long c2 = clock64();
-        const int row0 = ((s & 1) * p.dirs + dir) * p.BP;
-        for (int i = 0; i < p.nkc; ++i) {
-          int kc = i + kc_rot;
-          if (kc >= p.nkc) kc -= p.nkc;
-          long long w0 = clock64();
-          if (!wait_abortable(&empty[stage], phase ^ 1, p.abort_flag)) { ok = false; break; }
-          d_empty += clock64() - w0;
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) break;
+        long long c1 = clock64();
+        asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
+        d_spin += c1 - c0;
+        d_fence += clock64() - c1;
+      }
+      long long c2 = clock64();
+      const int row0 = ((s & 1) * p.dirs + dir) * p.BP;
+      for (int i = 0; i < p.nkc; ++i) {
+        int kc = i + kc_rot;
+        if (kc >= p.nkc) kc -= p.nkc;
+        long long w0 = clock64();
+        ok = __all_sync(0xffffffffu, wait_abortable(&empty[stage], phase ^ 1, p.abort_flag));
+        if (!ok) break;
+        d_empty += clock64() - w0;
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full[stage], (uint32_t)pl.stage_bytes);
+          if (p.dbg && s == 100 && i < 24) p.dbg[blockIdx.x * 128 + 16 + i] = clock64();
           if (CL == 1)
             tma_load_2d(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0);
           else if (i % CL == crank)
             tma_load_2d_mcast(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0, cmask);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        d_issue += clock64() - c2;
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg) {
-        p.dbg[blockIdx.x * 16 + 0] = d_spin;
-        p.dbg[blockIdx.x * 16 + 1] = d_fence;
-        p.dbg[blockIdx.x * 16 + 2] = d_issue;
-        p.dbg[blockIdx.x * 16 + 11] = d_empty;
-      }
+      if (p.dbg && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 15] = c2;
+      d_issue += clock64() - c2;
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 128 + 0] = d_spin;
+      p.dbg[blockIdx.x * 128 + 1] = d_fence;
+      p.dbg[blockIdx.x * 128 + 2] = d_issue;
+      p.dbg[blockIdx.x * 128 + 11] = d_empty;
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(p.BP, RT_N);
-      bool ok = wait_abortable(wbar, 0, p.abort_flag);
-      int stage = 0;
-      uint32_t phase = 0;
-      unsigned long long d_wait0 = 0, d_rest = 0, d_waitn = 0;
-      for (int s = 0; s < p.Tmax && ok; ++s) {
-        long long m0 = clock64();
-        for (int i = 0; i < p.nkc; ++i) {
-          int kc = i + kc_rot;
-          if (kc >= p.nkc) kc -= p.nkc;
-          long long w0 = clock64();
-          if (!wait_abortable(&full[stage], phase, p.abort_flag)) { ok = false; break; }
-          if (i == 0) { long long m1 = clock64(); d_wait0 += m1 - m0; m0 = m1; }
-          else d_waitn += clock64() - w0;
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * pl.stage_bytes), 16, 1024, 2);
-          const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)kc * RT_W_BYTES), 16, 1024, 2);
+    // ---- MMA issuer: whole warp waits, one elected lane issues ----
+    const uint32_t idesc = make_idesc_bf16(p.BP, RT_N);
+    bool ok = __all_sync(0xffffffffu, wait_abortable(wbar, 0, p.abort_flag));
+    int stage = 0;
+    uint32_t phase = 0;
+    unsigned long long d_wait0 = 0, d_rest = 0, d_waitn = 0;
+    for (int s = 0; s < p.Tmax && ok; ++s) {
+      long long m0 = clock64();
+      for (int i = 0; i < p.nkc; ++i) {
+        int kc = i + kc_rot;
+        if (kc >= p.nkc) kc -= p.nkc;
+        long long w0 = clock64();
+        ok = __all_sync(0xffffffffu, wait_abortable(&full[stage], phase, p.abort_flag));
+        if (!ok) break;
+        if (i == 0) { long long m1 = clock64(); d_wait0 += m1 - m0; m0 = m1; }
+        else d_waitn += clock64() - w0;
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * pl.stage_bytes), 16, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)kc * RT_W_BYTES), 16, 1024, 2);
+        if (elect_one_sync()) {
+          if (p.dbg && s == 100 && i < 24) p.dbg[blockIdx.x * 128 + 40 + i] = clock64();
 #pragma unroll
           for (int k = 0; k < RT_BK / 16; ++k)
             umma_bf16(tmem_base + (uint32_t)((k % RT_ACC) * RT_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
                       idesc, (i != 0) || (k >= RT_ACC));
           if (CL == 1) umma_commit(&empty[stage]);
           else umma_commit_mcast(&empty[stage], cmask);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          if (i == p.nkc - 1) umma_commit(dfull);
         }
-        if (ok) umma_commit(dfull);
-        d_rest += clock64() - m0;
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg) {
-        p.dbg[blockIdx.x * 16 + 3] = d_wait0;
-        p.dbg[blockIdx.x * 16 + 4] = d_rest;
-        p.dbg[blockIdx.x * 16 + 10] = d_waitn;
-      }
+      if (p.dbg && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 64] = clock64();
+      d_rest += clock64() - m0;
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 128 + 3] = d_wait0;
+      p.dbg[blockIdx.x * 128 + 4] = d_rest;
+      p.dbg[blockIdx.x * 128 + 10] = d_waitn;
     }
   } else {
     // ---- epilogue: 8 warps.  TMEM lane quarter q = warp % 4 holds batch rows [q*rpq, (q+1)*rpq)
@@ -318,6 +332,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       long long e1 = clock64();
       const bool ok = wait_abortable(dfull, (uint32_t)(s & 1), p.abort_flag);
       long long e2 = clock64();
+      if (p.dbg && s == 100 && et == 64) p.dbg[blockIdx.x * 128 + 65] = e2;
       tc_fence_after();
       uint32_t r[32];
       tmem_ld32(t_addr, r);
@@ -382,6 +397,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       named_bar_sync(2, 256);                          // all h stores issued
       long long e4 = clock64();
       if (et == 0) red_release_gpu_add(p.counters + dir, 1u);   // publish h_t (release: cumulative over the CTA)
+      if (p.dbg && s == 99 && et == 0) p.dbg[blockIdx.x * 128 + 66] = clock64();
+      if (p.dbg && s == 100 && et == 0) p.dbg[blockIdx.x * 128 + 67] = clock64();
       // y_t -> global (fp32) after the publish: nobody waits on these stores
       {
         const int n_valid = min(U, p.H - c * U);
@@ -406,11 +423,11 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       e_load += e1 - e0; e_wait += e2 - e1; e_math += e3 - e2; e_bar += e4 - e3; e_pub += clock64() - e4;
     }
     if (p.dbg && et == 64) {   // warp 4: quarter 0, an active row
-      p.dbg[blockIdx.x * 16 + 5] = e_load;
-      p.dbg[blockIdx.x * 16 + 6] = e_wait;
-      p.dbg[blockIdx.x * 16 + 7] = e_math;
-      p.dbg[blockIdx.x * 16 + 8] = e_bar;
-      p.dbg[blockIdx.x * 16 + 9] = e_pub;
+      p.dbg[blockIdx.x * 128 + 5] = e_load;
+      p.dbg[blockIdx.x * 128 + 6] = e_wait;
+      p.dbg[blockIdx.x * 128 + 7] = e_math;
+      p.dbg[blockIdx.x * 128 + 8] = e_bar;
+      p.dbg[blockIdx.x * 128 + 9] = e_pub;
     }
   }
   tc_fence_before();
@@ -485,8 +502,48 @@ int pack_whh_tc(const RnnLayer& L, __nv_bfloat16* out, cudaStream_t st) {
   return 0;
 }
 
+namespace tc {
+// 4 hidden units per thread (H % 4 == 0): float4 loads of both directions, 8-byte bf16 stores
+__global__ void combine_dirs_vec4_kernel(const float* __restrict__ y, int dirs, int T, int B, int H,
+                                         const int32_t* __restrict__ lens, __nv_bfloat16* __restrict__ xb, int ldx,
+                                         float* __restrict__ xf) {
+  const int H4 = H >> 2;
+  const int64_t total4 = (int64_t)T * B * H4;
+  const int64_t dstride4 = total4;
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j4 = (int)(i % H4);
+    const int64_t tb = i / H4;
+    const int b = (int)(tb % B), t = (int)(tb / B);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < lens[b]) {
+      v = y4[i];
+      if (dirs == 2) {
+        const float4 w = y4[i + dstride4];
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
+    }
+    if (xb) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(xb + tb * ldx + j4 * 4) = pk;
+    }
+    if (xf) reinterpret_cast<float4*>(xf)[i] = v;
+  }
+}
+}  // namespace tc
+
 int combine_dirs_tc(const float* y, int dirs, int T, int B, int H, const int32_t* d_len, __nv_bfloat16* xb, int ldx,
                     float* xf, cudaStream_t st) {
+  if ((H & 3) == 0 && (ldx & 3) == 0) {
+    const int64_t total4 = (int64_t)T * B * (H >> 2);
+    tc::combine_dirs_vec4_kernel<<<(int)(cdiv64(total4, 256) < 148 * 16 ? cdiv64(total4, 256) : 148 * 16), 256, 0, st>>>(
+        y, dirs, T, B, H, d_len, xb, ldx, xf);
+    DSB_CHECK_LAUNCH();
+    return 0;
+  }
   const int64_t total = (int64_t)T * B * H;
   tc::combine_dirs_kernel<<<(int)(cdiv64(total, 256) < 148 * 16 ? cdiv64(total, 256) : 148 * 16), 256, 0, st>>>(
       y, dirs, T, B, H, d_len, xb, ldx, xf);
@@ -535,8 +592,8 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   unsigned long long* dbg = nullptr;
   const int grid = dirs_per_launch * cpd;
   if (debug) {
-    DSB_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * 16 * grid));
-    DSB_CUDA(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 16 * grid, st));
+    DSB_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * 128 * grid));
+    DSB_CUDA(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 128 * grid, st));
   }
   p.dbg = dbg;
   static const int cl_env = getenv("DSB_RNN_CLUSTER") ? atoi(getenv("DSB_RNN_CLUSTER")) : 4;
@@ -577,9 +634,9 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     count_launch();
   }
   if (debug) {
-    std::vector<unsigned long long> h(16 * grid);
+    std::vector<unsigned long long> h(128 * grid);
     DSB_CUDA(cudaStreamSynchronize(st));
-    DSB_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * 16 * grid, cudaMemcpyDeviceToHost));
+    DSB_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * 128 * grid, cudaMemcpyDeviceToHost));
     cudaFree(dbg);
     const char* names[12] = {"prod.spin", "prod.fence", "prod.issue", "mma.wait_first", "mma.rest", "epi.gload",
                              "epi.wait_mma", "epi.math_store", "epi.bar", "epi.publish", "mma.wait_rest",
@@ -587,8 +644,18 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     fprintf(stderr, "[rnn_tc debug] H=%d B=%d Tmax=%d grid=%d  cycles/step (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid);
     for (int k = 0; k < 12; ++k) {
       double sum = 0, mx = 0;
-      for (int c = 0; c < grid; ++c) { double v = (double)h[c * 16 + k] / Tmax; sum += v; mx = v > mx ? v : mx; }
+      for (int c = 0; c < grid; ++c) { double v = (double)h[c * 128 + k] / Tmax; sum += v; mx = v > mx ? v : mx; }
       fprintf(stderr, "   %-16s %9.0f | %9.0f\n", names[k], sum / grid, mx);
+    }
+    for (int c = 0; c < grid; c += grid / 2 + 1) {   // step-100 timeline of two CTAs (cycles since this CTA published step 99)
+      const unsigned long long* d = &h[c * 128];
+      const long long t0 = (long long)d[66];
+      fprintf(stderr, "   [cta %d] barrier passed %+lld | tma issue:", c, (long long)d[15] - t0);
+      for (int i = 0; i < nkc && i < 24; ++i) fprintf(stderr, " %lld", (long long)d[16 + i] - t0);
+      fprintf(stderr, "\n   [cta %d] chunk ready:", c);
+      for (int i = 0; i < nkc && i < 24; ++i) fprintf(stderr, " %lld", (long long)d[40 + i] - t0);
+      fprintf(stderr, "\n   [cta %d] mma issued %+lld | epilogue saw dfull %+lld | published %+lld\n", c,
+              (long long)d[64] - t0, (long long)d[65] - t0, (long long)d[67] - t0);
     }
   }
   return 0;

@@ -10,6 +10,20 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a *converged* warp.  tcgen05.mma / tcgen05.commit / cp.async.bulk.tensor are uniform-datapath
+// instructions: issued from a divergent `if (lane == 0)` region the compiler wraps every one of them in a
+// waterfall loop (ELECT + R2UR.BROADCAST + BRA.U.ANY, ~80-380 cycles per instruction, measured with
+// scripts/mma_microbench.py); issued under elect_one_sync() in warp-uniform control flow they cost a few cycles.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
