@@ -29,32 +29,35 @@ namespace tc {
 constexpr int RT_BK = 64;
 constexpr int RT_N = 64;                       // W_hh rows per CTA = 2 halves x 32 columns
 constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk (8 KB)
-constexpr int RT_MAX_STAGES = 8;
-// Consecutive tcgen05.mma into the SAME accumulator serialise on the accumulate dependency (~100 cycles
-// each, measured), which dwarfs the 32 cycles of work of a 64x64x16 MMA.  The four K=16 slices of a chunk
-// therefore go to four independent TMEM accumulators that the epilogue adds up.
-constexpr int RT_ACC = 1;   // measured: 4 accumulators do not help, the MMA is bound by shared-memory operand bandwidth (~64 B/clk), not by the accumulate dependency
+constexpr int RT_GROUP = 4;        // K chunks handled per elected issue region
+constexpr int RT_MAX_GROUPS = 2;   // ring = RT_MAX_GROUPS x RT_GROUP stages
+constexpr int RT_MAX_STAGES = RT_GROUP * RT_MAX_GROUPS;
+// Consecutive tcgen05.mma into the same accumulator do not stall each other (tested with 4 independent
+// accumulators: no change), so a single TMEM accumulator is used.
+constexpr int RT_ACC = 1;
 constexpr int RT_THREADS = 64 + 256;
 constexpr long long RT_TIMEOUT_CYCLES = 4000000000LL;
 constexpr int RT_SMEM_LIMIT = 227 * 1024;
 
-// Shared-memory plan: [W slice: nkc x 8 KB][h ring: stages x BP*128 B][store staging][barriers].
-// The MMA is M = BP (64 or 128 batch rows): with M = 64 only the 64 valid rows are read from shared
-// memory, which matters because the SS-mode MMA is shared-memory-bandwidth bound at N = 64.
+// Shared-memory plan: [W slice: nkc x 8 KB][h ring: groups x 4 stages x BP*128 B][h store staging][barriers].
+// The MMA is M = BP (64 or 128 batch rows): with M = 64 only the 64 valid rows are read from shared memory.
+// Every elected issue region (elect.sync + single-lane branch + reconvergence) costs ~200 cycles on top
+// of ~35 cycles per tcgen05.mma / TMA instruction (scripts/mma_microbench.py), so the producer and the MMA
+// warp work in groups of RT_GROUP chunks: one region issues 4 TMA loads, one region issues 16 MMAs.
 struct RtPlan {
-  int stages, stage_bytes, stage_off, stg_off, bar_off, total;
+  int groups, stage_bytes, stage_off, stg_off, bar_off, total;
 };
 __host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U) {
   RtPlan pl;
   pl.stage_bytes = BP * RT_BK * 2;
   const int w_bytes = nkc * RT_W_BYTES;
-  const int stg = 2 * BP * U * (2 + 4);          // double-buffered h (bf16) + y (fp32) staging
+  const int stg = BP * U * 2;                    // h (bf16) staging for coalesced stores
   const int stg_al = (stg + 1023) / 1024 * 1024;
-  int stages = (RT_SMEM_LIMIT - 2048 - 256 - w_bytes - stg_al) / pl.stage_bytes;   // 1 KB align slack + 1 KB static
-  if (stages > RT_MAX_STAGES) stages = RT_MAX_STAGES;
-  pl.stages = stages;
+  int groups = (RT_SMEM_LIMIT - 2048 - 256 - w_bytes - stg_al) / (pl.stage_bytes * RT_GROUP);   // 1 KB align slack + 1 KB static
+  if (groups > RT_MAX_GROUPS) groups = RT_MAX_GROUPS;
+  pl.groups = groups;
   pl.stage_off = w_bytes;
-  pl.stg_off = w_bytes + stages * pl.stage_bytes;
+  pl.stg_off = w_bytes + groups * RT_GROUP * pl.stage_bytes;
   pl.bar_off = pl.stg_off + stg_al;
   pl.total = pl.bar_off + 256 + 1024;
   return pl;
@@ -135,20 +138,20 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   unsigned char* sW = smem;
   unsigned char* sA = smem + pl.stage_off;
   unsigned char* sStg = smem + pl.stg_off;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
-  uint64_t* empty = full + RT_MAX_STAGES;
-  uint64_t* wbar = empty + RT_MAX_STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.bar_off);   // [RT_MAX_STAGES] per chunk stage (TMA tx)
+  uint64_t* gempty = full + RT_MAX_STAGES;                           // [RT_MAX_GROUPS] group consumed by the MMAs
+  uint64_t* wbar = gempty + RT_MAX_GROUPS;
   uint64_t* dfull = wbar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
-  const int n_stages = pl.stages;
+  const int n_groups = pl.groups;
+  const int gps = (p.nkc + RT_GROUP - 1) / RT_GROUP;   // group uses per step
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dir_local = blockIdx.x / p.cpd;
   const int dir = p.dir0 + dir_local;
   const int c = blockIdx.x % p.cpd;
-  // Clusters of CL CTAs (same direction) share the h stream: each CTA issues every CL-th chunk as a TMA
-  // multicast into all CL shared memories, which divides the L2 reads of the (hot, 60x re-read) h buffer
-  // and the per-SM TMA issue rate by CL.  Every cluster walks the chunks in its own rotation.
+  // Optional clusters of CL CTAs (same direction) share the h stream by TMA multicast; every cluster (or
+  // CTA) walks the K chunks in its own rotation so that the readers do not hit the same L2 lines together.
   const int CL = (int)cluster_nctarank();
   const int crank = (int)cluster_ctarank();
   const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
@@ -157,15 +160,13 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_h);
-    for (int i = 0; i < n_stages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], CL);      // one tcgen05.commit from every CTA of the cluster
-    }
+    for (int i = 0; i < RT_MAX_STAGES; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < RT_MAX_GROUPS; ++i) mbar_init(&gempty[i], CL);   // one commit from every CTA of the cluster
     mbar_init(wbar, 1);
     mbar_init(dfull, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<RT_ACC * RT_N>(tmem_slot);
+  if (warp == 1) tmem_alloc<64>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();    // peers' barriers are initialised before anything arrives on them
@@ -181,11 +182,10 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         tma_load_2d(sW + (size_t)kc * RT_W_BYTES, &tmap_w, wbar, kc * RT_BK, (dir * p.cpd + c) * RT_N);
     }
     __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
     bool ok = true;
     const unsigned* ctr = p.counters + dir;
     unsigned long long d_spin = 0, d_fence = 0, d_issue = 0, d_empty = 0;
+    long long use = 0;   // group uses so far (ring position)
     for (int s = 0; s < p.Tmax && ok; ++s) {
       long long c0 = clock64();
       if (s > 0) {
@@ -209,26 +209,31 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         d_fence += clock64() - c1;
       }
       long long c2 = clock64();
+      if (p.dbg && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 15] = c2;
       const int row0 = ((s & 1) * p.dirs + dir) * p.BP;
-      for (int i = 0; i < p.nkc; ++i) {
-        int kc = i + kc_rot;
-        if (kc >= p.nkc) kc -= p.nkc;
+      for (int g = 0; g < gps; ++g, ++use) {
+        const int grp = (int)(use % n_groups);
+        const uint32_t gphase = (uint32_t)((use / n_groups) & 1);
         long long w0 = clock64();
-        ok = __all_sync(0xffffffffu, wait_abortable(&empty[stage], phase ^ 1, p.abort_flag));
+        ok = __all_sync(0xffffffffu, wait_abortable(&gempty[grp], gphase ^ 1, p.abort_flag));
         if (!ok) break;
         d_empty += clock64() - w0;
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)pl.stage_bytes);
-          if (p.dbg && s == 100 && i < 24) p.dbg[blockIdx.x * 128 + 16 + i] = clock64();
-          if (CL == 1)
-            tma_load_2d(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0);
-          else if (i % CL == crank)
-            tma_load_2d_mcast(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0, cmask);
+          const int i0 = g * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
+          for (int i = i0; i < i1; ++i) {
+            int kc = i + kc_rot;
+            if (kc >= p.nkc) kc -= p.nkc;
+            const int stage = grp * RT_GROUP + (i - i0);
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)pl.stage_bytes);
+            if (CL == 1)
+              tma_load_2d(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0);
+            else if (i % CL == crank)
+              tma_load_2d_mcast(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0, cmask);
+          }
+          if (p.dbg && s == 100 && g < 8) p.dbg[blockIdx.x * 128 + 16 + g] = clock64();
         }
         __syncwarp();
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 15] = c2;
       d_issue += clock64() - c2;
     }
     if (p.dbg && lane == 0) {
@@ -238,37 +243,40 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       p.dbg[blockIdx.x * 128 + 11] = d_empty;
     }
   } else if (warp == 1) {
-    // ---- MMA issuer: whole warp waits, one elected lane issues ----
+    // ---- MMA issuer: whole warp waits for the chunks of a group, one elected lane issues its 16 MMAs ----
     const uint32_t idesc = make_idesc_bf16(p.BP, RT_N);
     bool ok = __all_sync(0xffffffffu, wait_abortable(wbar, 0, p.abort_flag));
-    int stage = 0;
-    uint32_t phase = 0;
     unsigned long long d_wait0 = 0, d_rest = 0, d_waitn = 0;
+    long long use = 0;
     for (int s = 0; s < p.Tmax && ok; ++s) {
       long long m0 = clock64();
-      for (int i = 0; i < p.nkc; ++i) {
-        int kc = i + kc_rot;
-        if (kc >= p.nkc) kc -= p.nkc;
+      for (int g = 0; g < gps; ++g, ++use) {
+        const int grp = (int)(use % n_groups);
+        const uint32_t fphase = (uint32_t)((use / n_groups) & 1);
+        const int i0 = g * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
         long long w0 = clock64();
-        ok = __all_sync(0xffffffffu, wait_abortable(&full[stage], phase, p.abort_flag));
+        for (int i = i0; i < i1 && ok; ++i)
+          ok = __all_sync(0xffffffffu, wait_abortable(&full[grp * RT_GROUP + (i - i0)], fphase, p.abort_flag));
         if (!ok) break;
-        if (i == 0) { long long m1 = clock64(); d_wait0 += m1 - m0; m0 = m1; }
+        if (g == 0) { long long m1 = clock64(); d_wait0 += m1 - m0; m0 = m1; }
         else d_waitn += clock64() - w0;
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * pl.stage_bytes), 16, 1024, 2);
-        const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)kc * RT_W_BYTES), 16, 1024, 2);
         if (elect_one_sync()) {
-          if (p.dbg && s == 100 && i < 24) p.dbg[blockIdx.x * 128 + 40 + i] = clock64();
+          if (p.dbg && s == 100 && g < 8) p.dbg[blockIdx.x * 128 + 40 + g] = clock64();
+          for (int i = i0; i < i1; ++i) {
+            int kc = i + kc_rot;
+            if (kc >= p.nkc) kc -= p.nkc;
+            const uint64_t adesc = make_smem_desc(smem_u32(sA + (grp * RT_GROUP + (i - i0)) * pl.stage_bytes), 16, 1024, 2);
+            const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)kc * RT_W_BYTES), 16, 1024, 2);
 #pragma unroll
-          for (int k = 0; k < RT_BK / 16; ++k)
-            umma_bf16(tmem_base + (uint32_t)((k % RT_ACC) * RT_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2),
-                      idesc, (i != 0) || (k >= RT_ACC));
-          if (CL == 1) umma_commit(&empty[stage]);
-          else umma_commit_mcast(&empty[stage], cmask);
-          if (i == p.nkc - 1) umma_commit(dfull);
+            for (int k = 0; k < RT_BK / 16; ++k)
+              umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) != 0);
+          }
+          if (CL == 1) umma_commit(&gempty[grp]);
+          else umma_commit_mcast(&gempty[grp], cmask);
+          if (g == gps - 1) umma_commit(dfull);
         }
         __syncwarp();
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
       if (p.dbg && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 64] = clock64();
       d_rest += clock64() - m0;
@@ -298,17 +306,16 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       bhn[u] = (GATES == 3 && p.b_hn && j0 + u < p.H) ? p.b_hn[(size_t)dir * p.H + j0 + u] : 0.f;
     }
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
-    // store staging (double buffered by step parity): sH [2][BP][U] bf16, sY [2][BP][U] fp32, sT [2][BP] int
+    // h store staging sH [BP][U] bf16 + row validity sT [BP].  Single-buffered: the next write happens after
+    // this CTA's publish of the step (behind the second named barrier), i.e. after every read of it.
     __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(sStg);
-    float* sY = reinterpret_cast<float*>(sStg + 2 * p.BP * U * 2);
-    __shared__ int sT[2][128];
+    __shared__ int sT[128];
     const bool vec2 = ((p.H & 1) == 0) && ((UH & 1) == 0);
     unsigned long long e_load = 0, e_wait = 0, e_math = 0, e_bar = 0, e_pub = 0;
     for (int s = 0; s < p.Tmax; ++s) {
       long long e0 = clock64();
       const bool active = row_ok && s < len;
       const int t = dir == 0 ? s : len - 1 - s;
-      const int par = s & 1;
       float gxv[GATES][UH];
       if (active) {
         const float* gp = p.gx + ((size_t)t * p.B + b) * ncol + (size_t)dir * GATES * p.H + j0;
@@ -328,7 +335,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             for (int u = 0; u < UH; ++u) gxv[g][u] = (j0 + u < p.H) ? __ldg(gp + (size_t)g * p.H + u) : 0.f;
         }
       }
-      if (half == 0 && lane < rpq) sT[par][q * rpq + lane] = active ? t : -1;
+      if (half == 0 && lane < rpq) sT[q * rpq + lane] = active ? t : -1;
       long long e1 = clock64();
       const bool ok = wait_abortable(dfull, (uint32_t)(s & 1), p.abort_flag);
       long long e2 = clock64();
@@ -347,8 +354,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       }
       tc_fence_before();
       if (ok && active) {
-        __nv_bfloat16* sh = sH + ((size_t)par * p.BP + b) * U + half * UH;
-        float* sy = sY + ((size_t)par * p.BP + b) * U + half * UH;
+        __nv_bfloat16* sh = sH + (size_t)b * U + half * UH;
 #pragma unroll
         for (int u = 0; u < UH; ++u) {
           float hn;
@@ -368,7 +374,6 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             hn = fast_tanh(gxv[0][u] + __uint_as_float(r[u]));
           }
           hprev[u] = hn;
-          sy[u] = hn;
           sh[u] = __float2bfloat16_rn(hn);
         }
       }
@@ -383,14 +388,14 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           const int per_row = U / 4;                   // 8-byte pieces
           for (int i = et; i < p.BP * per_row; i += 256) {
             const int row = i / per_row, part = i - row * per_row;
-            if (sT[par][row] >= 0)
+            if (sT[row] >= 0)
               *reinterpret_cast<uint2*>(hrow0 + (size_t)row * p.HP + part * 4) =
-                  *reinterpret_cast<const uint2*>(sH + ((size_t)par * p.BP + row) * U + part * 4);
+                  *reinterpret_cast<const uint2*>(sH + (size_t)row * U + part * 4);
           }
         } else {
           for (int i = et; i < p.BP * U; i += 256) {
             const int row = i / U, u = i - row * U;
-            if (sT[par][row] >= 0 && u < n_valid) hrow0[(size_t)row * p.HP + u] = sH[((size_t)par * p.BP + row) * U + u];
+            if (sT[row] >= 0 && u < n_valid) hrow0[(size_t)row * p.HP + u] = sH[(size_t)row * U + u];
           }
         }
       }
@@ -399,25 +404,17 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       if (et == 0) red_release_gpu_add(p.counters + dir, 1u);   // publish h_t (release: cumulative over the CTA)
       if (p.dbg && s == 99 && et == 0) p.dbg[blockIdx.x * 128 + 66] = clock64();
       if (p.dbg && s == 100 && et == 0) p.dbg[blockIdx.x * 128 + 67] = clock64();
-      // y_t -> global (fp32) after the publish: nobody waits on these stores
-      {
-        const int n_valid = min(U, p.H - c * U);
-        float* ybase = p.y + (size_t)dir * p.T * p.B * p.H + c * U;
-        if ((U & 3) == 0 && n_valid == U && (p.H & 3) == 0) {
-          const int per_row = U / 4;                   // float4 pieces
-          for (int i = et; i < p.BP * per_row; i += 256) {
-            const int row = i / per_row, part = i - row * per_row;
-            const int tt = sT[par][row];
-            if (tt >= 0)
-              *reinterpret_cast<float4*>(ybase + ((size_t)tt * p.B + row) * p.H + part * 4) =
-                  *reinterpret_cast<const float4*>(sY + ((size_t)par * p.BP + row) * U + part * 4);
-          }
+      // y_t -> global (fp32) straight from registers, after the publish: nobody waits on these stores
+      if (ok && active) {
+        float* yo = p.y + (((size_t)dir * p.T + t) * p.B + b) * p.H + j0;
+        if ((UH & 1) == 0 && (p.H & 1) == 0 && j0 + UH <= p.H) {
+#pragma unroll
+          for (int u = 0; u < UH; u += 2)
+            *reinterpret_cast<float2*>(yo + u) = make_float2(hprev[u], hprev[u + 1 < UH ? u + 1 : u]);
         } else {
-          for (int i = et; i < p.BP * U; i += 256) {
-            const int row = i / U, u = i - row * U;
-            const int tt = sT[par][row];
-            if (tt >= 0 && u < n_valid) ybase[((size_t)tt * p.B + row) * p.H + u] = sY[((size_t)par * p.BP + row) * U + u];
-          }
+#pragma unroll
+          for (int u = 0; u < UH; ++u)
+            if (j0 + u < p.H) yo[u] = hprev[u];
         }
       }
       e_load += e1 - e0; e_wait += e2 - e1; e_math += e3 - e2; e_bar += e4 - e3; e_pub += clock64() - e4;
@@ -487,7 +484,7 @@ bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* laun
   const int cpd = cdiv(L.H, U);
   const int HP = (L.H + 63) / 64 * 64;
   const tc::RtPlan pl = tc::rt_plan(HP / 64, B <= 64 ? 64 : 128, U);
-  if (B > 128 || pl.stages < 2 || pl.total > tc::RT_SMEM_LIMIT || cpd > sms) return false;
+  if (B > 128 || pl.groups < 1 || pl.total > tc::RT_SMEM_LIMIT || cpd > sms) return false;
   if (cpd_out) *cpd_out = cpd;
   if (launches_out) *launches_out = (L.dirs * cpd <= sms) ? 1 : L.dirs;
   return true;
@@ -650,10 +647,10 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     for (int c = 0; c < grid; c += grid / 2 + 1) {   // step-100 timeline of two CTAs (cycles since this CTA published step 99)
       const unsigned long long* d = &h[c * 128];
       const long long t0 = (long long)d[66];
-      fprintf(stderr, "   [cta %d] barrier passed %+lld | tma issue:", c, (long long)d[15] - t0);
-      for (int i = 0; i < nkc && i < 24; ++i) fprintf(stderr, " %lld", (long long)d[16 + i] - t0);
-      fprintf(stderr, "\n   [cta %d] chunk ready:", c);
-      for (int i = 0; i < nkc && i < 24; ++i) fprintf(stderr, " %lld", (long long)d[40 + i] - t0);
+      fprintf(stderr, "   [cta %d] barrier passed %+lld | tma group issued:", c, (long long)d[15] - t0);
+      for (int i = 0; i < (nkc + RT_GROUP - 1) / RT_GROUP && i < 8; ++i) fprintf(stderr, " %lld", (long long)d[16 + i] - t0);
+      fprintf(stderr, "\n   [cta %d] group ready:", c);
+      for (int i = 0; i < (nkc + RT_GROUP - 1) / RT_GROUP && i < 8; ++i) fprintf(stderr, " %lld", (long long)d[40 + i] - t0);
       fprintf(stderr, "\n   [cta %d] mma issued %+lld | epilogue saw dfull %+lld | published %+lld\n", c,
               (long long)d[64] - t0, (long long)d[65] - t0, (long long)d[67] - t0);
     }
