@@ -230,6 +230,9 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             else if (i % CL == crank)
               tma_load_2d_mcast(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0, cmask);
           }
+          // a partial last group: complete the phase of its unused stages so that all full barriers of a
+          // group stay in lock-step (the MMA warp always waits on all RT_GROUP of them)
+          for (int j = i1 - i0; j < RT_GROUP; ++j) mbar_arrive(&full[grp * RT_GROUP + j]);
           if (p.dbg && s == 100 && g < 8) p.dbg[blockIdx.x * 128 + 16 + g] = clock64();
         }
         __syncwarp();
@@ -255,8 +258,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         const uint32_t fphase = (uint32_t)((use / n_groups) & 1);
         const int i0 = g * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
         long long w0 = clock64();
-        for (int i = i0; i < i1 && ok; ++i)
-          ok = __all_sync(0xffffffffu, wait_abortable(&full[grp * RT_GROUP + (i - i0)], fphase, p.abort_flag));
+        for (int j = 0; j < RT_GROUP && ok; ++j)
+          ok = __all_sync(0xffffffffu, wait_abortable(&full[grp * RT_GROUP + j], fphase, p.abort_flag));
         if (!ok) break;
         if (g == 0) { long long m1 = clock64(); d_wait0 += m1 - m0; m0 = m1; }
         else d_waitn += clock64() - w0;
