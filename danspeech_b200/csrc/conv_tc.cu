@@ -20,7 +20,7 @@ namespace dsb {
 namespace tc {
 
 constexpr int CV_BM = 128;
-constexpr int CV_STAGES = 8;
+constexpr int CV_GROUP = 4;     // (kh, kw) steps per elected issue region (~200 cycles fixed cost per region)
 constexpr int CV_THREADS = 192;
 
 struct ConvTcParams {
@@ -39,7 +39,9 @@ struct ConvSmem {
   static constexpr int B_BYTES = NOUT * ROW;
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;
-  static constexpr int BAR_OFF = CV_STAGES * (A_STRIDE + B_STRIDE);
+  static constexpr int GROUPS = NOUT <= 32 ? 4 : 3;                 // ring depth in groups
+  static constexpr int STAGES = GROUPS * CV_GROUP;
+  static constexpr int BAR_OFF = STAGES * (A_STRIDE + B_STRIDE);
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
@@ -55,10 +57,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;
-  unsigned char* sB = smem + CV_STAGES * S::A_STRIDE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-  uint64_t* empty = full + CV_STAGES;
-  uint64_t* tfull = empty + CV_STAGES;
+  unsigned char* sB = smem + S::STAGES * S::A_STRIDE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // one per group
+  uint64_t* empty = full + S::GROUPS;
+  uint64_t* tfull = empty + S::GROUPS;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -69,7 +71,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
     prefetch_tmap(&tmap_w);
-    for (int i = 0; i < CV_STAGES; ++i) {
+    for (int i = 0; i < S::GROUPS; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -95,30 +97,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   };
 
   if (warp == 0) {
-    // whole warp, warp-uniform control flow; one elected lane issues (see elect_one_sync)
-    int stage = 0;
+    // whole warp, warp-uniform control flow; one elected lane issues a group of steps (see elect_one_sync)
+    int grp = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       int b, d, t0;
       decode(tile, b, d, t0);
       const int kh_lo = max(0, p.pd - p.sd * d), kh_hi = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d);
-      for (int kh = kh_lo; kh <= kh_hi; ++kh) {
-        const int row = p.sd * d + kh - p.pd;
-        for (int kw = 0; kw < p.KW; ++kw) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&full[stage], S::A_BYTES + S::B_BYTES);
-            tma_load_4d(sA + stage * S::A_STRIDE, &tmap_x, &full[stage], 0, t0 + kw - p.pt, row, b);
-            tma_load_2d(sB + stage * S::B_STRIDE, &tmap_w, &full[stage], 0, (kh * p.KW + kw) * NOUT);
+      const int steps = (kh_hi - kh_lo + 1) * p.KW;
+      for (int s0 = 0; s0 < steps; s0 += CV_GROUP) {
+        const int n = min(CV_GROUP, steps - s0);
+        mbar_wait(&empty[grp], phase ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full[grp], (uint32_t)n * (S::A_BYTES + S::B_BYTES));
+          for (int j = 0; j < n; ++j) {
+            const int st = s0 + j;
+            const int kh = kh_lo + st / p.KW, kw = st - (st / p.KW) * p.KW;
+            const int stage = grp * CV_GROUP + j;
+            tma_load_4d(sA + stage * S::A_STRIDE, &tmap_x, &full[grp], 0, t0 + kw - p.pt, p.sd * d + kh - p.pd, b);
+            tma_load_2d(sB + stage * S::B_STRIDE, &tmap_w, &full[grp], 0, (kh * p.KW + kw) * NOUT);
           }
-          __syncwarp();
-          if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++grp == S::GROUPS) { grp = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(CV_BM, NOUT);
-    int stage = 0;
+    int grp = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -130,20 +136,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-      for (int s = 0; s < steps; ++s) {
-        mbar_wait(&full[stage], phase);
+      for (int s0 = 0; s0 < steps; s0 += CV_GROUP) {
+        const int n = min(CV_GROUP, steps - s0);
+        mbar_wait(&full[grp], phase);
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * S::A_STRIDE), 16, SBO, SWZ);
-        const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * S::B_STRIDE), 16, SBO, SWZ);
         if (elect_one_sync()) {
+          for (int j = 0; j < n; ++j) {
+            const int stage = grp * CV_GROUP + j;
+            const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * S::A_STRIDE), 16, SBO, SWZ);
+            const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * S::B_STRIDE), 16, SBO, SWZ);
 #pragma unroll
-          for (int k = 0; k < CIN / 16; ++k)
-            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (s | k) != 0);
-          umma_commit(&empty[stage]);
-          if (s == steps - 1) umma_commit(&tfull[acc]);
+            for (int k = 0; k < CIN / 16; ++k)
+              umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, ((s0 + j) | k) != 0);
+          }
+          umma_commit(&empty[grp]);
+          if (s0 + n >= steps) umma_commit(&tfull[acc]);
         }
         __syncwarp();
-        if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
+        if (++grp == S::GROUPS) { grp = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

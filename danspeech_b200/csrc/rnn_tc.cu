@@ -186,8 +186,46 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     const unsigned* ctr = p.counters + dir;
     unsigned long long d_spin = 0, d_fence = 0, d_issue = 0, d_empty = 0;
     long long use = 0;   // group uses so far (ring position)
+    // Arming a group (waiting for its slot, arrive.expect_tx on its stages) does not depend on h, so the first
+    // `n_groups` groups of a step are armed BEFORE the step barrier is polled; after the barrier only the
+    // proxy fence and the TMA issues remain on the critical path.
+    auto arm_group = [&](long long u, int g) -> bool {
+      const int grp = (int)(u % n_groups);
+      const uint32_t gphase = (uint32_t)((u / n_groups) & 1);
+      if (!__all_sync(0xffffffffu, wait_abortable(&gempty[grp], gphase ^ 1, p.abort_flag))) return false;
+      if (elect_one_sync()) {
+        const int i0 = g * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
+        for (int j = 0; j < RT_GROUP; ++j) {
+          if (j < i1 - i0) mbar_arrive_expect_tx(&full[grp * RT_GROUP + j], (uint32_t)pl.stage_bytes);
+          else mbar_arrive(&full[grp * RT_GROUP + j]);   // unused stage of a partial group: keep phases in lock-step
+        }
+      }
+      __syncwarp();
+      return true;
+    };
+    auto load_group = [&](long long u, int g, int row0) {
+      const int grp = (int)(u % n_groups);
+      if (elect_one_sync()) {
+        const int i0 = g * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
+        for (int i = i0; i < i1; ++i) {
+          int kc = i + kc_rot;
+          if (kc >= p.nkc) kc -= p.nkc;
+          const int stage = grp * RT_GROUP + (i - i0);
+          if (CL == 1)
+            tma_load_2d(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0);
+          else if (i % CL == crank)
+            tma_load_2d_mcast(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0, cmask);
+        }
+      }
+      __syncwarp();
+    };
     for (int s = 0; s < p.Tmax && ok; ++s) {
       long long c0 = clock64();
+      const int pre = min(gps, n_groups);
+      for (int g = 0; g < pre && ok; ++g) ok = arm_group(use + g, g);
+      if (!ok) break;
+      d_empty += clock64() - c0;
+      c0 = clock64();
       if (s > 0) {
         // direction-wide barrier: every CTA of this direction has published h_{s-1}
         const unsigned target = (unsigned)p.cpd * (unsigned)s;
@@ -211,32 +249,17 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       long long c2 = clock64();
       if (p.dbg && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 15] = c2;
       const int row0 = ((s & 1) * p.dirs + dir) * p.BP;
-      for (int g = 0; g < gps; ++g, ++use) {
-        const int grp = (int)(use % n_groups);
-        const uint32_t gphase = (uint32_t)((use / n_groups) & 1);
-        long long w0 = clock64();
-        ok = __all_sync(0xffffffffu, wait_abortable(&gempty[grp], gphase ^ 1, p.abort_flag));
-        if (!ok) break;
-        d_empty += clock64() - w0;
-        if (elect_one_sync()) {
-          const int i0 = g * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
-          for (int i = i0; i < i1; ++i) {
-            int kc = i + kc_rot;
-            if (kc >= p.nkc) kc -= p.nkc;
-            const int stage = grp * RT_GROUP + (i - i0);
-            mbar_arrive_expect_tx(&full[stage], (uint32_t)pl.stage_bytes);
-            if (CL == 1)
-              tma_load_2d(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0);
-            else if (i % CL == crank)
-              tma_load_2d_mcast(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0, cmask);
-          }
-          // a partial last group: complete the phase of its unused stages so that all full barriers of a
-          // group stay in lock-step (the MMA warp always waits on all RT_GROUP of them)
-          for (int j = i1 - i0; j < RT_GROUP; ++j) mbar_arrive(&full[grp * RT_GROUP + j]);
-          if (p.dbg && s == 100 && g < 8) p.dbg[blockIdx.x * 128 + 16 + g] = clock64();
+      for (int g = 0; g < gps && ok; ++g) {
+        if (g >= pre) {
+          long long w0 = clock64();
+          ok = arm_group(use + g, g);
+          d_empty += clock64() - w0;
+          if (!ok) break;
         }
-        __syncwarp();
+        load_group(use + g, g, row0);
+        if (p.dbg && s == 100 && g < 8 && lane == 0) p.dbg[blockIdx.x * 128 + 16 + g] = clock64();
       }
+      use += gps;
       d_issue += clock64() - c2;
     }
     if (p.dbg && lane == 0) {
