@@ -138,8 +138,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   unsigned char* sW = smem;
   unsigned char* sA = smem + pl.stage_off;
   unsigned char* sStg = smem + pl.stg_off;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.bar_off);   // [RT_MAX_STAGES] per chunk stage (TMA tx)
-  uint64_t* gempty = full + RT_MAX_STAGES;                           // [RT_MAX_GROUPS] group consumed by the MMAs
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.bar_off);   // [RT_MAX_GROUPS] group landed (TMA tx)
+  uint64_t* gempty = full + RT_MAX_GROUPS;                           // [RT_MAX_GROUPS] group consumed by the MMAs
   uint64_t* wbar = gempty + RT_MAX_GROUPS;
   uint64_t* dfull = wbar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
@@ -155,12 +155,12 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   const int CL = (int)cluster_nctarank();
   const int crank = (int)cluster_ctarank();
   const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
-  const int kc_rot = (int)(((long long)(c / CL) * p.nkc) / ((p.cpd + CL - 1) / CL));
+  const int g_rot = (int)(((long long)(c / CL) * gps) / ((p.cpd + CL - 1) / CL));   // rotation in whole groups
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_h);
-    for (int i = 0; i < RT_MAX_STAGES; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < RT_MAX_GROUPS; ++i) mbar_init(&full[i], 1);
     for (int i = 0; i < RT_MAX_GROUPS; ++i) mbar_init(&gempty[i], CL);   // one commit from every CTA of the cluster
     mbar_init(wbar, 1);
     mbar_init(dfull, 1);
@@ -189,33 +189,27 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     // Arming a group (waiting for its slot, arrive.expect_tx on its stages) does not depend on h, so the first
     // `n_groups` groups of a step are armed BEFORE the step barrier is polled; after the barrier only the
     // proxy fence and the TMA issues remain on the critical path.
+    // One TMA per group: the h buffer is mapped as a 3-D tensor {64 k, BP rows, nkc chunks}, so a box
+    // {64, BP, RT_GROUP} lands as RT_GROUP consecutive 128B-swizzled K-chunk tiles (a TMA instruction costs
+    // ~240 cycles of issue; chunks beyond nkc are zero-filled and never used by the MMAs).
     auto arm_group = [&](long long u, int g) -> bool {
+      (void)g;
       const int grp = (int)(u % n_groups);
       const uint32_t gphase = (uint32_t)((u / n_groups) & 1);
       if (!__all_sync(0xffffffffu, wait_abortable(&gempty[grp], gphase ^ 1, p.abort_flag))) return false;
-      if (elect_one_sync()) {
-        const int i0 = g * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
-        for (int j = 0; j < RT_GROUP; ++j) {
-          if (j < i1 - i0) mbar_arrive_expect_tx(&full[grp * RT_GROUP + j], (uint32_t)pl.stage_bytes);
-          else mbar_arrive(&full[grp * RT_GROUP + j]);   // unused stage of a partial group: keep phases in lock-step
-        }
-      }
+      if (elect_one_sync()) mbar_arrive_expect_tx(&full[grp], (uint32_t)(RT_GROUP * pl.stage_bytes));
       __syncwarp();
       return true;
     };
     auto load_group = [&](long long u, int g, int row0) {
       const int grp = (int)(u % n_groups);
+      int gg = g + g_rot;
+      if (gg >= gps) gg -= gps;
       if (elect_one_sync()) {
-        const int i0 = g * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
-        for (int i = i0; i < i1; ++i) {
-          int kc = i + kc_rot;
-          if (kc >= p.nkc) kc -= p.nkc;
-          const int stage = grp * RT_GROUP + (i - i0);
-          if (CL == 1)
-            tma_load_2d(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0);
-          else if (i % CL == crank)
-            tma_load_2d_mcast(sA + stage * pl.stage_bytes, &tmap_h, &full[stage], kc * RT_BK, row0, cmask);
-        }
+        if (CL == 1)
+          tma_load_3d(sA + grp * RT_GROUP * pl.stage_bytes, &tmap_h, &full[grp], 0, row0, gg * RT_GROUP);
+        else if (g % CL == crank)
+          tma_load_3d_mcast(sA + grp * RT_GROUP * pl.stage_bytes, &tmap_h, &full[grp], 0, row0, gg * RT_GROUP, cmask);
       }
       __syncwarp();
     };
@@ -279,10 +273,11 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       for (int g = 0; g < gps; ++g, ++use) {
         const int grp = (int)(use % n_groups);
         const uint32_t fphase = (uint32_t)((use / n_groups) & 1);
-        const int i0 = g * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
+        int gg = g + g_rot;
+        if (gg >= gps) gg -= gps;
+        const int i0 = gg * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
         long long w0 = clock64();
-        for (int j = 0; j < RT_GROUP && ok; ++j)
-          ok = __all_sync(0xffffffffu, wait_abortable(&full[grp * RT_GROUP + j], fphase, p.abort_flag));
+        ok = __all_sync(0xffffffffu, wait_abortable(&full[grp], fphase, p.abort_flag));
         if (!ok) break;
         if (g == 0) { long long m1 = clock64(); d_wait0 += m1 - m0; m0 = m1; }
         else d_waitn += clock64() - w0;
@@ -290,13 +285,11 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         if (elect_one_sync()) {
           if (p.dbg && s == 100 && g < 8) p.dbg[blockIdx.x * 128 + 40 + g] = clock64();
           for (int i = i0; i < i1; ++i) {
-            int kc = i + kc_rot;
-            if (kc >= p.nkc) kc -= p.nkc;
             const uint64_t adesc = make_smem_desc(smem_u32(sA + (grp * RT_GROUP + (i - i0)) * pl.stage_bytes), 16, 1024, 2);
-            const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)kc * RT_W_BYTES), 16, 1024, 2);
+            const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)i * RT_W_BYTES), 16, 1024, 2);
 #pragma unroll
             for (int k = 0; k < RT_BK / 16; ++k)
-              umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) != 0);
+              umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (g | (i - i0) | k) != 0);
           }
           if (CL == 1) umma_commit(&gempty[grp]);
           else umma_commit_mcast(&gempty[grp], cmask);
@@ -592,9 +585,11 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   uint64_t dw[2] = {(uint64_t)HP, (uint64_t)L.dirs * cpd * RT_N}, sw[2] = {2, (uint64_t)HP * 2};
   uint32_t bw[2] = {RT_BK, RT_N};
   if (int e = make_tmap_bf16(&tw, L.w_hh_pack, 2, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  uint64_t dh[2] = {(uint64_t)HP, (uint64_t)2 * L.dirs * BP}, sh[2] = {2, (uint64_t)HP * 2};
-  uint32_t bh[2] = {RT_BK, (uint32_t)BP};
-  if (int e = make_tmap_bf16(&th, hbuf, 2, dh, sh, bh, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  // h exchange buffer as {64 k, rows, K chunks}: one box {64, BP, RT_GROUP} = RT_GROUP consecutive chunk tiles
+  uint64_t dh[3] = {(uint64_t)RT_BK, (uint64_t)2 * L.dirs * BP, (uint64_t)nkc};
+  uint64_t sh[3] = {2, (uint64_t)HP * 2, (uint64_t)RT_BK * 2};
+  uint32_t bh[3] = {RT_BK, (uint32_t)BP, RT_GROUP};
+  if (int e = make_tmap_bf16(&th, hbuf, 3, dh, sh, bh, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
 
   RnnTcParams p{};
   p.gx = gx;

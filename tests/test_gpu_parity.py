@@ -301,3 +301,26 @@ def test_streaming_transcribe_engine_matches_oracle(golden):
     r.enable_real_time_streaming(build_model("CPUStreamingRNN", seed=5, **kw).set_precision("fp32"), string_parts=True)
     got = [r.streaming_transcribe(c, is_last=(i == len(chunks) - 1), is_first=(i == 0)) for i, c in enumerate(chunks)]
     assert got == expect
+
+
+# ------------------------------------------------------------------ utterance sharding (BASELINE config 5 in miniature)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_shard_invariance_of_transcripts(precision):
+    """Transcripts must not depend on how the utterances are split over ranks / batches."""
+    from danspeech_b200 import Recognizer, sharding
+    from danspeech_b200.pretrained_models import build_model
+    rng = np.random.default_rng(5)
+    lens = rng.integers(1 * 16000, 6 * 16000, size=24)
+    recs = [syn.synthetic_audio(int(n), seed=200 + i) for i, n in enumerate(lens)]
+    r = Recognizer(model=build_model("TestModel", seed=0, rnn_hidden_size=160, rnn_layers=3).set_precision(precision))
+    base = sharding.transcribe_sharded(r.recognize_batch, recs, 0, 1, max_batch=64)
+    assert len(base) == 24 and all(isinstance(t, str) for t in base)
+    assert base[3] == r.recognize(recs[3])                       # batch == single utterance
+    for world in (2, 4):
+        merged = {}
+        for rank in range(world):
+            mine = sharding.lpt_shards([len(x) for x in recs], world)[rank]
+            for batch in sharding.make_batches(mine, [len(x) for x in recs], max_batch=5):
+                for i, o in zip(batch, r.recognize_batch([recs[i] for i in batch])):
+                    merged[i] = o
+        assert [merged[i] for i in range(24)] == base
