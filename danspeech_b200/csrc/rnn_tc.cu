@@ -51,7 +51,7 @@ __host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U) {
   RtPlan pl;
   pl.stage_bytes = BP * RT_BK * 2;
   const int w_bytes = nkc * RT_W_BYTES;
-  const int stg = 0 * BP * U;                    // (no store staging: every warp stores its own part of h_t)
+  const int stg = BP * U * 2;                    // h (bf16) staging: [BP rows][U units], one slice per lane quarter
   const int stg_al = (stg + 1023) / 1024 * 1024;
   int groups = (RT_SMEM_LIMIT - 2048 - 256 - w_bytes - stg_al) / (pl.stage_bytes * RT_GROUP);   // 1 KB align slack + 1 KB static
   if (groups > RT_MAX_GROUPS) groups = RT_MAX_GROUPS;
@@ -137,6 +137,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   const RtPlan pl = rt_plan(p.nkc, p.BP, U);
   unsigned char* sW = smem;
   unsigned char* sA = smem + pl.stage_off;
+  unsigned char* sStg = smem + pl.stg_off;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.bar_off);   // [RT_MAX_GROUPS] group landed (TMA tx)
   uint64_t* gempty = full + RT_MAX_GROUPS;                           // [RT_MAX_GROUPS] group consumed by the MMAs
   uint64_t* wbar = gempty + RT_MAX_GROUPS;
@@ -221,7 +222,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       c0 = clock64();
       if (s > 0) {
         // direction-wide barrier: every CTA of this direction has published h_{s-1}
-        const unsigned target = (unsigned)p.cpd * 8u * (unsigned)s;   // every epilogue warp publishes once per step
+        const unsigned target = (unsigned)p.cpd * 4u * (unsigned)s;   // every lane quarter publishes once per step
         long long t0 = 0;
         unsigned n = 0;
         while (ld_acquire_gpu(ctr) < target) {
@@ -309,8 +310,10 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     //      TMEM lane quarter q = warp % 4 holds batch rows [q*rpq, (q+1)*rpq) (rpq = 16 for the M = 64 MMA,
     //      32 for M = 128); the two warps of a quarter split the 64 gate columns.  With M = 64 only lanes 0..15
     //      of a quarter carry rows, so lanes 16..31 take over the upper half of the units of the same row
-    //      (their accumulators are shuffled over).  Every warp publishes its own part of h_t with one
-    //      red.release.gpu (the step counter therefore counts warps: target = 8 * CTAs * step).
+    //      (their accumulators are shuffled over).  The two warps of a quarter stage their rows of h_t in
+    //      shared memory, meet at a 64-thread named barrier and write 8-byte pieces (a release has to wait
+    //      for every prior store to be acknowledged, so few wide stores matter); one lane then publishes
+    //      with red.release.gpu (the step counter counts quarters: target = 4 * CTAs * step).
     constexpr int UQ = UH / 2;           // units per pass
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -335,6 +338,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         bhn[ps][u] = (GATES == 3 && p.b_hn && j < p.H) ? p.b_hn[(size_t)dir * p.H + j] : 0.f;
       }
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+    __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(sStg);   // [BP][U]
+    __shared__ int sT[128];                                       // row active in this step
     unsigned long long e_load = 0, e_wait = 0, e_math = 0, e_bar = 0, e_pub = 0;
     for (int s = 0; s < p.Tmax; ++s) {
       long long e0 = clock64();
@@ -358,7 +363,6 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       const bool ok = __all_sync(0xffffffffu, wait_abortable(dfull, (uint32_t)(s & 1), p.abort_flag));
       long long e2 = clock64();
       if (p.dbg && s == 100 && threadIdx.x == 128) p.dbg[blockIdx.x * 128 + 65] = e2;
-      if (!ok) break;
       tc_fence_after();
       uint32_t r[32];
       tmem_ld32(t_addr, r);
@@ -372,7 +376,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           if (lane >= 16) r[k] = v;
         }
       }
-      if (active) {
+      if (ok && active) {
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
           if (ps < npass) {
@@ -401,17 +405,39 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
               hprev[ps][u] = hn;
               hv[u] = hn;
             }
-            // h_t (bf16) for the next step's MMA: the only stores the step barrier has to wait for
-            __nv_bfloat16* ho = p.hbuf + ((size_t)(((s + 1) & 1) * p.dirs + dir) * p.BP + b) * p.HP + j0;
+            // h_t (bf16) for the next step's MMA -> staging [row][U]
+            __nv_bfloat16* sh = sH + (size_t)b * U + (j0 - c * U);
 #pragma unroll
-            for (int u = 0; u < UQ; ++u)
-              if (j0 + u < p.H) ho[u] = __float2bfloat16_rn(hv[u]);
+            for (int u = 0; u < UQ; ++u) sh[u] = __float2bfloat16_rn(hv[u]);
           }
         }
       }
+      if (half == 0 && lane < rpq) sT[q * rpq + lane] = (ok && active) ? 1 : 0;
       long long e3 = clock64();
-      __syncwarp();
-      if (lane == 0) red_release_gpu_add(p.counters + dir, 1u);   // publish this warp's part of h_t
+      if (!bar_red_and(ok, 1 + q, 64)) break;                     // both warps of the quarter have staged (uniform abort)
+      {
+        // rows [q*rpq, (q+1)*rpq) x U units -> global, the only stores the step barrier has to wait for
+        const int n_valid = min(U, p.H - c * U);
+        const int pt = half * 32 + lane;                          // 0..63 within the pair
+        __nv_bfloat16* hrow0 = p.hbuf + ((size_t)(((s + 1) & 1) * p.dirs + dir) * p.BP + q * rpq) * p.HP + c * U;
+        const __nv_bfloat16* srow0 = sH + (size_t)q * rpq * U;
+        if ((U & 3) == 0 && n_valid == U && (p.HP & 3) == 0) {
+          const int per_row = U / 4;                              // 8-byte pieces
+          for (int i = pt; i < rpq * per_row; i += 64) {
+            const int row = i / per_row, part = i - row * per_row;
+            if (sT[q * rpq + row])
+              *reinterpret_cast<uint2*>(hrow0 + (size_t)row * p.HP + part * 4) =
+                  *reinterpret_cast<const uint2*>(srow0 + (size_t)row * U + part * 4);
+          }
+        } else {
+          for (int i = pt; i < rpq * U; i += 64) {
+            const int row = i / U, u = i - row * U;
+            if (sT[q * rpq + row] && u < n_valid) hrow0[(size_t)row * p.HP + u] = srow0[(size_t)row * U + u];
+          }
+        }
+      }
+      named_bar_sync(1 + q, 64);                                  // the quarter's stores are issued
+      if (half == 0 && lane == 0) red_release_gpu_add(p.counters + dir, 1u);   // publish (cumulative over the pair)
       long long e4 = clock64();
       if (p.dbg && s == 99 && threadIdx.x == 128) p.dbg[blockIdx.x * 128 + 66] = e4;
       if (p.dbg && s == 100 && threadIdx.x == 128) p.dbg[blockIdx.x * 128 + 67] = e4;
