@@ -340,7 +340,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
     __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(sStg);   // [BP][U]
     __shared__ int sT[128];                                       // row active in this step
-    unsigned long long e_load = 0, e_wait = 0, e_math = 0, e_bar = 0, e_pub = 0;
+    unsigned long long e_load = 0, e_wait = 0, e_math = 0, e_bar = 0, e_pub = 0, e_ld = 0;
     for (int s = 0; s < p.Tmax; ++s) {
       long long e0 = clock64();
       const bool active = row_ok && s < len;
@@ -376,6 +376,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           if (lane >= 16) r[k] = v;
         }
       }
+      long long e2a = clock64();
+      e_ld += e2a - e2;
       if (ok && active) {
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
@@ -414,8 +416,10 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       }
       if (half == 0 && lane < rpq) sT[q * rpq + lane] = (ok && active) ? 1 : 0;
       long long e3 = clock64();
-      if (!bar_red_and(ok, 1 + q, 64)) break;                     // both warps of the quarter have staged (uniform abort)
-      {
+      // both warps of the quarter have staged.  After an abort (ok == false: the abort flag is set, so every
+      // later wait returns at once) the loop keeps running without doing work, so that no barrier is left short.
+      const bool all_ok = bar_red_and(ok, 1 + q, 64);
+      if (all_ok) {
         // rows [q*rpq, (q+1)*rpq) x U units -> global, the only stores the step barrier has to wait for
         const int n_valid = min(U, p.H - c * U);
         const int pt = half * 32 + lane;                          // 0..63 within the pair
@@ -437,12 +441,14 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         }
       }
       named_bar_sync(1 + q, 64);                                  // the quarter's stores are issued
-      if (half == 0 && lane == 0) red_release_gpu_add(p.counters + dir, 1u);   // publish (cumulative over the pair)
+      if (all_ok && half == 0 && lane == 0) red_release_gpu_add(p.counters + dir, 1u);   // publish (cumulative over the pair)
       long long e4 = clock64();
       if (p.dbg && s == 99 && threadIdx.x == 128) p.dbg[blockIdx.x * 128 + 66] = e4;
       if (p.dbg && s == 100 && threadIdx.x == 128) p.dbg[blockIdx.x * 128 + 67] = e4;
-      // y_t (fp32) straight from registers, after the publish: nobody waits on these stores
-      if (active) {
+      // y_t (fp32) straight from registers.  A release waits for every store the SM has in flight, so these
+      // stores are held back until all four quarters have published (off the critical path).
+      named_bar_sync(9, 256);
+      if (ok && active) {
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
           if (ps < npass) {
@@ -462,6 +468,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       p.dbg[blockIdx.x * 128 + 7] = e_math;
       p.dbg[blockIdx.x * 128 + 8] = e_bar;
       p.dbg[blockIdx.x * 128 + 9] = e_pub;
+      p.dbg[blockIdx.x * 128 + 12] = e_ld;
     }
   }
   tc_fence_before();
@@ -674,11 +681,11 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     DSB_CUDA(cudaStreamSynchronize(st));
     DSB_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * 128 * grid, cudaMemcpyDeviceToHost));
     cudaFree(dbg);
-    const char* names[12] = {"prod.spin", "prod.fence", "prod.issue", "mma.wait_first", "mma.rest", "epi.gload",
+    const char* names[13] = {"prod.spin", "prod.fence", "prod.issue", "mma.wait_first", "mma.rest", "epi.gload",
                              "epi.wait_mma", "epi.math_store", "epi.bar", "epi.publish", "mma.wait_rest",
-                             "prod.wait_empty"};
+                             "prod.wait_empty", "epi.tmem_ld"};
     fprintf(stderr, "[rnn_tc debug] H=%d B=%d Tmax=%d grid=%d  cycles/step (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid);
-    for (int k = 0; k < 12; ++k) {
+    for (int k = 0; k < 13; ++k) {
       double sum = 0, mx = 0;
       for (int c = 0; c < grid; ++c) { double v = (double)h[c * 128 + k] / Tmax; sum += v; mx = v > mx ? v : mx; }
       fprintf(stderr, "   %-16s %9.0f | %9.0f\n", names[k], sum / grid, mx);
