@@ -51,7 +51,7 @@ __host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U) {
   RtPlan pl;
   pl.stage_bytes = BP * RT_BK * 2;
   const int w_bytes = nkc * RT_W_BYTES;
-  const int stg = BP * U * 2;                    // h (bf16) staging: [BP rows][U units], one slice per lane quarter
+  const int stg = BP * U * 2;                    // h (bf16) staging for coalesced stores
   const int stg_al = (stg + 1023) / 1024 * 1024;
   int groups = (RT_SMEM_LIMIT - 2048 - 256 - w_bytes - stg_al) / (pl.stage_bytes * RT_GROUP);   // 1 KB align slack + 1 KB static
   if (groups > RT_MAX_GROUPS) groups = RT_MAX_GROUPS;
@@ -222,7 +222,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       c0 = clock64();
       if (s > 0) {
         // direction-wide barrier: every CTA of this direction has published h_{s-1}
-        const unsigned target = (unsigned)p.cpd * 4u * (unsigned)s;   // every lane quarter publishes once per step
+        const unsigned target = (unsigned)p.cpd * (unsigned)s;
         long long t0 = 0;
         unsigned n = 0;
         while (ld_acquire_gpu(ctr) < target) {
@@ -306,169 +306,144 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       p.dbg[blockIdx.x * 128 + 10] = d_waitn;
     }
   } else {
-    // ---- epilogue: 8 warps, no CTA-wide synchronisation inside the step loop.
-    //      TMEM lane quarter q = warp % 4 holds batch rows [q*rpq, (q+1)*rpq) (rpq = 16 for the M = 64 MMA,
-    //      32 for M = 128); the two warps of a quarter split the 64 gate columns.  With M = 64 only lanes 0..15
-    //      of a quarter carry rows, so lanes 16..31 take over the upper half of the units of the same row
-    //      (their accumulators are shuffled over).  The two warps of a quarter stage their rows of h_t in
-    //      shared memory, meet at a 64-thread named barrier and write 8-byte pieces (a release has to wait
-    //      for every prior store to be acknowledged, so few wide stores matter); one lane then publishes
-    //      with red.release.gpu (the step counter counts quarters: target = 4 * CTAs * step).
-    constexpr int UQ = UH / 2;           // units per pass
+    // ---- epilogue: 8 warps.  TMEM lane quarter q = warp % 4 holds batch rows [q*rpq, (q+1)*rpq)
+    //      (rpq = 16 for the M = 64 MMA, 32 for M = 128); the two warps of a quarter split the columns.
+    const int et = threadIdx.x - 64;     // 0..255
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int rpq = p.BP >> 2;
-    const bool split = rpq == 16;        // lanes 16..31 mirror the rows of lanes 0..15
-    const int rl = split ? (lane & 15) : lane;
-    const int b = q * rpq + rl;
-    const bool row_ok = b < p.B;
+    const int b = q * rpq + lane;
+    const bool row_ok = lane < rpq && b < p.B;
     const int len = row_ok ? p.lens[b] : 0;
-    const int npass = split ? 1 : 2;
-    const int uo0 = (split && lane >= 16) ? UQ : 0;
-    const int jbase = c * U + half * UH;
+    const int j0 = c * U + half * UH;
     const int ncol = p.dirs * GATES * p.H;
-    float hprev[2][UQ], cst[2][UQ], bhn[2][UQ];
+    float hprev[UH], cst[UH], bhn[UH];
 #pragma unroll
-    for (int ps = 0; ps < 2; ++ps)
-#pragma unroll
-      for (int u = 0; u < UQ; ++u) {
-        const int j = jbase + (split ? uo0 : ps * UQ) + u;
-        hprev[ps][u] = 0.f;
-        cst[ps][u] = 0.f;
-        bhn[ps][u] = (GATES == 3 && p.b_hn && j < p.H) ? p.b_hn[(size_t)dir * p.H + j] : 0.f;
-      }
+    for (int u = 0; u < UH; ++u) {
+      hprev[u] = 0.f;
+      cst[u] = 0.f;
+      bhn[u] = (GATES == 3 && p.b_hn && j0 + u < p.H) ? p.b_hn[(size_t)dir * p.H + j0 + u] : 0.f;
+    }
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
-    __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(sStg);   // [BP][U]
-    __shared__ int sT[128];                                       // row active in this step
-    unsigned long long e_load = 0, e_wait = 0, e_math = 0, e_bar = 0, e_pub = 0, e_ld = 0;
+    // h store staging sH [BP][U] bf16 + row validity sT [BP].  Single-buffered: the next write happens after
+    // this CTA's publish of the step (behind the second named barrier), i.e. after every read of it.
+    __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(sStg);
+    __shared__ int sT[128];
+    const bool vec2 = ((p.H & 1) == 0) && ((UH & 1) == 0);
+    unsigned long long e_load = 0, e_wait = 0, e_math = 0, e_bar = 0, e_pub = 0;
     for (int s = 0; s < p.Tmax; ++s) {
       long long e0 = clock64();
       const bool active = row_ok && s < len;
       const int t = dir == 0 ? s : len - 1 - s;
-      float gxv[2][GATES][UQ];
+      float gxv[GATES][UH];
       if (active) {
+        const float* gp = p.gx + ((size_t)t * p.B + b) * ncol + (size_t)dir * GATES * p.H + j0;
+        if (vec2 && j0 + UH <= p.H) {
 #pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {
-          if (ps < npass) {
-            const int j0 = jbase + (split ? uo0 : ps * UQ);
-            const float* gp = p.gx + ((size_t)t * p.B + b) * ncol + (size_t)dir * GATES * p.H + j0;
+          for (int g = 0; g < GATES; ++g)
 #pragma unroll
-            for (int g = 0; g < GATES; ++g)
+            for (int u = 0; u < UH; u += 2) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(gp + (size_t)g * p.H + u));
+              gxv[g][u] = v.x;
+              gxv[g][u + 1 < UH ? u + 1 : u] = v.y;
+            }
+        } else {
 #pragma unroll
-              for (int u = 0; u < UQ; ++u) gxv[ps][g][u] = (j0 + u < p.H) ? __ldg(gp + (size_t)g * p.H + u) : 0.f;
-          }
+          for (int g = 0; g < GATES; ++g)
+#pragma unroll
+            for (int u = 0; u < UH; ++u) gxv[g][u] = (j0 + u < p.H) ? __ldg(gp + (size_t)g * p.H + u) : 0.f;
         }
       }
+      if (half == 0 && lane < rpq) sT[q * rpq + lane] = active ? t : -1;
       long long e1 = clock64();
-      const bool ok = __all_sync(0xffffffffu, wait_abortable(dfull, (uint32_t)(s & 1), p.abort_flag));
+      const bool ok = wait_abortable(dfull, (uint32_t)(s & 1), p.abort_flag);
       long long e2 = clock64();
-      if (p.dbg && s == 100 && threadIdx.x == 128) p.dbg[blockIdx.x * 128 + 65] = e2;
+      if (p.dbg && s == 100 && et == 64) p.dbg[blockIdx.x * 128 + 65] = e2;
       tc_fence_after();
       uint32_t r[32];
       tmem_ld32(t_addr, r);
       tmem_ld_wait();
+#pragma unroll
+      for (int a = 1; a < RT_ACC; ++a) {
+        uint32_t r2[32];
+        tmem_ld32(t_addr + (uint32_t)(a * RT_N), r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      }
       tc_fence_before();
-      if (split) {
-        // upper lanes fetch the accumulators of units [UQ, UH) from the lane that holds the row
-#pragma unroll
-        for (int k = 0; k < UQ * GATES; ++k) {
-          const uint32_t v = __shfl_sync(0xffffffffu, r[UQ * GATES + k], lane & 15);
-          if (lane >= 16) r[k] = v;
-        }
-      }
-      long long e2a = clock64();
-      e_ld += e2a - e2;
       if (ok && active) {
+        __nv_bfloat16* sh = sH + (size_t)b * U + half * UH;
 #pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {
-          if (ps < npass) {
-            const int ro = split ? 0 : ps * UQ * GATES;     // offset into r[]
-            const int j0 = jbase + (split ? uo0 : ps * UQ);
-            float hv[UQ];
-#pragma unroll
-            for (int u = 0; u < UQ; ++u) {
-              float hn;
-              if (GATES == 3) {
-                const float rg = fast_sigmoid(gxv[ps][0][u] + __uint_as_float(r[ro + u * GATES + 0]));
-                const float zg = fast_sigmoid(gxv[ps][1 % GATES][u] + __uint_as_float(r[ro + u * GATES + (1 % GATES)]));
-                const float ng = fast_tanh(gxv[ps][2 % GATES][u] +
-                                           rg * (__uint_as_float(r[ro + u * GATES + (2 % GATES)]) + bhn[ps][u]));
-                hn = (1.0f - zg) * ng + zg * hprev[ps][u];
-              } else if (GATES == 4) {
-                const float ig = fast_sigmoid(gxv[ps][0][u] + __uint_as_float(r[ro + u * GATES + 0]));
-                const float fg = fast_sigmoid(gxv[ps][1 % GATES][u] + __uint_as_float(r[ro + u * GATES + (1 % GATES)]));
-                const float gg = fast_tanh(gxv[ps][2 % GATES][u] + __uint_as_float(r[ro + u * GATES + (2 % GATES)]));
-                const float og = fast_sigmoid(gxv[ps][3 % GATES][u] + __uint_as_float(r[ro + u * GATES + (3 % GATES)]));
-                cst[ps][u] = fg * cst[ps][u] + ig * gg;
-                hn = og * fast_tanh(cst[ps][u]);
-              } else {
-                hn = fast_tanh(gxv[ps][0][u] + __uint_as_float(r[ro + u]));
-              }
-              hprev[ps][u] = hn;
-              hv[u] = hn;
-            }
-            // h_t (bf16) for the next step's MMA -> staging [row][U]
-            __nv_bfloat16* sh = sH + (size_t)b * U + (j0 - c * U);
-#pragma unroll
-            for (int u = 0; u < UQ; ++u) sh[u] = __float2bfloat16_rn(hv[u]);
+        for (int u = 0; u < UH; ++u) {
+          float hn;
+          if (GATES == 3) {
+            const float rg = fast_sigmoid(gxv[0][u] + __uint_as_float(r[u * GATES + 0]));
+            const float zg = fast_sigmoid(gxv[1 % GATES][u] + __uint_as_float(r[u * GATES + (1 % GATES)]));
+            const float ng = fast_tanh(gxv[2 % GATES][u] + rg * (__uint_as_float(r[u * GATES + (2 % GATES)]) + bhn[u]));
+            hn = (1.0f - zg) * ng + zg * hprev[u];
+          } else if (GATES == 4) {
+            const float ig = fast_sigmoid(gxv[0][u] + __uint_as_float(r[u * GATES + 0]));
+            const float fg = fast_sigmoid(gxv[1 % GATES][u] + __uint_as_float(r[u * GATES + (1 % GATES)]));
+            const float gg = fast_tanh(gxv[2 % GATES][u] + __uint_as_float(r[u * GATES + (2 % GATES)]));
+            const float og = fast_sigmoid(gxv[3 % GATES][u] + __uint_as_float(r[u * GATES + (3 % GATES)]));
+            cst[u] = fg * cst[u] + ig * gg;
+            hn = og * fast_tanh(cst[u]);
+          } else {
+            hn = fast_tanh(gxv[0][u] + __uint_as_float(r[u]));
           }
+          hprev[u] = hn;
+          sh[u] = __float2bfloat16_rn(hn);
         }
       }
-      if (half == 0 && lane < rpq) sT[q * rpq + lane] = (ok && active) ? 1 : 0;
       long long e3 = clock64();
-      // both warps of the quarter have staged.  After an abort (ok == false: the abort flag is set, so every
-      // later wait returns at once) the loop keeps running without doing work, so that no barrier is left short.
-      const bool all_ok = bar_red_and(ok, 1 + q, 64);
-      if (all_ok) {
-        // rows [q*rpq, (q+1)*rpq) x U units -> global, the only stores the step barrier has to wait for
-        const int n_valid = min(U, p.H - c * U);
-        const int pt = half * 32 + lane;                          // 0..63 within the pair
-        __nv_bfloat16* hrow0 = p.hbuf + ((size_t)(((s + 1) & 1) * p.dirs + dir) * p.BP + q * rpq) * p.HP + c * U;
-        const __nv_bfloat16* srow0 = sH + (size_t)q * rpq * U;
+      const bool all_ok = bar_red_and(ok, 1, 256);     // staging complete (and uniform abort decision)
+      if (!all_ok) break;
+      // h_t -> global (bf16), coalesced: each row contributes U contiguous values
+      {
+        const int n_valid = min(U, p.H - c * U);       // units of this CTA inside H
+        __nv_bfloat16* hrow0 = p.hbuf + ((size_t)(((s + 1) & 1) * p.dirs + dir) * p.BP) * p.HP + c * U;
         if ((U & 3) == 0 && n_valid == U && (p.HP & 3) == 0) {
-          const int per_row = U / 4;                              // 8-byte pieces
-          for (int i = pt; i < rpq * per_row; i += 64) {
+          const int per_row = U / 4;                   // 8-byte pieces
+          for (int i = et; i < p.BP * per_row; i += 256) {
             const int row = i / per_row, part = i - row * per_row;
-            if (sT[q * rpq + row])
+            if (sT[row] >= 0)
               *reinterpret_cast<uint2*>(hrow0 + (size_t)row * p.HP + part * 4) =
-                  *reinterpret_cast<const uint2*>(srow0 + (size_t)row * U + part * 4);
+                  *reinterpret_cast<const uint2*>(sH + (size_t)row * U + part * 4);
           }
         } else {
-          for (int i = pt; i < rpq * U; i += 64) {
+          for (int i = et; i < p.BP * U; i += 256) {
             const int row = i / U, u = i - row * U;
-            if (sT[q * rpq + row] && u < n_valid) hrow0[(size_t)row * p.HP + u] = srow0[(size_t)row * U + u];
+            if (sT[row] >= 0 && u < n_valid) hrow0[(size_t)row * p.HP + u] = sH[(size_t)row * U + u];
           }
         }
       }
-      named_bar_sync(1 + q, 64);                                  // the quarter's stores are issued
-      if (all_ok && half == 0 && lane == 0) red_release_gpu_add(p.counters + dir, 1u);   // publish (cumulative over the pair)
+      named_bar_sync(2, 256);                          // all h stores issued
       long long e4 = clock64();
-      if (p.dbg && s == 99 && threadIdx.x == 128) p.dbg[blockIdx.x * 128 + 66] = e4;
-      if (p.dbg && s == 100 && threadIdx.x == 128) p.dbg[blockIdx.x * 128 + 67] = e4;
-      // y_t (fp32) straight from registers.  A release waits for every store the SM has in flight, so these
-      // stores are held back until all four quarters have published (off the critical path).
-      named_bar_sync(9, 256);
+      if (et == 0) red_release_gpu_add(p.counters + dir, 1u);   // publish h_t (release: cumulative over the CTA)
+      if (p.dbg && s == 99 && et == 0) p.dbg[blockIdx.x * 128 + 66] = clock64();
+      if (p.dbg && s == 100 && et == 0) p.dbg[blockIdx.x * 128 + 67] = clock64();
+      // y_t -> global (fp32) straight from registers, after the publish: nobody waits on these stores
       if (ok && active) {
+        float* yo = p.y + (((size_t)dir * p.T + t) * p.B + b) * p.H + j0;
+        if ((UH & 1) == 0 && (p.H & 1) == 0 && j0 + UH <= p.H) {
 #pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {
-          if (ps < npass) {
-            const int j0 = jbase + (split ? uo0 : ps * UQ);
-            float* yo = p.y + (((size_t)dir * p.T + t) * p.B + b) * p.H + j0;
+          for (int u = 0; u < UH; u += 2)
+            *reinterpret_cast<float2*>(yo + u) = make_float2(hprev[u], hprev[u + 1 < UH ? u + 1 : u]);
+        } else {
 #pragma unroll
-            for (int u = 0; u < UQ; ++u)
-              if (j0 + u < p.H) yo[u] = hprev[ps][u];
-          }
+          for (int u = 0; u < UH; ++u)
+            if (j0 + u < p.H) yo[u] = hprev[u];
         }
       }
       e_load += e1 - e0; e_wait += e2 - e1; e_math += e3 - e2; e_bar += e4 - e3; e_pub += clock64() - e4;
     }
-    if (p.dbg && threadIdx.x == 128) {   // warp 4: quarter 0, an active row
+    if (p.dbg && et == 64) {   // warp 4: quarter 0, an active row
       p.dbg[blockIdx.x * 128 + 5] = e_load;
       p.dbg[blockIdx.x * 128 + 6] = e_wait;
       p.dbg[blockIdx.x * 128 + 7] = e_math;
       p.dbg[blockIdx.x * 128 + 8] = e_bar;
       p.dbg[blockIdx.x * 128 + 9] = e_pub;
-      p.dbg[blockIdx.x * 128 + 12] = e_ld;
     }
   }
   tc_fence_before();
@@ -681,11 +656,11 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     DSB_CUDA(cudaStreamSynchronize(st));
     DSB_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * 128 * grid, cudaMemcpyDeviceToHost));
     cudaFree(dbg);
-    const char* names[13] = {"prod.spin", "prod.fence", "prod.issue", "mma.wait_first", "mma.rest", "epi.gload",
+    const char* names[12] = {"prod.spin", "prod.fence", "prod.issue", "mma.wait_first", "mma.rest", "epi.gload",
                              "epi.wait_mma", "epi.math_store", "epi.bar", "epi.publish", "mma.wait_rest",
-                             "prod.wait_empty", "epi.tmem_ld"};
+                             "prod.wait_empty"};
     fprintf(stderr, "[rnn_tc debug] H=%d B=%d Tmax=%d grid=%d  cycles/step (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid);
-    for (int k = 0; k < 13; ++k) {
+    for (int k = 0; k < 12; ++k) {
       double sum = 0, mx = 0;
       for (int c = 0; c < grid; ++c) { double v = (double)h[c * 128 + k] / Tmax; sum += v; mx = v > mx ? v : mx; }
       fprintf(stderr, "   %-16s %9.0f | %9.0f\n", names[k], sum / grid, mx);
