@@ -51,7 +51,8 @@ class DanSpeechRecognizer(object):
         self.audio_config = model.audio_conf
         self.model = model.to(self.device)
         self.model.eval()
-        self.audio_parser = SpectrogramAudioParser(self.audio_config, device=self.device)
+        self.audio_parser = SpectrogramAudioParser(self.audio_config, device=self.device,
+                                                   fast_fft=getattr(self.model, "precision", "fp32") == "bf16")
         self.labels = self.model.labels
         # as DanSpeechRecognizer.py:54-56 (quirk Q4: labels are assigned first, so an existing decoder is
         # only rebuilt when lm/alpha/beta/beam_width change)

@@ -34,13 +34,24 @@ enum { MODE_STATS = 0, MODE_NORM = 1, MODE_RAW = 2 };
 // dynamic range between strong and weak bins, so an fp32 FFT leaves ~1e-3 errors in the weak bins
 // after log1p.  The transform therefore runs in fp64 (B200 FP64 is half the FP32 rate; the kernel
 // stays far from the FP64 roof); only log1p and the normalisation are fp32, as upstream.
-struct SpecTables {
-  double window[kNfft];      // symmetric Hamming
-  double2 tw160[5][32];      // W160^(lane*k1)
-  double2 tw32[4][32];       // radix-2 DIF stage twiddles, halves 16, 8, 4, 2
-  double2 tw320[kBins + 3];  // W320^k, k = 0..160
+// A second instantiation runs the transform in fp32 ("fast" FFT): 2-4x fewer issue slots, errors up to ~2e-3
+// in weak bins, i.e. inside the 2e-2 bar of the bf16 mode whose convolutions round the input to bf16 anyway.
+template <typename T> struct V2;
+template <> struct V2<double> { typedef double2 type; };
+template <> struct V2<float> { typedef float2 type; };
+template <typename T>
+struct SpecTablesT {
+  T window[kNfft];                       // symmetric Hamming
+  typename V2<T>::type tw160[5][32];     // W160^(lane*k1)
+  typename V2<T>::type tw32[4][32];      // radix-2 DIF stage twiddles, halves 16, 8, 4, 2
+  typename V2<T>::type tw320[kBins + 3]; // W320^k, k = 0..160
 };
-__device__ SpecTables g_tab;
+typedef SpecTablesT<double> SpecTables;
+__device__ SpecTablesT<double> g_tab;
+__device__ SpecTablesT<float> g_tabf;
+template <typename T> __device__ __forceinline__ const SpecTablesT<T>& tables();
+template <> __device__ __forceinline__ const SpecTablesT<double>& tables<double>() { return g_tab; }
+template <> __device__ __forceinline__ const SpecTablesT<float>& tables<float>() { return g_tabf; }
 
 static std::once_flag g_tab_once;
 static cudaError_t g_tab_err = cudaSuccess;
@@ -66,13 +77,44 @@ static void init_tables() {
     h.tw320[k] = make_double2(cos(a), sin(a));
   }
   g_tab_err = cudaMemcpyToSymbol(g_tab, &h, sizeof(h));
+  static SpecTablesT<float> hf;
+  for (int k = 0; k < kNfft; ++k) hf.window[k] = (float)h.window[k];
+  for (int a = 0; a < 5; ++a)
+    for (int l = 0; l < 32; ++l) hf.tw160[a][l] = make_float2((float)h.tw160[a][l].x, (float)h.tw160[a][l].y);
+  for (int a = 0; a < 4; ++a)
+    for (int l = 0; l < 32; ++l) hf.tw32[a][l] = make_float2((float)h.tw32[a][l].x, (float)h.tw32[a][l].y);
+  for (int k = 0; k < kBins + 3; ++k) hf.tw320[k] = make_float2((float)h.tw320[k].x, (float)h.tw320[k].y);
+  if (g_tab_err == cudaSuccess) g_tab_err = cudaMemcpyToSymbol(g_tabf, &hf, sizeof(hf));
 }
 
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+template <typename C, typename T>
+__device__ __forceinline__ C mk2(T x, T y) {
+  C r;
+  r.x = x;
+  r.y = y;
+  return r;
 }
-__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+template <typename C>
+__device__ __forceinline__ C cmul(C a, C b) {
+  C r;
+  r.x = a.x * b.x - a.y * b.y;
+  r.y = a.x * b.y + a.y * b.x;
+  return r;
+}
+template <typename C>
+__device__ __forceinline__ C cadd(C a, C b) {
+  C r;
+  r.x = a.x + b.x;
+  r.y = a.y + b.y;
+  return r;
+}
+template <typename C>
+__device__ __forceinline__ C csub(C a, C b) {
+  C r;
+  r.x = a.x - b.x;
+  r.y = a.y - b.y;
+  return r;
+}
 
 // numpy 'reflect' padding index (periodic extension with period 2(n-1), no edge repeat).
 __device__ __forceinline__ int reflect_index(int j, int n) {
@@ -84,23 +126,27 @@ __device__ __forceinline__ int reflect_index(int j, int n) {
   return j < n ? j : period - j;
 }
 
-struct SpecSmem {
+template <typename T>
+struct SpecSmemT {
   alignas(16) float samples[kTileSamples];   // read as float2 / written as float4
-  alignas(16) double window[kNfft];          // read as double2
-  alignas(16) double2 z[kWarps][160];
-  alignas(16) double2 tw320[kBins + 3];
+  alignas(16) T window[kNfft];               // read as pairs
+  alignas(16) typename V2<T>::type z[kWarps][160];
+  alignas(16) typename V2<T>::type tw320[kBins + 3];
   alignas(16) double red[kWarps][2];
   alignas(16) float tile[kBins][kFT + 1];
   float mean_std[2];
 };
 
-template <int MODE>
+template <int MODE, typename T>
 __global__ void __launch_bounds__(kWarps * 32)
 spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const int32_t* __restrict__ n_samples,
                    float* __restrict__ out, int64_t out_stride, float* __restrict__ mean_std_out,
                    double* __restrict__ partials, int n_partials, int center, int normalize) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef typename V2<T>::type T2;
+  typedef SpecSmemT<T> SpecSmem;
   SpecSmem& sm = *reinterpret_cast<SpecSmem*>(smem_raw);
+  const SpecTablesT<T>& g_tab = tables<T>();
 
   const int b = blockIdx.y;
   const int tile_idx = blockIdx.x;
@@ -161,7 +207,7 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
     for (int i = tid; i < kBins + 3; i += kWarps * 32) sm.tw320[i] = g_tab.tw320[i];
   }
   // per-lane twiddles (registers)
-  double2 tw160[5], tw32[4];
+  T2 tw160[5], tw32[4];
 #pragma unroll
   for (int k1 = 0; k1 < 5; ++k1) tw160[k1] = g_tab.tw160[k1][lane];
 #pragma unroll
@@ -169,34 +215,34 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
   __syncthreads();
 
   double dsum = 0.0, dsq = 0.0;
-  const double C1 = 0.30901699437494742, C2 = -0.80901699437494742;
-  const double S1 = 0.95105651629515357, S2 = 0.58778525229247313;
+  const T C1 = (T)0.30901699437494742, C2 = (T)-0.80901699437494742;
+  const T S1 = (T)0.95105651629515357, S2 = (T)0.58778525229247313;
   const int rlane = __brev((unsigned)lane) >> 27;
 
   for (int f = warp; f < frames_here; f += kWarps) {
     const float* s = sm.samples + f * kHop;
-    double2 z[5];
+    T2 z[5];
 #pragma unroll
     for (int n1 = 0; n1 < 5; ++n1) {
       int idx = 2 * (32 * n1 + lane);
       float2 v = *reinterpret_cast<const float2*>(s + idx);
-      double2 w = *reinterpret_cast<const double2*>(sm.window + idx);
-      z[n1] = make_double2((double)v.x * w.x, (double)v.y * w.y);
+      T2 w = *reinterpret_cast<const T2*>(sm.window + idx);
+      z[n1] = mk2<T2, T>((T)v.x * w.x, (T)v.y * w.y);
     }
     // radix-5 over n1
-    double2 a1 = cadd(z[1], z[4]), a2 = cadd(z[2], z[3]);
-    double2 b1 = csub(z[1], z[4]), b2 = csub(z[2], z[3]);
-    double2 Y[5];
-    Y[0] = make_double2(z[0].x + a1.x + a2.x, z[0].y + a1.y + a2.y);
-    double2 p1 = make_double2(z[0].x + C1 * a1.x + C2 * a2.x, z[0].y + C1 * a1.y + C2 * a2.y);
-    double2 p2 = make_double2(z[0].x + C2 * a1.x + C1 * a2.x, z[0].y + C2 * a1.y + C1 * a2.y);
-    double2 q1 = make_double2(S1 * b1.x + S2 * b2.x, S1 * b1.y + S2 * b2.y);
-    double2 q2 = make_double2(S2 * b1.x - S1 * b2.x, S2 * b1.y - S1 * b2.y);
+    T2 a1 = cadd(z[1], z[4]), a2 = cadd(z[2], z[3]);
+    T2 b1 = csub(z[1], z[4]), b2 = csub(z[2], z[3]);
+    T2 Y[5];
+    Y[0] = mk2<T2, T>(z[0].x + a1.x + a2.x, z[0].y + a1.y + a2.y);
+    T2 p1 = mk2<T2, T>(z[0].x + C1 * a1.x + C2 * a2.x, z[0].y + C1 * a1.y + C2 * a2.y);
+    T2 p2 = mk2<T2, T>(z[0].x + C2 * a1.x + C1 * a2.x, z[0].y + C2 * a1.y + C1 * a2.y);
+    T2 q1 = mk2<T2, T>(S1 * b1.x + S2 * b2.x, S1 * b1.y + S2 * b2.y);
+    T2 q2 = mk2<T2, T>(S2 * b1.x - S1 * b2.x, S2 * b1.y - S1 * b2.y);
     // -i*q = (q.y, -q.x)
-    Y[1] = make_double2(p1.x + q1.y, p1.y - q1.x);
-    Y[4] = make_double2(p1.x - q1.y, p1.y + q1.x);
-    Y[2] = make_double2(p2.x + q2.y, p2.y - q2.x);
-    Y[3] = make_double2(p2.x - q2.y, p2.y + q2.x);
+    Y[1] = mk2<T2, T>(p1.x + q1.y, p1.y - q1.x);
+    Y[4] = mk2<T2, T>(p1.x - q1.y, p1.y + q1.x);
+    Y[2] = mk2<T2, T>(p2.x + q2.y, p2.y - q2.x);
+    Y[3] = mk2<T2, T>(p2.x - q2.y, p2.y + q2.x);
 #pragma unroll
     for (int k1 = 1; k1 < 5; ++k1) Y[k1] = cmul(Y[k1], tw160[k1]);
     // five interleaved 32-point DIF FFTs across the lanes
@@ -206,12 +252,12 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
       const bool upper = (lane & half) != 0;
 #pragma unroll
       for (int k1 = 0; k1 < 5; ++k1) {
-        double px = __shfl_xor_sync(0xffffffffu, Y[k1].x, half);
-        double py = __shfl_xor_sync(0xffffffffu, Y[k1].y, half);
+        T px = __shfl_xor_sync(0xffffffffu, Y[k1].x, half);
+        T py = __shfl_xor_sync(0xffffffffu, Y[k1].y, half);
         if (!upper) {
-          Y[k1] = make_double2(Y[k1].x + px, Y[k1].y + py);
+          Y[k1] = mk2<T2, T>(Y[k1].x + px, Y[k1].y + py);
         } else {
-          double2 d = make_double2(px - Y[k1].x, py - Y[k1].y);
+          T2 d = mk2<T2, T>(px - Y[k1].x, py - Y[k1].y);
           Y[k1] = (st < 4) ? cmul(d, tw32[st < 4 ? st : 0]) : d;
         }
       }
@@ -226,16 +272,17 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
     for (int j = 0; j < 6; ++j) {
       int k = lane + 32 * j;
       if (k <= 160) {
-        double2 zk = sm.z[warp][k == 160 ? 0 : k];
-        double2 zn = sm.z[warp][k == 0 || k == 160 ? 0 : 160 - k];
+        T2 zk = sm.z[warp][k == 160 ? 0 : k];
+        T2 zn = sm.z[warp][k == 0 || k == 160 ? 0 : 160 - k];
         zn.y = -zn.y;
-        double2 e = cadd(zk, zn);
-        double2 o = csub(zk, zn);
-        double2 wo = cmul(sm.tw320[k], o);
+        T2 e = cadd(zk, zn);
+        T2 o = csub(zk, zn);
+        T2 wo = cmul(sm.tw320[k], o);
         // -i*wo = (wo.y, -wo.x); complex64 storage of D upstream -> round the parts to fp32
-        float re = (float)(0.5 * (e.x + wo.y));
-        float im = (float)(0.5 * (e.y - wo.x));
-        float mag = (float)sqrt((double)re * (double)re + (double)im * (double)im);
+        float re = (float)((T)0.5 * (e.x + wo.y));
+        float im = (float)((T)0.5 * (e.y - wo.x));
+        float mag = sizeof(T) == 8 ? (float)sqrt((double)re * (double)re + (double)im * (double)im)
+                                   : sqrtf(re * re + im * im);
         float v = log1pf(mag);
         if (MODE != MODE_NORM) {
           dsum += (double)v;
@@ -350,18 +397,18 @@ static int ensure_tables() {
   return 0;
 }
 
-template <int MODE>
+template <int MODE, typename T>
 static int launch_spec(const float* audio, int64_t audio_stride, const int32_t* d_n, int B, float* out,
                        int64_t out_stride, float* mean_std, double* partials, int n_partials, int tiles, int center,
                        int normalize, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    DSB_CUDA(cudaFuncSetAttribute(spectrogram_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(SpecSmem)));
+    DSB_CUDA(cudaFuncSetAttribute(spectrogram_kernel<MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(SpecSmemT<T>)));
     attr_set = true;
   }
   dim3 grid(tiles, B);
-  spectrogram_kernel<MODE><<<grid, kWarps * 32, sizeof(SpecSmem), st>>>(audio, audio_stride, d_n, out, out_stride,
+  spectrogram_kernel<MODE, T><<<grid, kWarps * 32, sizeof(SpecSmemT<T>), st>>>(audio, audio_stride, d_n, out, out_stride,
                                                                       mean_std, partials, n_partials, center,
                                                                       normalize);
   DSB_CHECK_LAUNCH();
@@ -378,7 +425,9 @@ extern "C" int dsb_spectrogram_partials(int max_frames) { return cdiv(max_frames
 
 extern "C" int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int B,
                                    int max_samples, float* out, int64_t out_stride, float* mean_std,
-                                   double* partials, int normalize, void* stream) {
+                                   double* partials, int flags, void* stream) {
+  const int normalize = flags & DSB_SPECT_NORMALIZE;
+  const bool fast = (flags & DSB_SPECT_FAST_FFT) != 0;
   DSB_REQUIRE(audio && n_samples && out && partials && B > 0, "dsb_spectrogram_f32: null argument or B <= 0");
   DSB_REQUIRE(max_samples >= 2 && max_samples <= audio_stride, "dsb_spectrogram_f32: max_samples %d out of range",
               max_samples);
@@ -395,8 +444,10 @@ extern "C" int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, con
   // one fp64 FFT pass writes log1p|X| and per-tile (sum, sum of squares); the normalisation is a cheap
   // elementwise pass over data that is still in L2 (the FFT is instruction-bound, not HBM-bound, so
   // recomputing it for the second pass would double the kernel time)
-  if (int e = launch_spec<MODE_RAW>(audio, audio_stride, n_samples, B, out, out_stride, nullptr, partials, n_partials,
-                                    tiles_all, 1, 0, st))
+  if (int e = fast ? launch_spec<MODE_RAW, float>(audio, audio_stride, n_samples, B, out, out_stride, nullptr, partials,
+                                                  n_partials, tiles_all, 1, 0, st)
+                   : launch_spec<MODE_RAW, double>(audio, audio_stride, n_samples, B, out, out_stride, nullptr, partials,
+                                                   n_partials, tiles_all, 1, 0, st))
     return e;
   if (!normalize) return 0;
   stream_stats_kernel<<<cdiv(B, 128), 128, 0, st>>>(partials, n_partials, n_samples, nullptr, B, 1, normalize,
@@ -423,7 +474,7 @@ extern "C" int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stri
   const int max_frames = 1 + (max_samples - kNfft) / kHop;
   DSB_REQUIRE(out_stride >= max_frames, "dsb_spectrogram_stream_f32: out_stride too small");
   const int n_partials = dsb_spectrogram_partials((int)out_stride);
-  if (int e = launch_spec<MODE_RAW>(audio, audio_stride, n_samples, S, out, out_stride, nullptr, partials,
+  if (int e = launch_spec<MODE_RAW, double>(audio, audio_stride, n_samples, S, out, out_stride, nullptr, partials,
                                     n_partials, cdiv((int)out_stride, kFT), 0, 0, st))
     return e;
   stream_stats_kernel<<<cdiv(S, 128), 128, 0, st>>>(partials, n_partials, n_samples, stats, S, 0, 1, nullptr,

@@ -56,13 +56,17 @@ int dsb_profile_read(int stage, double* total_ms, int* spans);
  *   out            device f32 [B, n_freq=161, out_stride]; frames t >= 1+n/160 are written as 0
  *   mean_std       device f32 [B, 2] (mean, std actually applied)  -- may be NULL
  *   partials       device f64 [B, dsb_spectrogram_partials(max_frames), 2] scratch
- *   normalize      audio_conf["normalize"] (parsers.py:25)
+ *   flags          DSB_SPECT_NORMALIZE: audio_conf["normalize"] (parsers.py:25);
+ *                  DSB_SPECT_FAST_FFT: run the transform in fp32 instead of fp64 (errors up to ~2e-3 in weak
+ *                  bins: inside the 2e-2 bar of the bf16 mode, outside the 1e-4 bar of the fp32 mode)
  * ------------------------------------------------------------------------- */
+#define DSB_SPECT_NORMALIZE 1
+#define DSB_SPECT_FAST_FFT 2
 int dsb_spectrogram_num_frames(int n_samples);                 /* 1 + n/160 */
 int dsb_spectrogram_partials(int max_frames);                  /* scratch rows per utterance */
 int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int B,
                         int max_samples, float* out, int64_t out_stride, float* mean_std, double* partials,
-                        int normalize, void* stream);
+                        int flags, void* stream);
 
 /* Streaming spectrogram (replaces parsers.py:101-163, InferenceSpectrogramAudioParser:
  * center=False STFT of an already assembled chunk, log1p, BIASED mean/std of the chunk

@@ -324,3 +324,15 @@ def test_shard_invariance_of_transcripts(precision):
                 for i, o in zip(batch, r.recognize_batch([recs[i] for i in batch])):
                     merged[i] = o
         assert [merged[i] for i in range(24)] == base
+
+
+def test_spectrogram_fast_fft_within_bf16_bar(golden):
+    """fp32-FFT variant used together with the bf16 model mode: spectrograms within 2e-2 relative."""
+    from danspeech_b200.audio.parsers import SpectrogramAudioParser
+    p = SpectrogramAudioParser(fast_fft=True)
+    for name in ("u0013002", "u0042018"):
+        s = p.parse_audio(golden["wav_" + name].astype(np.float64))
+        err = rel_err(s.cpu().numpy(), golden["spect_" + name])
+        assert err < BF16_TOL, err
+    s = p.parse_audio(syn.synthetic_audio(40001, seed=103))
+    assert rel_err(s.cpu().numpy(), golden["spect_syn40001"]) < BF16_TOL
