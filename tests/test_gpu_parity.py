@@ -336,3 +336,44 @@ def test_spectrogram_fast_fft_within_bf16_bar(golden):
         assert err < BF16_TOL, err
     s = p.parse_audio(syn.synthetic_audio(40001, seed=103))
     assert rel_err(s.cpu().numpy(), golden["spect_syn40001"]) < BF16_TOL
+
+
+# ------------------------------------------------------------------ edge shapes
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_edge_shapes_match_oracle(precision, tol):
+    """Odd hidden size (padding paths), one-frame utterances, ragged batch with a minimum-length item."""
+    kw = dict(rnn_hidden_size=100, rnn_layers=2)
+    cfg = case_config("TestModel", kw)
+    sd = syn.make_state_dict(seed=9, **cfg)
+    m = _model("TestModel", kw, seed=9, precision=precision)
+    p = osp.SpectrogramOracle()
+    auds = [syn.synthetic_audio(n, seed=300 + i) for i, n in enumerate((9000, 700, 161))]
+    specs = [p.parse_audio(a) for a in auds]
+    x = torch.zeros(3, 1, 161, specs[0].size(1))
+    for i, s in enumerate(specs):
+        x[i, 0, :, : s.size(1)] = s
+    xl = torch.IntTensor([s.size(1) for s in specs])
+    assert xl.tolist()[-1] == 2                      # 161 samples -> 2 frames -> 1 model frame
+    ref, rs = om.forward(sd, x, xl, cfg["conv_layers"], cfg["rnn_layers"])
+    probs, sizes = m(x.cuda(), xl)
+    assert sizes.tolist() == rs.tolist() and sizes.tolist()[-1] == 1
+    for b, L in enumerate(sizes.tolist()):
+        assert logit_rel_err(probs[b, :L].cpu().numpy(), ref[b, :L].numpy()) < tol
+
+
+def test_large_batch_falls_back_to_per_step_recurrence():
+    """More than 128 sequences: the persistent recurrence does not apply; the bf16 path must still be right."""
+    kw = dict(rnn_hidden_size=64, rnn_layers=1)
+    cfg = case_config("TestModel", kw)
+    sd = syn.make_state_dict(seed=12, **cfg)
+    m = _model("TestModel", kw, seed=12, precision="bf16")
+    p = osp.SpectrogramOracle()
+    spec = p.parse_audio(syn.synthetic_audio(4000, seed=400))
+    B = 130
+    x = spec.view(1, 1, 161, -1).repeat(B, 1, 1, 1)
+    xl = torch.IntTensor([spec.size(1)] * B)
+    ref, rs = om.forward(sd, x[:1], xl[:1], cfg["conv_layers"], cfg["rnn_layers"])
+    probs, sizes = m(x.cuda(), xl)
+    assert probs.shape[0] == B
+    assert logit_rel_err(probs[0].cpu().numpy(), ref[0].numpy()) < BF16_TOL
+    assert torch.equal(probs[0], probs[B - 1])
