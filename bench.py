@@ -320,8 +320,12 @@ def run_ours(args):
     flops = {"conv": conv_f, "rnn_input_proj": proj_f, "rnn_recurrence": rec_f}[dominant]
     achieved = flops / (stage_ms[dominant] / 1e3) / 1e12 if stage_ms[dominant] > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and args.precision == "bf16":
+        traffic = json.load(open(tp)).get(dominant, {}).get("bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                 "ms_per_step": stage_ms[dominant], "launches_per_step": prof[dominant][1] / max(args.steps, 1)}
     spect_bytes = BATCH * (4 * n + 4 * 161 * (1 + n // 160))
     stages = {k: {"ms_per_step": round(v, 4)} for k, v in stage_ms.items() if v > 0}

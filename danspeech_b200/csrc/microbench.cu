@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(128, 1) mma_issue_bench_kernel(int n_mma, int 
   __shared__ uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  for (int i = threadIdx.x; i < 65536 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);   // scratch: receives the per-group commits (never waited on)
     mbar_init(&bars[1], 1);   // done barrier
@@ -90,7 +90,7 @@ extern "C" int dsb_debug_mma_bench(int M, int N, int n_mma, int group, int varia
   using namespace dsb;
   long long* d = nullptr;
   DSB_CUDA(cudaMalloc(&d, 2 * sizeof(long long)));
-  const int smem = 32768 + 1024;
+  const int smem = 65536 + 1024;
 #define RUN(MM, NN)                                                                                     \
   DSB_CUDA(cudaFuncSetAttribute(tc::mma_issue_bench_kernel<MM, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
   tc::mma_issue_bench_kernel<MM, NN><<<1, 128, smem>>>(n_mma, group, variant, d);
