@@ -109,7 +109,6 @@ struct TcWorkspace {
   float* xf;
   __nv_bfloat16* hbuf;
   unsigned int* sync_words;
-  int* h_abort;   // unused (device flag is read back through a pinned-less copy)
   float* hstate;
   float* cstate;
   float* logits;

@@ -59,11 +59,6 @@ __global__ void fold_linear_kernel(const float* __restrict__ w, const float* __r
   if (lane == 0 && b_out) b_out[row] = (float)((b ? (double)b[row] : 0.0) + acc);
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    y[i] = __float2bfloat16_rn(x[i]);
-}
-
 static int grid_for(int64_t n) { return (int)(cdiv64(n, 256) < 4096 ? cdiv64(n, 256) : 4096); }
 
 struct Lookup {

@@ -31,10 +31,8 @@ constexpr int RT_N = 64;                       // W_hh rows per CTA = 2 halves x
 constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk (8 KB)
 constexpr int RT_GROUP = 4;        // K chunks handled per elected issue region
 constexpr int RT_MAX_GROUPS = 2;   // ring = RT_MAX_GROUPS x RT_GROUP stages
-constexpr int RT_MAX_STAGES = RT_GROUP * RT_MAX_GROUPS;
-// Consecutive tcgen05.mma into the same accumulator do not stall each other (tested with 4 independent
-// accumulators: no change), so a single TMEM accumulator is used.
-constexpr int RT_ACC = 1;
+// (Consecutive tcgen05.mma into the same accumulator do not stall each other -- tested with 4 independent
+// accumulators: no change -- so a single 64-column TMEM accumulator is used.)
 constexpr int RT_THREADS = 64 + 256;
 constexpr long long RT_TIMEOUT_CYCLES = 4000000000LL;
 constexpr int RT_SMEM_LIMIT = 227 * 1024;
@@ -363,14 +361,6 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       uint32_t r[32];
       tmem_ld32(t_addr, r);
       tmem_ld_wait();
-#pragma unroll
-      for (int a = 1; a < RT_ACC; ++a) {
-        uint32_t r2[32];
-        tmem_ld32(t_addr + (uint32_t)(a * RT_N), r2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-      }
       tc_fence_before();
       if (ok && active) {
         __nv_bfloat16* sh = sH + (size_t)b * U + half * UH;
@@ -451,7 +441,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   if (CL > 1) cluster_sync_all();    // nobody leaves while a peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<RT_ACC * RT_N>(tmem_base);
+    tmem_dealloc<64>(tmem_base);
   }
 }
 
