@@ -12,6 +12,7 @@
 #include "tc_common.cuh"
 #include "model_types.cuh"
 #include <mutex>
+#include <cstdlib>
 
 namespace dsb {
 namespace tc {
@@ -206,6 +207,203 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs computes a 256 x BN tile.  Each CTA stages its own
+// 128 rows of A and BN/2 rows of W, the leader issues one tcgen05.mma per K=16 slice for both SMs, each
+// CTA's TMEM holds its 128 accumulator rows.  The SS-mode operand fetch (~64 B/clk/SM) per slice drops
+// from (128 + BN) to (128 + BN/2) rows, which is what bounds the 1-CTA kernel.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct Gemm2Smem {
+  static constexpr int STAGES2 = 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int BAR_OFF = STAGES2 * (A_BYTES + B_STRIDE);
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K) {
+  using S = Gemm2Smem<BN>;
+  constexpr int STAGES2 = S::STAGES2;
+  constexpr int TMEM_COLS = 512;
+  constexpr int ACC_STRIDE = 256;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + STAGES2 * S::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // used in the leader only
+  uint64_t* empty = full + STAGES2;                                  // per CTA (multicast commit)
+  uint64_t* tfull = empty + STAGES2;                                 // per CTA (multicast commit)
+  uint64_t* tempty = tfull + 2;                                      // leader only, 8 arrivals (4 warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int m_blocks = (M + 2 * BM - 1) / (2 * BM), n_blocks = (N + BN - 1) / BN;
+  const int n_tiles = m_blocks * n_blocks;
+  const int nkb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int i = 0; i < STAGES2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    // producer of this CTA's halves; completion is signalled on the LEADER's full barrier
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+      const int m0 = (tile / n_blocks) * 2 * BM + rank * BM, n0 = (tile % n_blocks) * BN + rank * (BN / 2);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait_trap(&empty[stage], phase ^ 1);
+        if (elect_one_sync()) {
+          const uint32_t lead_bar = mapa_u32(smem_u32(&full[stage]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (S::A_BYTES + S::B_BYTES));
+          tma_load_2d_2cta(sA + stage * S::A_BYTES, &tmap_a, lead_bar, kb * BK, m0);
+          tma_load_2d_2cta(sB + stage * S::B_STRIDE, &tmap_b, lead_bar, kb * BK, n0);
+        }
+        __syncwarp();
+        if (++stage == STAGES2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // leader: issues the MMAs of the pair
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        mbar_wait_trap(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_trap(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * S::A_BYTES), 16, 1024, 2);
+          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * S::B_STRIDE), 16, 1024, 2);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            umma_commit_2cta(&empty[stage], 3);
+            if (kb == nkb - 1) umma_commit_2cta(&tfull[acc], 3);
+          }
+          __syncwarp();
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+      const int m0 = (tile / n_blocks) * 2 * BM + rank * BM, n0 = (tile % n_blocks) * BN;
+      mbar_wait_trap(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t t_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_addr + c0, r);
+        tmem_ld_wait();
+        if (row < M) {
+          float* dst = C + (int64_t)row * ldc + n0 + c0;
+          if (vec_ok && n0 + c0 + 16 <= N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 v;
+              v.x = __uint_as_float(r[j + 0]) + (bias ? __ldg(bias + n0 + c0 + j + 0) : 0.f);
+              v.y = __uint_as_float(r[j + 1]) + (bias ? __ldg(bias + n0 + c0 + j + 1) : 0.f);
+              v.z = __uint_as_float(r[j + 2]) + (bias ? __ldg(bias + n0 + c0 + j + 2) : 0.f);
+              v.w = __uint_as_float(r[j + 3]) + (bias ? __ldg(bias + n0 + c0 + j + 3) : 0.f);
+              *reinterpret_cast<float4*>(dst + j) = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < N) dst[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));   // the leader's barrier
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's shared memory / TMEM stay valid until both CTAs are done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_gemm2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
+                        float* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}, strA[2] = {2, (uint64_t)lda * 2};
+  uint32_t boxA[2] = {BK, BM};
+  if (int e = make_tmap_bf16(&ta, A, 2, dimsA, strA, boxA, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  uint64_t dimsB[2] = {(uint64_t)K, (uint64_t)N}, strB[2] = {2, (uint64_t)ldw * 2};
+  uint32_t boxB[2] = {BK, BN / 2};
+  if (int e = make_tmap_bf16(&tb, W, 2, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  static bool attr = false;
+  if (!attr) {
+    DSB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::TOTAL));
+    attr = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = cdiv(M, 2 * BM) * cdiv(N, BN);
+  int pairs = sms / 2;
+  if (tiles < pairs) pairs = tiles;
+  gemm_tc2_kernel<BN><<<2 * pairs, GEMM_THREADS, Gemm2Smem<BN>::TOTAL, st>>>(ta, tb, bias, C, ldc, M, N, K);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
 template <int BN>
 static int launch_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
                        float* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
@@ -240,6 +438,8 @@ int gemm_bias_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return set_error(DSB_ERR_INVALID, "gemm_bias_tc: operands must be 16-byte aligned");
   // pick the widest tile that divides N evenly into few blocks (7200 = 30 x 240; 2400 = 10 x 240; ...)
+  static const bool two_cta = !(getenv("DSB_GEMM_2CTA") && atoi(getenv("DSB_GEMM_2CTA")) == 0);
+  if (N % 240 == 0 && M >= 256 && two_cta) return tc::launch_gemm2<240>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
   if (N % 240 == 0) return tc::launch_gemm<240>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
   if (N >= 256 && N % 256 == 0) return tc::launch_gemm<256>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
   if (N % 192 == 0) return tc::launch_gemm<192>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
