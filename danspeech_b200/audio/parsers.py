@@ -103,6 +103,29 @@ class SpectrogramAudioParser(AudioParser):
         lengths = torch.IntTensor([1 + n // self.hop_length for n in ns])
         return out.view(len(ns), 1, 161, out.shape[2]), lengths
 
+    def parse_pcm16(self, host_pcm, n_samples):
+        """Interleaved 16-bit PCM straight from WAV files: host int16 tensor [B, frames] or [B, frames, channels]
+        (ideally pinned), sorted by length descending.  Stereo is mixed down on the GPU as clip(L+R)."""
+        dev = self._dev()
+        if host_pcm.dtype != torch.int16 or host_pcm.dim() not in (2, 3):
+            raise ValueError("parse_pcm16 expects an int16 tensor [B, frames] or [B, frames, channels]")
+        ns = [int(v) for v in n_samples]
+        B, stride = host_pcm.shape[0], host_pcm.shape[1]
+        ch = host_pcm.shape[2] if host_pcm.dim() == 3 else 1
+        pcm = host_pcm.contiguous().to(dev, non_blocking=True)
+        n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
+        L = N.lib()
+        frames = L.dsb_spectrogram_num_frames(max(ns))
+        out = torch.empty((B, 161, frames), dtype=torch.float32, device=dev)
+        mean_std = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        partials = torch.empty((B, L.dsb_spectrogram_partials(frames), 2), dtype=torch.float64, device=dev)
+        N.check(L.dsb_spectrogram_s16(N.ptr(pcm), ch, stride, N.ptr(n_dev), B, max(ns), N.ptr(out), frames,
+                                      N.ptr(mean_std), N.ptr(partials),
+                                      (1 if self.normalize else 0) | (2 if self.fast_fft else 0), N.current_stream()),
+                "dsb_spectrogram_s16")
+        lengths = torch.IntTensor([1 + n // self.hop_length for n in ns])
+        return out.view(B, 1, 161, frames), lengths
+
     def parse_audio(self, recording):
         """1-D numpy array at raw int16 sample scale -> FloatTensor[161, 1 + n//160] (on the CUDA device)."""
         spect, _ = self.parse_batch([recording])

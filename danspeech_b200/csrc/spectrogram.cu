@@ -137,9 +137,20 @@ struct SpecSmemT {
   float mean_std[2];
 };
 
-template <int MODE, typename T>
+// sample j of an utterance: fp32 mono, or interleaved s16 PCM mixed down as clip(sum of channels) -- the
+// audioop.tomono(buf, width, 1, 1) mix of the reference's load_audio (resources.py:302-303, quirk Q1)
+template <bool S16>
+__device__ __forceinline__ float load_sample(const void* __restrict__ base, int64_t j, int channels) {
+  if (!S16) return __ldg(reinterpret_cast<const float*>(base) + j);
+  const int16_t* p = reinterpret_cast<const int16_t*>(base) + j * channels;
+  int acc = 0;
+  for (int c = 0; c < channels; ++c) acc += (int)__ldg(p + c);
+  return (float)max(-32768, min(32767, acc));
+}
+
+template <int MODE, typename T, bool S16>
 __global__ void __launch_bounds__(kWarps * 32)
-spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const int32_t* __restrict__ n_samples,
+spectrogram_kernel(const void* __restrict__ audio_v, int channels, int64_t audio_stride, const int32_t* __restrict__ n_samples,
                    float* __restrict__ out, int64_t out_stride, float* __restrict__ mean_std_out,
                    double* __restrict__ partials, int n_partials, int center, int normalize) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -154,7 +165,10 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(n_samples[b], (int)audio_stride);
   const int n_frames = center ? 1 + n / kHop : (n >= kNfft ? 1 + (n - kNfft) / kHop : 0);
-  const float* y = audio + (int64_t)b * audio_stride;
+  const float* audio = reinterpret_cast<const float*>(audio_v);
+  const float* y = audio + (int64_t)b * audio_stride;                       // fp32 input
+  const void* yb = S16 ? static_cast<const void*>(reinterpret_cast<const int16_t*>(audio_v) + (int64_t)b * audio_stride * channels)
+                       : static_cast<const void*>(y);
 
   // mean / std from the MODE_STATS partials (fixed summation order -> deterministic).
   if (MODE == MODE_NORM) {
@@ -188,7 +202,7 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
     // ---- stage samples (reflect padding at both utterance ends) ----
     const int g0 = t0 * kHop - (center ? kNfft / 2 : 0);
     const int need = kHop * (frames_here - 1) + kNfft;
-    const bool interior = (g0 >= 0) && (g0 + need <= n) && ((audio_stride & 3) == 0) &&
+    const bool interior = !S16 && (g0 >= 0) && (g0 + need <= n) && ((audio_stride & 3) == 0) &&
                           ((reinterpret_cast<uintptr_t>(audio) & 15) == 0);
     if (interior) {
       const float4* src = reinterpret_cast<const float4*>(y + g0);   // g0 % 4 == 0
@@ -198,8 +212,8 @@ spectrogram_kernel(const float* __restrict__ audio, int64_t audio_stride, const 
       for (int i = tid; i < need; i += kWarps * 32) {
         int j = g0 + i;
         float v = 0.0f;
-        if (center) v = __ldg(y + reflect_index(j, n));
-        else if (j < n) v = __ldg(y + j);
+        if (center) v = load_sample<S16>(yb, reflect_index(j, n), channels);
+        else if (j < n) v = load_sample<S16>(yb, j, channels);
         sm.samples[i] = v;
       }
     }
@@ -397,18 +411,18 @@ static int ensure_tables() {
   return 0;
 }
 
-template <int MODE, typename T>
-static int launch_spec(const float* audio, int64_t audio_stride, const int32_t* d_n, int B, float* out,
+template <int MODE, typename T, bool S16 = false>
+static int launch_spec(const void* audio, int channels, int64_t audio_stride, const int32_t* d_n, int B, float* out,
                        int64_t out_stride, float* mean_std, double* partials, int n_partials, int tiles, int center,
                        int normalize, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    DSB_CUDA(cudaFuncSetAttribute(spectrogram_kernel<MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DSB_CUDA(cudaFuncSetAttribute(spectrogram_kernel<MODE, T, S16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(SpecSmemT<T>)));
     attr_set = true;
   }
   dim3 grid(tiles, B);
-  spectrogram_kernel<MODE, T><<<grid, kWarps * 32, sizeof(SpecSmemT<T>), st>>>(audio, audio_stride, d_n, out, out_stride,
+  spectrogram_kernel<MODE, T, S16><<<grid, kWarps * 32, sizeof(SpecSmemT<T>), st>>>(audio, channels, audio_stride, d_n, out, out_stride,
                                                                       mean_std, partials, n_partials, center,
                                                                       normalize);
   DSB_CHECK_LAUNCH();
@@ -423,32 +437,38 @@ extern "C" int dsb_spectrogram_num_frames(int n_samples) { return 1 + n_samples 
 extern "C" int dsb_spectrogram_partials(int max_frames) { return cdiv(max_frames > 0 ? max_frames : 1, kFT); }
 
 
-extern "C" int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int B,
-                                   int max_samples, float* out, int64_t out_stride, float* mean_std,
-                                   double* partials, int flags, void* stream) {
+static int spectrogram_offline(const void* audio, bool s16, int channels, int64_t audio_stride,
+                               const int32_t* n_samples, int B, int max_samples, float* out, int64_t out_stride,
+                               float* mean_std, double* partials, int flags, void* stream) {
   const int normalize = flags & DSB_SPECT_NORMALIZE;
   const bool fast = (flags & DSB_SPECT_FAST_FFT) != 0;
-  DSB_REQUIRE(audio && n_samples && out && partials && B > 0, "dsb_spectrogram_f32: null argument or B <= 0");
-  DSB_REQUIRE(max_samples >= 2 && max_samples <= audio_stride, "dsb_spectrogram_f32: max_samples %d out of range",
+  DSB_REQUIRE(audio && n_samples && out && partials && B > 0, "dsb_spectrogram: null argument or B <= 0");
+  DSB_REQUIRE(max_samples >= 2 && max_samples <= audio_stride, "dsb_spectrogram: max_samples %d out of range",
               max_samples);
+  DSB_REQUIRE(channels >= 1 && channels <= 8, "dsb_spectrogram: channels %d", channels);
   if (int e = ensure_tables()) return e;
   cudaStream_t st = (cudaStream_t)stream;
   const int max_frames = 1 + max_samples / kHop;
-  DSB_REQUIRE(out_stride >= max_frames, "dsb_spectrogram_f32: out_stride %lld < frames %d", (long long)out_stride,
+  DSB_REQUIRE(out_stride >= max_frames, "dsb_spectrogram: out_stride %lld < frames %d", (long long)out_stride,
               max_frames);
   const int n_partials = dsb_spectrogram_partials((int)out_stride);
-  const int tiles_valid = cdiv(max_frames, kFT);
   const int tiles_all = cdiv((int)out_stride, kFT);
   ProfScope scope(ST_SPECT, st);
-  (void)tiles_valid;
-  // one fp64 FFT pass writes log1p|X| and per-tile (sum, sum of squares); the normalisation is a cheap
+  // one FFT pass writes log1p|X| and per-tile (sum, sum of squares); the normalisation is a cheap
   // elementwise pass over data that is still in L2 (the FFT is instruction-bound, not HBM-bound, so
   // recomputing it for the second pass would double the kernel time)
-  if (int e = fast ? launch_spec<MODE_RAW, float>(audio, audio_stride, n_samples, B, out, out_stride, nullptr, partials,
-                                                  n_partials, tiles_all, 1, 0, st)
-                   : launch_spec<MODE_RAW, double>(audio, audio_stride, n_samples, B, out, out_stride, nullptr, partials,
-                                                   n_partials, tiles_all, 1, 0, st))
-    return e;
+  int e;
+  if (s16)
+    e = fast ? launch_spec<MODE_RAW, float, true>(audio, channels, audio_stride, n_samples, B, out, out_stride, nullptr,
+                                                  partials, n_partials, tiles_all, 1, 0, st)
+             : launch_spec<MODE_RAW, double, true>(audio, channels, audio_stride, n_samples, B, out, out_stride, nullptr,
+                                                   partials, n_partials, tiles_all, 1, 0, st);
+  else
+    e = fast ? launch_spec<MODE_RAW, float, false>(audio, 1, audio_stride, n_samples, B, out, out_stride, nullptr,
+                                                   partials, n_partials, tiles_all, 1, 0, st)
+             : launch_spec<MODE_RAW, double, false>(audio, 1, audio_stride, n_samples, B, out, out_stride, nullptr,
+                                                    partials, n_partials, tiles_all, 1, 0, st);
+  if (e) return e;
   if (!normalize) return 0;
   stream_stats_kernel<<<cdiv(B, 128), 128, 0, st>>>(partials, n_partials, n_samples, nullptr, B, 1, normalize,
                                                    mean_std, audio_stride);
@@ -463,6 +483,20 @@ extern "C" int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, con
   return 0;
 }
 
+extern "C" int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int B,
+                                   int max_samples, float* out, int64_t out_stride, float* mean_std,
+                                   double* partials, int flags, void* stream) {
+  return spectrogram_offline(audio, false, 1, audio_stride, n_samples, B, max_samples, out, out_stride, mean_std,
+                             partials, flags, stream);
+}
+
+extern "C" int dsb_spectrogram_s16(const int16_t* audio, int channels, int64_t audio_stride, const int32_t* n_samples,
+                                   int B, int max_samples, float* out, int64_t out_stride, float* mean_std,
+                                   double* partials, int flags, void* stream) {
+  return spectrogram_offline(audio, true, channels, audio_stride, n_samples, B, max_samples, out, out_stride, mean_std,
+                             partials, flags, stream);
+}
+
 extern "C" int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int S,
                                           int max_samples, float* out, int64_t out_stride, double* stats,
                                           double* partials, void* stream) {
@@ -474,7 +508,7 @@ extern "C" int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stri
   const int max_frames = 1 + (max_samples - kNfft) / kHop;
   DSB_REQUIRE(out_stride >= max_frames, "dsb_spectrogram_stream_f32: out_stride too small");
   const int n_partials = dsb_spectrogram_partials((int)out_stride);
-  if (int e = launch_spec<MODE_RAW, double>(audio, audio_stride, n_samples, S, out, out_stride, nullptr, partials,
+  if (int e = launch_spec<MODE_RAW, double, false>(audio, 1, audio_stride, n_samples, S, out, out_stride, nullptr, partials,
                                     n_partials, cdiv((int)out_stride, kFT), 0, 0, st))
     return e;
   stream_stats_kernel<<<cdiv(S, 128), 128, 0, st>>>(partials, n_partials, n_samples, stats, S, 0, 1, nullptr,

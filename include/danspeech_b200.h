@@ -68,6 +68,14 @@ int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, const int32_t*
                         int max_samples, float* out, int64_t out_stride, float* mean_std, double* partials,
                         int flags, void* stream);
 
+/* Same, fed with interleaved 16-bit PCM as it comes out of a WAV file ("next" row SURVEY 8f-3: replaces
+ * AudioData.get_array_data / _wav2array / audioop.tomono, danspeech/audio/resources.py:142-171,302-303,630-640):
+ *   audio  device s16 [B, audio_stride frames, channels]; channels are mixed down as clip(sum), the
+ *          audioop.tomono(buf, width, 1, 1) semantics of load_audio (quirk Q1).  Halves the host->device bytes. */
+int dsb_spectrogram_s16(const int16_t* audio, int channels, int64_t audio_stride, const int32_t* n_samples, int B,
+                        int max_samples, float* out, int64_t out_stride, float* mean_std, double* partials,
+                        int flags, void* stream);
+
 /* Streaming spectrogram (replaces parsers.py:101-163, InferenceSpectrogramAudioParser:
  * center=False STFT of an already assembled chunk, log1p, BIASED mean/std of the chunk
  * returned to the host, which owns the running-statistics recurrence; then

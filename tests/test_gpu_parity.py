@@ -377,3 +377,24 @@ def test_large_batch_falls_back_to_per_step_recurrence():
     assert probs.shape[0] == B
     assert logit_rel_err(probs[0].cpu().numpy(), ref[0].numpy()) < BF16_TOL
     assert torch.equal(probs[0], probs[B - 1])
+
+
+def test_pcm16_ingest_equals_host_mixdown():
+    """interleaved s16 stereo mixed down on the GPU as clip(L+R) == the reference loader's result."""
+    from danspeech_b200.audio.parsers import SpectrogramAudioParser
+    rng = np.random.default_rng(8)
+    ns = [24000, 9001]
+    pcm = torch.zeros((2, 24000, 2), dtype=torch.int16)
+    floats = []
+    for b, n in enumerate(ns):
+        st = rng.integers(-30000, 30000, size=(n, 2)).astype(np.int16)     # loud: exercises the clipping
+        pcm[b, :n] = torch.from_numpy(st)
+        floats.append(np.clip(st.astype(np.int64).sum(1), -32768, 32767).astype(np.float64))
+    p = SpectrogramAudioParser()
+    x16, l16 = p.parse_pcm16(pcm, ns)
+    xf, lf = p.parse_batch(floats)
+    assert l16.tolist() == lf.tolist()
+    assert torch.equal(x16, xf)
+    mono = torch.from_numpy(floats[0].astype(np.int16)).view(1, -1)
+    xm, _ = p.parse_pcm16(mono, [ns[0]])
+    assert torch.equal(xm[0], xf[0])
