@@ -30,6 +30,10 @@ struct ConvTcParams {
   int B, Tp, Din, Dout, KH, KW, sd, pd, pt;
   int rnn_layout;             // 0: [B][Dout][Tp][NOUT]   1: [(t*B+b)][Dout*NOUT] (feature = d*NOUT + co)
   int64_t out_ld;             // row stride of the rnn layout
+  // Segmented time axis (streaming, B == 1): the Tp frames are nb segments of seg_len frames, one per stream,
+  // each [seg_off zeros | seg_valid frames | zeros]; only the seg_valid frames of a segment are outputs and
+  // frame u of segment s is written as (b = s, t = u - seg_off).  seg_len == 0: plain layout.
+  int seg_len, seg_off, seg_valid, nb;
 };
 
 template <int NOUT, int CIN>
@@ -166,12 +170,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       decode(tile, b, d, t0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int t = t0 + q * 32 + lane;
-      const bool valid = t < p.Tp;
-      const bool live = valid && t < p.lens[b];
+      int t = t0 + q * 32 + lane;
+      bool valid = t < p.Tp;
+      int nb = p.B;
+      if (p.seg_len) {
+        b = t / p.seg_len;
+        t -= b * p.seg_len + p.seg_off;
+        valid = valid && t >= 0 && t < p.seg_valid;
+        nb = p.nb;
+      }
+      const bool live = valid && (p.lens == nullptr || t < p.lens[b]);
       __nv_bfloat16* dst = nullptr;
       if (valid)
-        dst = p.rnn_layout ? p.out + ((int64_t)t * p.B + b) * p.out_ld + (int64_t)d * NOUT
+        dst = p.rnn_layout ? p.out + ((int64_t)t * nb + b) * p.out_ld + (int64_t)d * NOUT
                            : p.out + (((int64_t)b * p.Dout + d) * p.Tp + t) * NOUT;
       const uint32_t t_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 #pragma unroll
@@ -298,9 +309,14 @@ int pack_conv_w_tc(const ConvLayer& L, bool first, __nv_bfloat16* out, cudaStrea
 }
 
 // x: block 0 -> time-expanded spectrogram [B][161][Tp][16]; later blocks -> [B][Din][Tp][32]
+// d_len == nullptr: no length mask.  seg != nullptr: segmented time axis {seg_len, seg_off, seg_valid, n_streams}.
 int conv_block_tc(const __nv_bfloat16* x, const ConvLayer& L, bool first, const int32_t* d_len, int B, int Tp,
-                  __nv_bfloat16* out, bool rnn_layout, int64_t out_ld, cudaStream_t st) {
+                  __nv_bfloat16* out, bool rnn_layout, int64_t out_ld, cudaStream_t st, const int* seg) {
   tc::ConvTcParams p{};
+  if (seg) {
+    if (B != 1 || !rnn_layout) return set_error(DSB_ERR_INVALID, "conv_block_tc: segmented mode needs B == 1 and the rnn layout");
+    p.seg_len = seg[0]; p.seg_off = seg[1]; p.seg_valid = seg[2]; p.nb = seg[3];
+  }
   p.bias = L.bias;
   p.lens = d_len;
   p.out = out;

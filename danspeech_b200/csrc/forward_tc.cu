@@ -31,6 +31,13 @@ __global__ void fold_rnn_bias_kernel(const float* __restrict__ b_ih, const float
   }
 }
 
+int f32_to_bf16_ld(const float* x, __nv_bfloat16* y, int64_t rows, int cols, int ld, cudaStream_t st) {
+  const int64_t n = rows * cols;
+  f32_to_bf16_ld_kernel<<<(int)(cdiv64(n, 256) < 4096 ? cdiv64(n, 256) : 4096), 256, 0, st>>>(x, y, rows, cols, ld);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
 template <typename T>
 static int dev_alloc_tc(dsb_model* m, T** p, int64_t n) {
   void* q = nullptr;
@@ -146,8 +153,8 @@ TcWorkspace carve_tc(const dsb_model* m, int B, int T, void* base) {
   const size_t o_g = take(sizeof(float) * (size_t)Tp * B * dirs * G * H);
   const size_t o_y = take(sizeof(float) * (size_t)dirs * Tp * B * H);
   const size_t o_xf = take(sizeof(float) * (size_t)Tp * B * H);
-  const size_t o_hb = take(sizeof(__nv_bfloat16) * 2 * (size_t)dirs * 128 * HP);
-  const size_t o_sw = take(64);
+  const size_t o_hb = take(sizeof(__nv_bfloat16) * rnn_tc_hbuf_elems(m->rnns[0], B));
+  const size_t o_sw = take(sizeof(unsigned int) * (kRnnSyncCounters + 1));
   const size_t o_h = take(sizeof(float) * 2 * (size_t)dirs * B * H);
   const size_t o_c = take(sizeof(float) * (size_t)dirs * B * H);
   const size_t o_l = take(sizeof(float) * (size_t)Tp * B * d.num_classes);
@@ -185,7 +192,7 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
   const int H = d.rnn_hidden_size, C = d.num_classes;
   const int64_t M = (int64_t)Tp * B;
   DSB_CUDA(cudaMemcpyAsync(ws.d_len, h_out_len, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
-  DSB_CUDA(cudaMemsetAsync(ws.sync_words, 0, 64, st));   // step counters + abort flag
+  DSB_CUDA(cudaMemsetAsync(ws.sync_words, 0, sizeof(unsigned int) * (kRnnSyncCounters + 1), st));   // step counters + abort flag
 
   prof_begin(ST_CONV, st);
   if (int e = im2col_time_tc(spect, ws.cb[0], B, T, Tp, st)) return e;
@@ -207,7 +214,7 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
     const RnnLayer& R = m->rnns[l];
     const bool last = l + 1 == m->rnns.size();
     const int N = R.dirs * R.gates * R.H;
-    const bool tc_rnn = R.tc_recurrence && B <= 128;
+    const bool tc_rnn = R.tc_recurrence;
     prof_begin(ST_PROJ, st);
     if (int e = gemm_bias_tc(ws.xb, R.in_ld, R.w_ih_tc, R.in_ld, tc_rnn ? R.b_ih_tc : R.b_ih, ws.gates, N, (int)M, N,
                              R.in_size, st))
@@ -244,7 +251,7 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
   if (used_tc_rnn) {
     // the persistent recurrence never spins forever: a stuck step barrier raises this flag instead
     int abort_flag = 0;
-    DSB_CUDA(cudaMemcpyAsync(&abort_flag, ws.sync_words + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DSB_CUDA(cudaMemcpyAsync(&abort_flag, ws.sync_words + kRnnSyncCounters, sizeof(int), cudaMemcpyDeviceToHost, st));
     DSB_CUDA(cudaStreamSynchronize(st));
     if (abort_flag) return set_error(DSB_ERR_CUDA, "dsb_forward: persistent recurrence step barrier timed out");
   }

@@ -52,6 +52,52 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 constexpr int BM = 128, BK = 64, STAGES = 4;
 constexpr int GEMM_THREADS = 192;
 
+
+// Epilogue of one 128-row accumulator tile: this thread owns one row (TMEM lane) and walks the BN columns in
+// chunks of 16, with the next tcgen05.ld in flight while the current chunk is stored.  Rows are written with
+// 256-bit stores (one full 32-byte sector per thread per instruction) when the output is 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void store_chunk16(const uint32_t (&r)[16], float* __restrict__ C, int64_t ldc, int row, int M,
+                                              int N, int col, const float* __restrict__ bias, bool vec_ok) {
+  if (row >= M) return;
+  float* dst = C + (int64_t)row * ldc + col;
+  if (vec_ok && col + 16 <= N) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]) + (bias ? __ldg(bias + col + j + i) : 0.f);
+      st_global_v8(dst + j, v);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col + j < N) dst[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + col + j) : 0.f);
+  }
+}
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(uint32_t t_addr, float* __restrict__ C, int64_t ldc, int row, int M, int N,
+                                              int n0, const float* __restrict__ bias, bool vec_ok) {
+  static_assert(BN % 16 == 0, "BN must be a multiple of 16");
+  uint32_t ra[16], rb[16];
+  tmem_ld16(t_addr, ra);
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    tmem_ld_wait_dep(ra);
+    if (c0 + 16 < BN) tmem_ld16(t_addr + c0 + 16, rb);
+    store_chunk16(ra, C, ldc, row, M, N, n0 + c0, bias, vec_ok);
+    if (c0 + 16 < BN) {
+      tmem_ld_wait_dep(rb);
+      if (c0 + 32 < BN) tmem_ld16(t_addr + c0 + 32, ra);
+      store_chunk16(rb, C, ldc, row, M, N, n0 + c0 + 16, bias, vec_ok);
+    }
+  }
+}
+
 template <int BN>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -159,37 +205,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+    const bool vec_ok = (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0 && (BN & 7) == 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t t_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_addr + c0, r);
-        tmem_ld_wait();
-        if (row < M) {
-          float* dst = C + (int64_t)row * ldc + n0 + c0;
-          if (vec_ok && n0 + c0 + 16 <= N) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 v;
-              v.x = __uint_as_float(r[j + 0]) + (bias ? __ldg(bias + n0 + c0 + j + 0) : 0.f);
-              v.y = __uint_as_float(r[j + 1]) + (bias ? __ldg(bias + n0 + c0 + j + 1) : 0.f);
-              v.z = __uint_as_float(r[j + 2]) + (bias ? __ldg(bias + n0 + c0 + j + 2) : 0.f);
-              v.w = __uint_as_float(r[j + 3]) + (bias ? __ldg(bias + n0 + c0 + j + 3) : 0.f);
-              *reinterpret_cast<float4*>(dst + j) = v;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < N) dst[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f);
-          }
-        }
-      }
+      epilogue_tile<BN>(t_addr, C, ldc, row, M, N, n0, bias, vec_ok);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -329,37 +352,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+    const bool vec_ok = (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0 && (BN & 7) == 0;
     for (int tile = pair; tile < n_tiles; tile += n_pairs) {
       const int m0 = (tile / n_blocks) * 2 * BM + rank * BM, n0 = (tile % n_blocks) * BN;
       mbar_wait_trap(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t t_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_addr + c0, r);
-        tmem_ld_wait();
-        if (row < M) {
-          float* dst = C + (int64_t)row * ldc + n0 + c0;
-          if (vec_ok && n0 + c0 + 16 <= N) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 v;
-              v.x = __uint_as_float(r[j + 0]) + (bias ? __ldg(bias + n0 + c0 + j + 0) : 0.f);
-              v.y = __uint_as_float(r[j + 1]) + (bias ? __ldg(bias + n0 + c0 + j + 1) : 0.f);
-              v.z = __uint_as_float(r[j + 2]) + (bias ? __ldg(bias + n0 + c0 + j + 2) : 0.f);
-              v.w = __uint_as_float(r[j + 3]) + (bias ? __ldg(bias + n0 + c0 + j + 3) : 0.f);
-              *reinterpret_cast<float4*>(dst + j) = v;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < N) dst[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f);
-          }
-        }
-      }
+      epilogue_tile<BN>(t_addr, C, ldc, row, M, N, n0, bias, vec_ok);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));   // the leader's barrier

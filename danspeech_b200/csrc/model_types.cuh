@@ -74,13 +74,17 @@ int gemm_bias_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
 int im2col_time_tc(const float* spect, __nv_bfloat16* x1, int B, int T, int Tp, cudaStream_t st);
 int pack_conv_w_tc(const ConvLayer& L, bool first, __nv_bfloat16* out, cudaStream_t st);
 int conv_block_tc(const __nv_bfloat16* x, const ConvLayer& L, bool first, const int32_t* d_len, int B, int Tp,
-                  __nv_bfloat16* out, bool rnn_layout, int64_t out_ld, cudaStream_t st);
+                  __nv_bfloat16* out, bool rnn_layout, int64_t out_ld, cudaStream_t st, const int* seg = nullptr);
 bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* launches_out);
 int pack_whh_tc(const RnnLayer& L, __nv_bfloat16* out, cudaStream_t st);
 int combine_dirs_tc(const float* y, int dirs, int T, int B, int H, const int32_t* d_len, __nv_bfloat16* xb, int ldx,
                     float* xf, cudaStream_t st);
+constexpr int kRnnSyncCounters = 16;   // sync words: [0,16) step counters, [16] abort flag
+size_t rnn_tc_hbuf_elems(const RnnLayer& L, int B);
 int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
-                 __nv_bfloat16* hbuf, unsigned int* sync_words, cudaStream_t st);
+                 __nv_bfloat16* hbuf, unsigned int* sync_words, cudaStream_t st, const float* h0 = nullptr,
+                 const float* c0 = nullptr, float* hT = nullptr, float* cT = nullptr);
+int f32_to_bf16_ld(const float* x, __nv_bfloat16* y, int64_t rows, int cols, int ld, cudaStream_t st);
 int finalize_tc(dsb_model* m, cudaStream_t st);
 size_t forward_tc_workspace_bytes(const dsb_model* m, int B, int T);
 int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B, int T, float* probs,

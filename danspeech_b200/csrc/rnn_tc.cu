@@ -65,14 +65,20 @@ struct RnnTcParams {
   const float* gx;          // [T*B][dirs*G*H]
   const float* b_hn;        // [dirs][H] GRU n-gate hidden bias (else nullptr)
   float* y;                 // [dirs][T][B][H]
-  __nv_bfloat16* hbuf;      // [2][dirs][BP][HP]
-  const int32_t* lens;      // [B]
-  unsigned int* counters;   // [dirs]
+  __nv_bfloat16* hbuf;      // [n_bgroups][2][dirs][BP][HP]
+  const int32_t* lens;      // [B] or nullptr (every sequence runs Tmax steps)
+  unsigned int* counters;   // [dirs][slots]
   int* abort_flag;
+  const float* h0;          // [dirs][B][H] initial hidden state or nullptr (zeros)
+  const float* c0;          // LSTM cell state, likewise
+  float* hT;                // [dirs][B][H] final hidden state or nullptr
+  float* cT;
   int B, H, HP, BP, T, Tmax;
   int dirs;   // directions in gx / y / hbuf / counters
   int dir0;   // first direction handled by this launch
-  int cpd;    // CTAs per direction
+  int cpd;    // CTAs per (direction, slot)
+  int n_bgroups;   // the batch is processed in groups of BP rows ...
+  int slots;       // ... by `slots` independent CTA sets per direction (set k takes groups k, k+slots, ...)
   int U;      // hidden units per CTA (2 * units per half)
   int nkc;    // K chunks of 64 (HP / 64)
   unsigned long long* dbg;   // optional [grid][16] cycle counters (DSB_RNN_DEBUG=1)
@@ -145,8 +151,9 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   const int gps = (p.nkc + RT_GROUP - 1) / RT_GROUP;   // group uses per step
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int dir_local = blockIdx.x / p.cpd;
-  const int dir = p.dir0 + dir_local;
+  const int set = blockIdx.x / p.cpd;          // (direction, slot)
+  const int dir = p.dir0 + set / p.slots;
+  const int slot = set % p.slots;
   const int c = blockIdx.x % p.cpd;
   // Optional clusters of CL CTAs (same direction) share the h stream by TMA multicast; every cluster (or
   // CTA) walks the K chunks in its own rotation so that the readers do not hit the same L2 lines together.
@@ -181,7 +188,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     }
     __syncwarp();
     bool ok = true;
-    const unsigned* ctr = p.counters + dir;
+    const unsigned* ctr = p.counters + dir * p.slots + slot;
     unsigned long long d_spin = 0, d_fence = 0, d_issue = 0, d_empty = 0;
     long long use = 0;   // group uses so far (ring position)
     // Arming a group (waiting for its slot, arrive.expect_tx on its stages) does not depend on h, so the first
@@ -211,6 +218,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       }
       __syncwarp();
     };
+    unsigned done = 0;   // steps of earlier batch groups (the step counter keeps counting across groups)
+    for (int bg = slot; bg < p.n_bgroups && ok; bg += p.slots, done += (unsigned)p.Tmax)
     for (int s = 0; s < p.Tmax && ok; ++s) {
       long long c0 = clock64();
       const int pre = min(gps, n_groups);
@@ -218,9 +227,10 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       if (!ok) break;
       d_empty += clock64() - c0;
       c0 = clock64();
-      if (s > 0) {
-        // direction-wide barrier: every CTA of this direction has published h_{s-1}
-        const unsigned target = (unsigned)p.cpd * (unsigned)s;
+      if (s > 0 || done > 0) {
+        // set-wide barrier: every CTA of this set has published h_{s-1} (at s = 0 of a later batch group:
+        // has finished the previous group, so its TMEM accumulator and staging buffers are free again)
+        const unsigned target = (unsigned)p.cpd * (done + (unsigned)s);
         long long t0 = 0;
         unsigned n = 0;
         while (ld_acquire_gpu(ctr) < target) {
@@ -240,7 +250,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       }
       long long c2 = clock64();
       if (p.dbg && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 15] = c2;
-      const int row0 = ((s & 1) * p.dirs + dir) * p.BP;
+      const int row0 = ((bg * 2 + (s & 1)) * p.dirs + dir) * p.BP;
       for (int g = 0; g < gps && ok; ++g) {
         if (g >= pre) {
           long long w0 = clock64();
@@ -266,6 +276,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     bool ok = __all_sync(0xffffffffu, wait_abortable(wbar, 0, p.abort_flag));
     unsigned long long d_wait0 = 0, d_rest = 0, d_waitn = 0;
     long long use = 0;
+    for (int bg = slot; bg < p.n_bgroups && ok; bg += p.slots)
     for (int s = 0; s < p.Tmax && ok; ++s) {
       long long m0 = clock64();
       for (int g = 0; g < gps; ++g, ++use) {
@@ -310,18 +321,13 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int rpq = p.BP >> 2;
-    const int b = q * rpq + lane;
-    const bool row_ok = lane < rpq && b < p.B;
-    const int len = row_ok ? p.lens[b] : 0;
+    const int lrow = q * rpq + lane;     // row inside the batch group (= TMEM lane / hbuf row)
     const int j0 = c * U + half * UH;
     const int ncol = p.dirs * GATES * p.H;
     float hprev[UH], cst[UH], bhn[UH];
 #pragma unroll
-    for (int u = 0; u < UH; ++u) {
-      hprev[u] = 0.f;
-      cst[u] = 0.f;
+    for (int u = 0; u < UH; ++u)
       bhn[u] = (GATES == 3 && p.b_hn && j0 + u < p.H) ? p.b_hn[(size_t)dir * p.H + j0 + u] : 0.f;
-    }
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
     // h store staging sH [BP][U] bf16 + row validity sT [BP].  Single-buffered: the next write happens after
     // this CTA's publish of the step (behind the second named barrier), i.e. after every read of it.
@@ -329,6 +335,18 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     __shared__ int sT[128];
     const bool vec2 = ((p.H & 1) == 0) && ((UH & 1) == 0);
     unsigned long long e_load = 0, e_wait = 0, e_math = 0, e_bar = 0, e_pub = 0;
+    unsigned done = 0;
+    bool alive = true;
+    for (int bg = slot; bg < p.n_bgroups && alive; bg += p.slots, done += (unsigned)p.Tmax) {
+    const int b = bg * p.BP + lrow;
+    const bool row_ok = lane < rpq && b < p.B;
+    const int len = row_ok ? (p.lens ? p.lens[b] : p.Tmax) : 0;
+#pragma unroll
+    for (int u = 0; u < UH; ++u) {
+      const bool in = row_ok && j0 + u < p.H;
+      hprev[u] = (p.h0 && in) ? p.h0[((size_t)dir * p.B + b) * p.H + j0 + u] : 0.f;
+      cst[u] = (p.c0 && in) ? p.c0[((size_t)dir * p.B + b) * p.H + j0 + u] : 0.f;
+    }
     for (int s = 0; s < p.Tmax; ++s) {
       long long e0 = clock64();
       const bool active = row_ok && s < len;
@@ -352,9 +370,9 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             for (int u = 0; u < UH; ++u) gxv[g][u] = (j0 + u < p.H) ? __ldg(gp + (size_t)g * p.H + u) : 0.f;
         }
       }
-      if (half == 0 && lane < rpq) sT[q * rpq + lane] = active ? t : -1;
+      if (half == 0 && lane < rpq) sT[lrow] = active ? t : -1;
       long long e1 = clock64();
-      const bool ok = wait_abortable(dfull, (uint32_t)(s & 1), p.abort_flag);
+      const bool ok = wait_abortable(dfull, (uint32_t)((done + (unsigned)s) & 1u), p.abort_flag);
       long long e2 = clock64();
       if (p.dbg && s == 100 && et == 64) p.dbg[blockIdx.x * 128 + 65] = e2;
       tc_fence_after();
@@ -363,7 +381,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       tmem_ld_wait();
       tc_fence_before();
       if (ok && active) {
-        __nv_bfloat16* sh = sH + (size_t)b * U + half * UH;
+        __nv_bfloat16* sh = sH + (size_t)lrow * U + half * UH;
 #pragma unroll
         for (int u = 0; u < UH; ++u) {
           float hn;
@@ -388,11 +406,11 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       }
       long long e3 = clock64();
       const bool all_ok = bar_red_and(ok, 1, 256);     // staging complete (and uniform abort decision)
-      if (!all_ok) break;
+      if (!all_ok) { alive = false; break; }
       // h_t -> global (bf16), coalesced: each row contributes U contiguous values
       {
         const int n_valid = min(U, p.H - c * U);       // units of this CTA inside H
-        __nv_bfloat16* hrow0 = p.hbuf + ((size_t)(((s + 1) & 1) * p.dirs + dir) * p.BP) * p.HP + c * U;
+        __nv_bfloat16* hrow0 = p.hbuf + ((size_t)((bg * 2 + ((s + 1) & 1)) * p.dirs + dir) * p.BP) * p.HP + c * U;
         if ((U & 3) == 0 && n_valid == U && (p.HP & 3) == 0) {
           const int per_row = U / 4;                   // 8-byte pieces
           for (int i = et; i < p.BP * per_row; i += 256) {
@@ -410,7 +428,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       }
       named_bar_sync(2, 256);                          // all h stores issued
       long long e4 = clock64();
-      if (et == 0) red_release_gpu_add(p.counters + dir, 1u);   // publish h_t (release: cumulative over the CTA)
+      if (et == 0) red_release_gpu_add(p.counters + dir * p.slots + slot, 1u);   // publish h_t (release: cumulative over the CTA)
       if (p.dbg && s == 99 && et == 0) p.dbg[blockIdx.x * 128 + 66] = clock64();
       if (p.dbg && s == 100 && et == 0) p.dbg[blockIdx.x * 128 + 67] = clock64();
       // y_t -> global (fp32) straight from registers, after the publish: nobody waits on these stores
@@ -427,6 +445,15 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         }
       }
       e_load += e1 - e0; e_wait += e2 - e1; e_math += e3 - e2; e_bar += e4 - e3; e_pub += clock64() - e4;
+    }
+    if (alive && row_ok) {   // carry the state out (streaming): the last active step's h (and c)
+#pragma unroll
+      for (int u = 0; u < UH; ++u)
+        if (j0 + u < p.H) {
+          if (p.hT) p.hT[((size_t)dir * p.B + b) * p.H + j0 + u] = hprev[u];
+          if (p.cT) p.cT[((size_t)dir * p.B + b) * p.H + j0 + u] = cst[u];
+        }
+    }
     }
     if (p.dbg && et == 64) {   // warp 4: quarter 0, an active row
       p.dbg[blockIdx.x * 128 + 5] = e_load;
@@ -488,15 +515,22 @@ __global__ void combine_dirs_kernel(const float* __restrict__ y, int dirs, int T
 
 }  // namespace tc
 
+// Batches larger than 128 run as groups of 128 rows inside the same launch (W_hh stays resident); when the
+// CTAs of one direction leave SMs free, several groups run side by side on independent CTA sets ("slots").
 bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* launches_out) {
   const int UH = 32 / L.gates, U = 2 * UH;
   const int cpd = cdiv(L.H, U);
   const int HP = (L.H + 63) / 64 * 64;
   const tc::RtPlan pl = tc::rt_plan(HP / 64, B <= 64 ? 64 : 128, U);
-  if (B > 128 || pl.groups < 1 || pl.total > tc::RT_SMEM_LIMIT || cpd > sms) return false;
+  if (B < 1 || pl.groups < 1 || pl.total > tc::RT_SMEM_LIMIT || cpd > sms) return false;
   if (cpd_out) *cpd_out = cpd;
   if (launches_out) *launches_out = (L.dirs * cpd <= sms) ? 1 : L.dirs;
   return true;
+}
+
+size_t rnn_tc_hbuf_elems(const RnnLayer& L, int B) {
+  const int HP = (L.H + 63) / 64 * 64, BP = B <= 64 ? 64 : 128;
+  return (size_t)cdiv(B, BP) * 2 * L.dirs * BP * HP;
 }
 
 int pack_whh_tc(const RnnLayer& L, __nv_bfloat16* out, cudaStream_t st) {
@@ -557,10 +591,30 @@ int combine_dirs_tc(const float* y, int dirs, int T, int B, int H, const int32_t
   return 0;
 }
 
+namespace tc {
+// slot 0 of every batch group's exchange buffer <- bf16(h0); rows/columns beyond B/H stay zero
+__global__ void init_hbuf_kernel(const float* __restrict__ h0, __nv_bfloat16* __restrict__ hbuf, int dirs, int B, int H,
+                                 int HP, int BP, int n_bgroups) {
+  const int64_t total = (int64_t)n_bgroups * dirs * BP * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % H);
+    int64_t r = i / H;
+    const int row = (int)(r % BP);
+    r /= BP;
+    const int d = (int)(r % dirs), bg = (int)(r / dirs);
+    const int b = bg * BP + row;
+    if (b < B) hbuf[(((int64_t)(bg * 2) * dirs + d) * BP + row) * HP + k] = __float2bfloat16_rn(h0[((int64_t)d * B + b) * H + k]);
+  }
+}
+}  // namespace tc
+
 // One BatchRNN layer.  gx [T*B][dirs*G*H] fp32, y [dirs][T][B][H] fp32 (rows t >= len_b are NOT written),
-// hbuf [2][dirs][BP][HP] bf16, sync = {counters[dirs] u32, abort i32} (device).
+// hbuf rnn_tc_hbuf_elems() bf16, sync = {counters[<= kRnnSyncCounters] u32, abort i32} (device).
+// d_len == nullptr: every sequence runs Tmax steps.  h0/c0 (nullptr = zeros) and hT/cT (nullptr = dropped)
+// are [dirs][B][H] fp32 and may alias (streaming state carried across chunks, model.py:219-237).
 int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
-                 __nv_bfloat16* hbuf, unsigned int* sync_words, cudaStream_t st) {
+                 __nv_bfloat16* hbuf, unsigned int* sync_words, cudaStream_t st, const float* h0, const float* c0,
+                 float* hT, float* cT) {
   using namespace tc;
   int dev = 0, sms = 148, cpd = 0, launches = 1;
   cudaGetDevice(&dev);
@@ -568,15 +622,27 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   if (!rnn_tc_supported(L, B, sms, &cpd, &launches))
     return set_error(DSB_ERR_UNSUPPORTED, "rnn_layer_tc: shape H=%d B=%d not supported", L.H, B);
   const int HP = (L.H + 63) / 64 * 64, BP = B <= 64 ? 64 : 128, nkc = HP / 64;
-  DSB_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(__nv_bfloat16) * 2 * (size_t)L.dirs * BP * HP, st));
-  DSB_CUDA(cudaMemsetAsync(sync_words, 0, sizeof(unsigned int) * 2, st));   // step counters only; abort flag is sticky
+  const int n_bgroups = cdiv(B, BP);
+  const int dirs_per_launch_ = L.dirs / launches;
+  int slots = sms / (dirs_per_launch_ * cpd);
+  if (slots > n_bgroups) slots = n_bgroups;
+  if (slots * L.dirs > kRnnSyncCounters) slots = kRnnSyncCounters / L.dirs;
+  if (slots < 1) slots = 1;
+  DSB_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(__nv_bfloat16) * rnn_tc_hbuf_elems(L, B), st));
+  DSB_CUDA(cudaMemsetAsync(sync_words, 0, sizeof(unsigned int) * kRnnSyncCounters, st));   // step counters only; abort flag is sticky
+  if (h0) {
+    const int64_t total = (int64_t)n_bgroups * L.dirs * BP * L.H;
+    init_hbuf_kernel<<<(int)(cdiv64(total, 256) < 1184 ? cdiv64(total, 256) : 1184), 256, 0, st>>>(h0, hbuf, L.dirs, B, L.H, HP,
+                                                                                                 BP, n_bgroups);
+    DSB_CHECK_LAUNCH();
+  }
 
   CUtensorMap tw, th;
   uint64_t dw[2] = {(uint64_t)HP, (uint64_t)L.dirs * cpd * RT_N}, sw[2] = {2, (uint64_t)HP * 2};
   uint32_t bw[2] = {RT_BK, RT_N};
   if (int e = make_tmap_bf16(&tw, L.w_hh_pack, 2, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   // h exchange buffer as {64 k, rows, K chunks}: one box {64, BP, RT_GROUP} = RT_GROUP consecutive chunk tiles
-  uint64_t dh[3] = {(uint64_t)RT_BK, (uint64_t)2 * L.dirs * BP, (uint64_t)nkc};
+  uint64_t dh[3] = {(uint64_t)RT_BK, (uint64_t)n_bgroups * 2 * L.dirs * BP, (uint64_t)nkc};
   uint64_t sh[3] = {2, (uint64_t)HP * 2, (uint64_t)RT_BK * 2};
   uint32_t bh[3] = {RT_BK, (uint32_t)BP, RT_GROUP};
   if (int e = make_tmap_bf16(&th, hbuf, 3, dh, sh, bh, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
@@ -588,7 +654,9 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.hbuf = hbuf;
   p.lens = d_len;
   p.counters = sync_words;
-  p.abort_flag = reinterpret_cast<int*>(sync_words + 2);
+  p.abort_flag = reinterpret_cast<int*>(sync_words + kRnnSyncCounters);
+  p.h0 = h0; p.c0 = c0; p.hT = hT; p.cT = cT;
+  p.n_bgroups = n_bgroups; p.slots = slots;
   p.B = B; p.H = L.H; p.HP = HP; p.BP = BP; p.T = T; p.Tmax = Tmax;
   p.dirs = L.dirs; p.cpd = cpd; p.U = 2 * (32 / L.gates); p.nkc = nkc;
   const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates)).total;
@@ -598,7 +666,7 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   const int dirs_per_launch = L.dirs / launches;
   static const bool debug = getenv("DSB_RNN_DEBUG") != nullptr;
   unsigned long long* dbg = nullptr;
-  const int grid = dirs_per_launch * cpd;
+  const int grid = dirs_per_launch * slots * cpd;
   if (debug) {
     DSB_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * 128 * grid));
     DSB_CUDA(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 128 * grid, st));

@@ -233,6 +233,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but with the destination registers of an earlier tcgen05.ld threaded through the statement, so
+// that arithmetic on them cannot be scheduled above the wait when other work sits between the ld and the wait.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 // Shared-memory matrix descriptor, K-major operand whose rows are `ROW_BYTES` (= swizzle span) apart and
 // whose 8-row groups are SBO bytes apart.  SWIZZLE: 2 = 128B, 4 = 64B, 6 = 32B, 0 = none.

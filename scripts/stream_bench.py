@@ -14,7 +14,8 @@ from danspeech_b200.pretrained_models import build_model  # noqa: E402
 
 S = int(os.environ.get("STREAMS", "1024"))
 CHUNKS = int(os.environ.get("CHUNKS", "8"))
-model = build_model("CPUStreamingRNN", seed=0).cuda().eval().set_precision("fp32")
+PRECISION = os.environ.get("PRECISION", "bf16")
+model = build_model("CPUStreamingRNN", seed=0).cuda().eval().set_precision(PRECISION)
 gen = torch.Generator(device="cuda").manual_seed(0)
 first = torch.randn((S, 1, 161, 53), generator=gen, device="cuda")
 mid = torch.randn((S, 1, 161, 39), generator=gen, device="cuda")
@@ -40,5 +41,5 @@ prof = N.profile_read()
 audio_s = S * (8640 + 6240 * (CHUNKS - 1)) / 16000.0
 print(json.dumps({"workload": "CPUStreamingRNN-shaped (2 conv, 5 x 800 uni-GRU, lookahead 20), %d lock-step streams, "
                               "%d chunks (8640 then 6240 samples)" % (S, CHUNKS),
-                  "rtfx": audio_s / dt, "ms_per_chunk_step": 1e3 * dt / CHUNKS, "frames_out_per_stream": frames,
+                  "precision": PRECISION, "rtfx": audio_s / dt, "ms_per_chunk_step": 1e3 * dt / CHUNKS, "frames_out_per_stream": frames,
                   "streams_real_time": audio_s / dt, "stages_ms": {k: round(v[0], 2) for k, v in prof.items() if v[0] > 0}}))

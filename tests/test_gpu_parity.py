@@ -361,22 +361,84 @@ def test_edge_shapes_match_oracle(precision, tol):
         assert logit_rel_err(probs[b, :L].cpu().numpy(), ref[b, :L].numpy()) < tol
 
 
-def test_large_batch_falls_back_to_per_step_recurrence():
-    """More than 128 sequences: the persistent recurrence does not apply; the bf16 path must still be right."""
-    kw = dict(rnn_hidden_size=64, rnn_layers=1)
+def test_large_batch_runs_in_groups_of_128():
+    """More than 128 sequences: the persistent recurrence walks the batch in groups of 128 rows (ragged lengths)."""
+    kw = dict(rnn_hidden_size=64, rnn_layers=2)
     cfg = case_config("TestModel", kw)
     sd = syn.make_state_dict(seed=12, **cfg)
     m = _model("TestModel", kw, seed=12, precision="bf16")
     p = osp.SpectrogramOracle()
-    spec = p.parse_audio(syn.synthetic_audio(4000, seed=400))
-    B = 130
-    x = spec.view(1, 1, 161, -1).repeat(B, 1, 1, 1)
-    xl = torch.IntTensor([spec.size(1)] * B)
-    ref, rs = om.forward(sd, x[:1], xl[:1], cfg["conv_layers"], cfg["rnn_layers"])
+    long_, short = p.parse_audio(syn.synthetic_audio(4000, seed=400)), p.parse_audio(syn.synthetic_audio(2500, seed=401))
+    n_long, B = 100, 150
+    x = torch.zeros(B, 1, 161, long_.size(1))
+    x[:n_long, 0] = long_
+    x[n_long:, 0, :, : short.size(1)] = short
+    xl = torch.IntTensor([long_.size(1)] * n_long + [short.size(1)] * (B - n_long))
     probs, sizes = m(x.cuda(), xl)
     assert probs.shape[0] == B
-    assert logit_rel_err(probs[0].cpu().numpy(), ref[0].numpy()) < BF16_TOL
-    assert torch.equal(probs[0], probs[B - 1])
+    for b in (0, n_long - 1, n_long, 127, 128, B - 1):
+        one = (long_ if b < n_long else short).view(1, 1, 161, -1)
+        ref, rs = om.forward(sd, one, torch.IntTensor([one.size(3)]), cfg["conv_layers"], cfg["rnn_layers"])
+        L = int(sizes[b])
+        assert L == int(rs[0])
+        assert logit_rel_err(probs[b, :L].cpu().numpy(), ref[0, :L].numpy()) < BF16_TOL
+    L = int(sizes[B - 1])
+    assert torch.equal(probs[0], probs[n_long - 1])             # same group
+    assert torch.allclose(probs[n_long, :L], probs[B - 1, :L], rtol=1e-4, atol=1e-6)   # group 0 row vs group 1 row
+
+
+def test_streaming_forward_bf16_matches_golden(golden):
+    """Streaming on the tensor-core kernels (streams laid side by side in time, state carried in fp32)."""
+    from danspeech_b200.audio.parsers import InferenceSpectrogramAudioParser
+    m = _model("CPUStreamingRNN", dict(rnn_hidden_size=128, rnn_layers=3), seed=5, precision="bf16")
+    a = golden["smodel_audio"].astype(np.float64)
+    chunks = [a[:8640]] + [a[8640 + 6240 * i: 8640 + 6240 * (i + 1)] for i in range(5)]
+    sp = InferenceSpectrogramAudioParser()
+    frames, worst = [], 0.0
+    for i, c in enumerate(chunks):
+        last = i == len(chunks) - 1
+        o = m(sp.parse_audio(c, is_last=last).view(1, 1, 161, -1), i == 0, last)
+        ref = golden["smodel_probs_%d" % i]
+        if ref.size == 0:
+            assert o is None
+            frames.append(0)
+        else:
+            assert tuple(o.shape) == ref.shape
+            worst = max(worst, logit_rel_err(o.cpu().numpy(), ref))
+            frames.append(o.shape[1])
+    print("streaming bf16 worst logit rel err %.2e" % worst)
+    assert worst < BF16_TOL
+    assert frames[:3] == [0, 50, 35]
+
+
+def test_streaming_bf16_many_streams_in_groups():
+    """130 lock-step streams = two batch groups on two CTA sets; every stream must equal its solo run."""
+    from danspeech_b200.audio.parsers import InferenceSpectrogramAudioParser
+    m = _model("CPUStreamingRNN", dict(rnn_hidden_size=96, rnn_layers=2), seed=6, precision="bf16")
+    f = _model("CPUStreamingRNN", dict(rnn_hidden_size=96, rnn_layers=2), seed=6, precision="fp32")
+    S, K = 130, 3
+    auds = [syn.synthetic_audio(8640 + 6240 * 3, seed=70 + i) for i in range(K)]
+    specs = []
+    for a in auds:
+        sp = InferenceSpectrogramAudioParser()
+        specs.append([sp.parse_audio(c, is_last=(i == 3)) for i, c in enumerate(_stream_chunks(a))])
+    solo, exact = [[] for _ in range(K)], [[] for _ in range(K)]
+    for s in range(K):
+        for i in range(4):
+            o = m(specs[s][i].view(1, 1, 161, -1), i == 0, i == 3)
+            solo[s].append(None if o is None else o.clone())
+        for i in range(4):
+            o = f(specs[s][i].view(1, 1, 161, -1), i == 0, i == 3)
+            exact[s].append(None if o is None else o.clone())
+    for i in range(4):
+        x = torch.stack([specs[s % K][i] for s in range(S)]).view(S, 1, 161, -1)
+        o = m(x, i == 0, i == 3)
+        for s in (0, 1, 2, 63, 64, 127, 128, 129):
+            if solo[s % K][i] is None:
+                assert o is None
+            else:
+                assert logit_rel_err(o[s].cpu().numpy(), solo[s % K][i][0].cpu().numpy()) < 2e-3
+                assert logit_rel_err(o[s].cpu().numpy(), exact[s % K][i][0].cpu().numpy()) < BF16_TOL
 
 
 def test_pcm16_ingest_equals_host_mixdown():
