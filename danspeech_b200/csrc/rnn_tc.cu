@@ -273,6 +273,11 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   } else if (warp == 1) {
     // ---- MMA issuer: whole warp waits for the chunks of a group, one elected lane issues its 16 MMAs ----
     const uint32_t idesc = make_idesc_bf16(p.BP, RT_N);
+    // Descriptors differ only in their 14-bit address field (shared-memory offset >> 4), so the four chunks of a
+    // group get theirs by one add each and the 16 MMAs go out back to back (building every descriptor from
+    // scratch inside the loop costs the single issuing thread more than the MMAs take).
+    const uint64_t desc0 = make_smem_desc(0, 16, 1024, 2);
+    const uint32_t a_lo = smem_u32(sA) >> 4, w_lo = smem_u32(sW) >> 4, stage16 = (uint32_t)pl.stage_bytes >> 4;
     bool ok = __all_sync(0xffffffffu, wait_abortable(wbar, 0, p.abort_flag));
     unsigned long long d_wait0 = 0, d_rest = 0, d_waitn = 0;
     long long use = 0;
@@ -293,12 +298,19 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         tc_fence_after();
         if (elect_one_sync()) {
           if (p.dbg && s == 100 && g < 8) p.dbg[blockIdx.x * 128 + 40 + g] = clock64();
-          for (int i = i0; i < i1; ++i) {
-            const uint64_t adesc = make_smem_desc(smem_u32(sA + (grp * RT_GROUP + (i - i0)) * pl.stage_bytes), 16, 1024, 2);
-            const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)i * RT_W_BYTES), 16, 1024, 2);
+          const uint32_t a0 = a_lo + (uint32_t)(grp * RT_GROUP) * stage16;
+          const uint32_t b0 = w_lo + (uint32_t)i0 * (RT_W_BYTES >> 4);
+          const int nch = i1 - i0;
 #pragma unroll
-            for (int k = 0; k < RT_BK / 16; ++k)
-              umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (g | (i - i0) | k) != 0);
+          for (int j = 0; j < RT_GROUP; ++j) {
+            if (j < nch) {
+              const uint64_t adesc = desc0 + (uint64_t)(a0 + (uint32_t)j * stage16);
+              const uint64_t bdesc = desc0 + (uint64_t)(b0 + (uint32_t)j * (RT_W_BYTES >> 4));
+#pragma unroll
+              for (int k = 0; k < RT_BK / 16; ++k)
+                umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                          (j | k) ? 1u : (uint32_t)(g != 0));
+            }
           }
           if (CL == 1) umma_commit(&gempty[grp]);
           else umma_commit_mcast(&gempty[grp], cmask);
