@@ -38,6 +38,8 @@ _SIGS = {
     "dsb_spectrogram_stream_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p,
                                            c_void_p, c_void_p]),
     "dsb_spectrogram_stream_normalize": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
+    "dsb_spectrogram_stream_running_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double,
+                                                     c_void_p]),
     "dsb_model_create": (c_int, [POINTER(ModelDesc), POINTER(c_void_p)]),
     "dsb_model_destroy": (None, [c_void_p]),
     "dsb_model_set_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
@@ -65,6 +67,10 @@ _SIGS = {
     "dsb_beam_lm_order": (c_int, [c_void_p]),
     "dsb_beam_lm_is_char_based": (c_int, [c_void_p]),
     "dsb_beam_lm_num_ngrams": (c_int64, [c_void_p]),
+    "dsb_vad_state_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
+    "dsb_vad_state_destroy": (None, [c_void_p]),
+    "dsb_vad_reset": (c_int, [c_void_p, c_void_p]),
+    "dsb_vad_push_s16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -517,6 +517,39 @@ extern "C" int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stri
   return 0;
 }
 
+// Running statistics of InferenceSpectrogramAudioParser.parse_audio (parsers.py:146-157), one thread per stream:
+// alpha += inc; input_mean = (input_mean + mean)/2; input_std = (input_std + std)/2; blended with the dataset
+// constants while alpha < 1 (all in float64, like the Python floats of the reference).
+__global__ void stream_running_stats_kernel(double* __restrict__ run, const double* __restrict__ stats,
+                                            float* __restrict__ mean_std, int S, double dataset_mean,
+                                            double dataset_std, double alpha_inc) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const double alpha = run[s * 3 + 2] + alpha_inc;
+  const double im = (run[s * 3 + 0] + stats[s * 2 + 0]) / 2;
+  const double is = (run[s * 3 + 1] + stats[s * 2 + 1]) / 2;
+  run[s * 3 + 0] = im;
+  run[s * 3 + 1] = is;
+  run[s * 3 + 2] = alpha;
+  double mean = im, sd = is;
+  if (alpha < 1.0) {
+    mean = im * alpha + (1 - alpha) * dataset_mean;
+    sd = is * alpha + (1 - alpha) * dataset_std;
+  }
+  mean_std[s * 2 + 0] = (float)mean;
+  mean_std[s * 2 + 1] = (float)sd;
+}
+
+extern "C" int dsb_spectrogram_stream_running_stats(double* run, const double* stats, float* mean_std, int S,
+                                                    double dataset_mean, double dataset_std, double alpha_increment,
+                                                    void* stream) {
+  DSB_REQUIRE(run && stats && mean_std && S > 0, "dsb_spectrogram_stream_running_stats: null argument");
+  stream_running_stats_kernel<<<cdiv(S, 128), 128, 0, (cudaStream_t)stream>>>(run, stats, mean_std, S, dataset_mean,
+                                                                             dataset_std, alpha_increment);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int dsb_spectrogram_stream_normalize(float* spect, int64_t out_stride, const int32_t* n_frames, int S,
                                                 const float* mean_std, void* stream) {
   DSB_REQUIRE(spect && n_frames && mean_std && S > 0, "dsb_spectrogram_stream_normalize: null argument");

@@ -90,6 +90,15 @@ int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stride, const i
                                void* stream);
 int dsb_spectrogram_stream_normalize(float* spect, int64_t out_stride, const int32_t* n_frames /* device */, int S,
                                      const float* mean_std /* device f32 [S,2] */, void* stream);
+/* The running-statistics recurrence of parsers.py:146-157 kept on the device for S lock-step streams (the
+ * single-stream parser keeps it on the host like the reference):
+ *   run      device f64 [S,3] = (input_mean, input_std, alpha), updated in place; all zero == reset() (:92-99)
+ *   stats    device f64 [S,2]   chunk statistics from dsb_spectrogram_stream_f32
+ *   mean_std device f32 [S,2]   out: the values dsb_spectrogram_stream_normalize applies
+ *   dataset_mean/std, alpha_increment: parsers.py:89-91 (5.492418704733003, 1.7552755216970917, 0.1) */
+int dsb_spectrogram_stream_running_stats(double* run, const double* stats, float* mean_std, int S,
+                                         double dataset_mean, double dataset_std, double alpha_increment,
+                                         void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Acoustic model (replaces danspeech/deepspeech/model.py: DeepSpeech.__init__ :293-425,
@@ -189,6 +198,31 @@ int dsb_beam_decode(dsb_beam* d, const float* probs, const int32_t* seq_lens, in
 int dsb_beam_lm_order(const dsb_beam* d);
 int dsb_beam_lm_is_char_based(const dsb_beam* d);
 int64_t dsb_beam_lm_num_ngrams(const dsb_beam* d);
+
+/* ------------------------------------------------------------------------- *
+ * Energy voice-activity detection for S concurrent 16-bit streams ("next" row SURVEY 8f-4; replaces, per
+ * stream, the phrase state machine of Recognizer.listen_stream, danspeech/Recognizer.py:218-324, and its
+ * audioop.rms calls :275,:304).  One buffer of every stream per call; the host owns the audio (pre-roll of
+ * non-speaking buffers, hand-over to the streaming model) and only reads one event code per stream.
+ * ------------------------------------------------------------------------- */
+typedef struct dsb_vad_state dsb_vad_state;
+typedef enum {
+  DSB_VAD_SILENCE = 0,        /* still waiting for speech (Recognizer.py:262-277): keep the buffer in the pre-roll */
+  DSB_VAD_PHRASE_START = 1,   /* first loud buffer: the generator yields (False, pre-roll frames) (:283) */
+  DSB_VAD_SPEECH = 2,         /* inside the phrase: yields (False, buffer) (:313) */
+  DSB_VAD_PHRASE_END = 3,     /* pause longer than pause_buffers after a long-enough phrase: yields (True, buffer) (:321-324) */
+  DSB_VAD_PHRASE_DROPPED = 4  /* phrase shorter than phrase_buffers: back to waiting (:316-318) */
+} dsb_vad_event;
+/* pause_buffers = ceil(pause_threshold / seconds_per_buffer), phrase_buffers = ceil(phrase_threshold / ...) (:244-247) */
+int dsb_vad_state_create(int n_streams, int pause_buffers, int phrase_buffers, dsb_vad_state** out);
+void dsb_vad_state_destroy(dsb_vad_state* v);
+int dsb_vad_reset(dsb_vad_state* v, void* stream);
+/*   chunks            device s16 [S, chunk_stride], chunk_samples valid samples per stream
+ *   energy_threshold  device i32 [S] (Recognizer.energy_threshold, :44)
+ *   energy_out        device i32 [S]  audioop.rms of the buffer = floor(sqrt(mean(x^2)))
+ *   event_out         device i32 [S]  dsb_vad_event */
+int dsb_vad_push_s16(dsb_vad_state* v, const int16_t* chunks, int64_t chunk_stride, int chunk_samples,
+                     const int32_t* energy_threshold, int32_t* energy_out, int32_t* event_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -4,10 +4,8 @@ set -u
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-echo "== pytest parity" ; timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py -q -m gpu ${PYTEST_ARGS:-} > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest.log
-grep -E "passed|failed|Error|error" gpurun_out/pytest.log | tail -15
-echo "== pytest kernels" ; timeout -s KILL 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu > gpurun_out/pytest_kernels.log 2>&1; echo "pytest kernels rc=$?" | tee -a gpurun_out/pytest_kernels.log
-grep -E "passed|failed|Error|error|assert" gpurun_out/pytest_kernels.log | tail -15
+echo "== pytest -m gpu" ; timeout -s KILL 1200 python -m pytest tests -q -m gpu ${PYTEST_ARGS:-} > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest.log
+grep -E "passed|failed|Error|error|assert" gpurun_out/pytest.log | tail -15
 if [ "${BENCH:-1}" = "1" ]; then
 echo "== bench" ; timeout -s KILL 900 python bench.py --steps ${BENCH_STEPS:-2} --warmup 3 --precision ${PRECISION:-bf16} > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
@@ -21,7 +19,7 @@ fi
 if [ "${NCU_FULL:-0}" = "1" ]; then
   echo "== ncu full (top kernels)"
   timeout -s KILL 900 ncu --set full --clock-control none --import-source on \
-     -k regex:'rnn_tc_kernel|gemm_tc_kernel|conv_tc_kernel|spectrogram_kernel' -c ${NCU_FULL_COUNT:-8} -f -o gpurun_out/prof_top \
+     -k regex:'rnn_tc_kernel|gemm_tc2?_kernel|conv_tc_kernel|spectrogram_kernel' -c ${NCU_FULL_COUNT:-8} -f -o gpurun_out/prof_top \
      python scripts/ncu_target.py > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
   tail -2 gpurun_out/ncu_full.log
 fi

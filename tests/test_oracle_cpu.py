@@ -1,5 +1,6 @@
 """CPU: the oracle restatements reproduce the golden outputs of the unmodified reference."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -10,6 +11,7 @@ from oracle import greedy as og
 from oracle import model as om
 from oracle import refharness
 from oracle import spectrogram as osp
+from oracle import vad as ov
 from danspeech_b200.utils import synthetic as syn
 
 
@@ -130,3 +132,59 @@ def test_repin_against_live_reference(golden):
         ref, rs = m(x, xl)
     probs, sizes = om.forward(sd, x, xl, 2, 2)
     assert rel_err(probs.numpy(), ref.numpy()) < 1e-6 and np.array_equal(sizes.numpy(), rs.numpy())
+
+
+# ------------------------------------------------------------------ energy VAD
+def _vad_rows(events, non_speaking):
+    """(is_last, buffers in the yield, source position) rows the reference generator produces for these events."""
+    rows, pre = [], 0
+    for i, ev in enumerate(events):
+        if ev in (ov.SILENCE, ov.PHRASE_START):
+            pre = min(pre + 1, non_speaking)
+            if ev == ov.PHRASE_START:
+                rows.append((0, pre, i + 1))
+                pre = 0
+        elif ev == ov.SPEECH:
+            rows.append((0, 1, i + 1))
+        elif ev == ov.PHRASE_END:
+            rows.append((1, 1, i + 1))
+            pre = 0
+        else:
+            pre = 0
+    return rows
+
+
+def _vad_fixture_events():
+    pcm = ov.fixture_pcm()
+    pause, phrase, non_speaking = ov.buffer_counts()
+    o = ov.ListenStreamOracle(1000, pause, phrase)
+    res = [o.push(pcm[i * 1024:(i + 1) * 1024]) for i in range(len(pcm) // 1024)]
+    return pcm, [e for _, e in res], [en for en, _ in res], non_speaking
+
+
+def test_vad_oracle_matches_reference_generator_golden():
+    """oracle/vad.py against the yields of the unmodified Recognizer.listen_stream (tests/golden/vad_reference.npz)."""
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "vad_reference.npz"))["yields"]
+    pcm, events, _, non_speaking = _vad_fixture_events()
+    n_buffers = len(pcm) // 1024
+    want = [tuple(r) for r in ref.tolist() if r[2] <= n_buffers]   # the tail is the source running dry
+    assert _vad_rows(events, non_speaking) == want
+    assert events.count(ov.PHRASE_END) == 2 and events.count(ov.PHRASE_DROPPED) == 1
+
+
+def test_vad_oracle_rms_is_audioop_rms():
+    audioop = pytest.importorskip("audioop")
+    rng = np.random.default_rng(3)
+    for n, scale in ((1024, 3000), (1024, 50), (7, 30000), (4096, 12000)):
+        x = np.clip(rng.normal(0, scale, n), -32768, 32767).astype(np.int16)
+        assert ov.rms(x) == audioop.rms(x.tobytes(), 2)
+    assert ov.rms(np.full(16, -32768, np.int16)) == audioop.rms(np.full(16, -32768, np.int16).tobytes(), 2) == 32768
+
+
+@pytest.mark.skipif(not refharness.reference_available(), reason="reference tree only exists in the build container")
+def test_vad_repin_against_live_reference():
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import gen_vad_golden
+    rows = gen_vad_golden.reference_yields(ov.fixture_pcm())
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "vad_reference.npz"))["yields"]
+    assert np.array_equal(rows, ref)
