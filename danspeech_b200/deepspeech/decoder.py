@@ -82,14 +82,15 @@ class GreedyDecoder(Decoder):
     def decode(self, probs, sizes=None):
         """Returns (strings: List[B][1] str, offsets: List[B][1] IntTensor) -- decoder.py:183-198."""
         tokens, offsets, out_len = self.decode_device(probs, sizes)
-        packed = torch.cat([out_len.view(-1, 1), tokens, offsets], dim=1).cpu()   # one D2H copy
+        packed = torch.cat([out_len.view(-1, 1), tokens, offsets], dim=1).cpu().numpy()   # one D2H copy
         B, T = tokens.shape
+        chars = self.int_to_char
+        lens = packed[:, 0].tolist()
+        offs_all = torch.from_numpy(packed[:, 1 + T:].copy())
         strings, offs = [], []
-        for b in range(B):
-            n = int(packed[b, 0])
-            ids = packed[b, 1:1 + n].tolist()
-            strings.append(["".join(self.int_to_char[i] for i in ids)])
-            offs.append([packed[b, 1 + T:1 + T + n].clone().to(torch.int)])
+        for b, n in enumerate(lens):
+            strings.append(["".join([chars[i] for i in packed[b, 1:1 + n].tolist()])])
+            offs.append([offs_all[b, :n]])
         return strings, offs
 
 
