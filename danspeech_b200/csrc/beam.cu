@@ -17,6 +17,7 @@
 #include "model_types.cuh"
 #include <float.h>
 #include <math.h>
+#include <cstring>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -472,7 +473,35 @@ struct HostLm {
   }
 };
 
+// KenLM binary files (lm/binary_format.cc: 88-byte sanity header starting with the magic string, then
+// FixedWidthParameters {order, probing_multiplier, model_type, has_vocabulary, search_version} and one uint64
+// count per order) are recognised and refused with what they contain: the device LM table is built from ARPA
+// text, and a .klm only stores 64-bit hashes of its n-grams (second half: not built).
+static int refuse_kenlm_binary(const char* path) {
+  FILE* fp = fopen(path, "rb");
+  if (!fp) return 0;
+  unsigned char hdr[88 + 20 + 8 * 8];
+  const size_t n = fread(hdr, 1, sizeof(hdr), fp);
+  fclose(fp);
+  static const char magic[] = "mmap lm http://kheafield.com/code format version";
+  if (n < sizeof(magic) - 1 || memcmp(hdr, magic, sizeof(magic) - 1) != 0) return 0;
+  int order = 0, type = -1;
+  unsigned long long counts[8] = {0};
+  if (n >= 88 + 20) {
+    order = hdr[88];
+    memcpy(&type, hdr + 96, 4);
+    for (int i = 0; i < order && i < 8 && 108 + 8 * (size_t)(i + 1) <= n; ++i) memcpy(&counts[i], hdr + 108 + 8 * i, 8);
+  }
+  static const char* names[] = {"probing", "rest-probing", "trie", "quantised trie", "array trie", "quantised array trie"};
+  return set_error(DSB_ERR_UNSUPPORTED,
+                   "dsb_beam_create: '%s' is a KenLM binary (format version %c, %s, order %d, %llu unigrams); this build "
+                   "reads ARPA text only -- pass the .arpa the binary was built from",
+                   path, n > sizeof(magic) ? (char)hdr[sizeof(magic)] : '?', (type >= 0 && type < 6) ? names[type] : "unknown type",
+                   order, counts[0]);
+}
+
 static int load_arpa(const char* path, HostLm& lm) {
+  if (int e = refuse_kenlm_binary(path)) return e;
   std::ifstream f(path);
   if (!f) return set_error(DSB_ERR_IO, "dsb_beam_create: cannot open language model '%s'", path);
   lm.vocab["<unk>"] = 0;

@@ -61,3 +61,20 @@ def test_product_fails_loudly_without_gpu():
         Recognizer()
     with pytest.raises(N.NativeError):
         Recognizer(with_gpu=False)
+
+
+def test_kenlm_binary_is_recognised_and_refused(lib, tmp_path):
+    """A .klm (KenLM binary, lm/binary_format.cc header) must fail with what it is, not with an ARPA parse error."""
+    import struct
+    from danspeech_b200.utils import synthetic as syn
+    magic = b"mmap lm http://kheafield.com/code format version 5\n\0"
+    sanity = magic.ljust(56, b"\0") + struct.pack("<fffIIQ", 0.0, 1.0, -0.5, 1, 0xFFFFFFFF, 1) + b"\0" * 4
+    assert len(sanity) == 88
+    params = struct.pack("<B3xfiB3xI", 3, 1.5, 2, 1, 1)          # order 3, trie, with vocabulary
+    p = tmp_path / "dsl_3gram.klm"
+    p.write_bytes(sanity + params + struct.pack("<QQQ", 12345, 99, 7) + b"\0" * 64)
+    labels = "\0".join(syn.LABELS).encode("utf-8") + b"\0"
+    h = ctypes.c_void_p()
+    rc = lib.dsb_beam_create(labels, len(syn.LABELS), str(p).encode(), 1.3, 0.2, 40, 1.0, 64, 0, 0, ctypes.byref(h))
+    msg = lib.dsb_last_error().decode()
+    assert rc != 0 and "KenLM binary" in msg and "trie" in msg and "order 3" in msg and "12345 unigrams" in msg
