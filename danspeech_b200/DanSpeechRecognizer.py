@@ -175,13 +175,36 @@ class DanSpeechRecognizer(object):
             # (host float32 tensor [B, stride] (ideally pinned), n_samples) already sorted by length descending
             host_audio, n_samples = recordings
             order = list(range(len(n_samples)))
-            spect, input_sizes = self.audio_parser.parse_packed(host_audio, n_samples)
         else:
             order = sorted(range(len(recordings)), key=lambda i: -len(recordings[i]))
-            spect, input_sizes = self.audio_parser.parse_batch([recordings[i] for i in order])
+            host_audio, n_samples = self.audio_parser.stage_batch([recordings[i] for i in order])
+        return self._transcribe_staged(host_audio, n_samples, order, show_all)
+
+    def _transcribe_staged(self, host_audio, n_samples, order, show_all=False):
+        spect, input_sizes = self.audio_parser.parse_packed(host_audio, n_samples)
         out, output_sizes = self.model(spect, input_sizes)
         decoded_output, _ = self.decoder.decode(out, output_sizes)
         results = [None] * len(order)
         for pos, i in enumerate(order):
             results[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
+        return results
+
+    def transcribe_batches(self, batches, show_all=False):
+        """Several batches back to back: a helper thread converts and stages batch k+1 into pinned memory while the
+        GPU works on batch k (two staging buffers).  Returns one result list per batch."""
+        import concurrent.futures
+
+        def stage(k):
+            recs = batches[k]
+            order = sorted(range(len(recs)), key=lambda i: -len(recs[i]))
+            host, ns = self.audio_parser.stage_batch([recs[i] for i in order], slot=k & 1)
+            return host, ns, order
+
+        results = []
+        with concurrent.futures.ThreadPoolExecutor(max_workers=1) as ex:
+            nxt = ex.submit(stage, 0) if batches else None
+            for k in range(len(batches)):
+                host, ns, order = nxt.result()
+                nxt = ex.submit(stage, k + 1) if k + 1 < len(batches) else None
+                results.append(self._transcribe_staged(host, ns, order, show_all))
         return results

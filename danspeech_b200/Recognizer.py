@@ -30,6 +30,10 @@ class Recognizer(object):
     def recognize_batch(self, audio_list, show_all=False):
         return self.danspeech_recognizer.transcribe_batch(audio_list, show_all=show_all)
 
+    def recognize_batches(self, batches, show_all=False):
+        """Several batches back to back with the host staging of the next batch overlapped with the GPU work."""
+        return self.danspeech_recognizer.transcribe_batches(batches, show_all=show_all)
+
     def update_model(self, model):
         self.danspeech_recognizer.update_model(model)
         print("DanSpeech model updated to: {0}".format(model.model_name))

@@ -75,21 +75,30 @@ class SpectrogramAudioParser(AudioParser):
                                       N.current_stream()), "dsb_spectrogram_f32")
         return out, mean_std
 
+    def stage_batch(self, recordings, slot=0):
+        """Host half of ``parse_batch``: converts the recordings to float32 straight into a cached pinned staging
+        buffer (one per ``slot``, grow-only; cudaHostAlloc per call would cost more than the GPU work).  Returns
+        (pinned f32 view [B, stride], n_samples list).  Rows are only read up to their own length on the device."""
+        ns = [int(np.asarray(r).size) for r in recordings]
+        stride = (max(ns) + 3) // 4 * 4
+        need = len(ns) * stride
+        if not hasattr(self, "_staging"):
+            self._staging = {}
+        buf = self._staging.get(slot)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty((max(need, 1),), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+            self._staging[slot] = buf
+        host = buf[:need].view(len(ns), stride)
+        host_np = host.numpy()
+        for i, r in enumerate(recordings):
+            np.copyto(host_np[i, : ns[i]], np.asarray(r).reshape(-1), casting="unsafe")
+        return host, ns
+
     def parse_batch(self, recordings):
         """List of 1-D arrays -> (spect cuda f32 [B,1,161,Tmax] zero-padded, lengths IntTensor[B] (CPU))."""
-        dev = self._dev()
-        arrs = [_as_f32(r) for r in recordings]
-        ns = [len(a) for a in arrs]
-        max_n = max(ns)
-        stride = (max_n + 3) // 4 * 4
-        host = torch.zeros((len(arrs), stride), dtype=torch.float32, pin_memory=True)
-        for i, a in enumerate(arrs):
-            host[i, : len(a)] = torch.from_numpy(a)
-        audio = host.to(dev, non_blocking=True)
-        n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
-        out, _ = self.parse_device(audio, n_dev, max_n)
-        lengths = torch.IntTensor([1 + n // self.hop_length for n in ns])
-        return out.view(len(arrs), 1, 161, out.shape[2]), lengths
+        self._dev()
+        host, ns = self.stage_batch(recordings)
+        return self.parse_packed(host, ns)
 
     def parse_packed(self, host_audio, n_samples):
         """host_audio: (pinned) CPU f32 tensor [B, stride] already sorted by length descending."""

@@ -51,15 +51,21 @@ def gather_transcripts(local, world_size, group=None):
     return merged
 
 
-def transcribe_sharded(recognize_batch, recordings, rank=0, world_size=1, max_batch=64, group=None):
+def transcribe_sharded(recognize_batch, recordings, rank=0, world_size=1, max_batch=64, group=None,
+                       recognize_batches=None):
     """Shard ``recordings`` over ``world_size`` ranks, run this rank's share through ``recognize_batch``
     (a callable list-of-audio -> list-of-results) and gather.  The result list is in input order and is
-    identical for every world size (shard invariance)."""
+    identical for every world size (shard invariance).  ``recognize_batches`` (list of batches -> list of result
+    lists, e.g. ``Recognizer.recognize_batches``) overlaps the host staging of a batch with the previous one."""
     lengths = [len(r) for r in recordings]
     mine = lpt_shards(lengths, world_size)[rank]
     local = {}
-    for batch in make_batches(mine, lengths, max_batch=max_batch):
-        out = recognize_batch([recordings[i] for i in batch])
+    batches = make_batches(mine, lengths, max_batch=max_batch)
+    if recognize_batches is not None:
+        outs = recognize_batches([[recordings[i] for i in batch] for batch in batches])
+    else:
+        outs = [recognize_batch([recordings[i] for i in batch]) for batch in batches]
+    for batch, out in zip(batches, outs):
         for i, o in zip(batch, out):
             local[i] = o
     merged = gather_transcripts(local, world_size, group=group)

@@ -315,6 +315,8 @@ def test_shard_invariance_of_transcripts(precision):
     r = Recognizer(model=build_model("TestModel", seed=0, rnn_hidden_size=160, rnn_layers=3).set_precision(precision))
     base = sharding.transcribe_sharded(r.recognize_batch, recs, 0, 1, max_batch=64)
     assert len(base) == 24 and all(isinstance(t, str) for t in base)
+    # pipelined staging (helper thread + two pinned buffers) must not change anything
+    assert sharding.transcribe_sharded(r.recognize_batch, recs, 0, 1, max_batch=5, recognize_batches=r.recognize_batches) == base
     assert base[3] == r.recognize(recs[3])                       # batch == single utterance
     for world in (2, 4):
         merged = {}
