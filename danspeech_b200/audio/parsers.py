@@ -80,6 +80,9 @@ class SpectrogramAudioParser(AudioParser):
         buffer (one per ``slot``, grow-only; cudaHostAlloc per call would cost more than the GPU work).  Returns
         (pinned f32 view [B, stride], n_samples list).  Rows are only read up to their own length on the device."""
         ns = [int(np.asarray(r).size) for r in recordings]
+        if not ns or min(ns) == 0:
+            # the reference dies in np.pad(mode="reflect") inside librosa.stft (parsers.py:59)
+            raise ValueError("can't extend empty axis 0 using modes other than 'constant' or 'empty'")
         stride = (max(ns) + 3) // 4 * 4
         need = len(ns) * stride
         if not hasattr(self, "_staging"):
@@ -106,6 +109,8 @@ class SpectrogramAudioParser(AudioParser):
         if host_audio.dtype != torch.float32 or host_audio.dim() != 2:
             raise ValueError("parse_packed expects a 2-D float32 tensor")
         ns = [int(v) for v in n_samples]
+        if not ns or min(ns) <= 0:
+            raise ValueError("can't extend empty axis 0 using modes other than 'constant' or 'empty'")
         audio = host_audio.to(dev, non_blocking=True)
         n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
         out, _ = self.parse_device(audio, n_dev, max(ns))

@@ -443,7 +443,7 @@ static int spectrogram_offline(const void* audio, bool s16, int channels, int64_
   const int normalize = flags & DSB_SPECT_NORMALIZE;
   const bool fast = (flags & DSB_SPECT_FAST_FFT) != 0;
   DSB_REQUIRE(audio && n_samples && out && partials && B > 0, "dsb_spectrogram: null argument or B <= 0");
-  DSB_REQUIRE(max_samples >= 2 && max_samples <= audio_stride, "dsb_spectrogram: max_samples %d out of range",
+  DSB_REQUIRE(max_samples >= 1 && max_samples <= audio_stride, "dsb_spectrogram: max_samples %d out of range",
               max_samples);
   DSB_REQUIRE(channels >= 1 && channels <= 8, "dsb_spectrogram: channels %d", channels);
   if (int e = ensure_tables()) return e;

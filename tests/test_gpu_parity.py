@@ -52,6 +52,20 @@ def test_spectrogram_ragged_batch_zero_padded():
         assert float(x[b, 0, :, L:].abs().max() if L < x.shape[3] else 0.0) == 0.0
 
 
+def test_spectrogram_tiny_inputs_match_oracle():
+    """Shorter than one hop / one window: np.pad(reflect) wraps around several times (n = 1 repeats the sample)."""
+    from danspeech_b200.audio.parsers import SpectrogramAudioParser
+    p, o = SpectrogramAudioParser(), osp.SpectrogramOracle()
+    for n in (1, 2, 3, 100, 159, 160, 319, 320, 321):
+        a = np.random.default_rng(900 + n).integers(-20000, 20000, n).astype(np.float64)
+        ref = o.parse_audio(a).numpy()
+        got = p.parse_audio(a).cpu().numpy()
+        assert got.shape == ref.shape == (161, 1 + n // 160)
+        assert rel_err(got, ref) < FP32_TOL, n
+    with pytest.raises(ValueError):
+        p.parse_audio(np.zeros(0))
+
+
 def test_spectrogram_full_size_properties():
     """BASELINE config-2 size (64 x 15 s): per-utterance mean 0 / unbiased std 1, batch == single."""
     from danspeech_b200.audio.parsers import SpectrogramAudioParser
@@ -462,3 +476,17 @@ def test_pcm16_ingest_equals_host_mixdown():
     mono = torch.from_numpy(floats[0].astype(np.int16)).view(1, -1)
     xm, _ = p.parse_pcm16(mono, [ns[0]])
     assert torch.equal(xm[0], xf[0])
+
+
+def test_api_errors_mirror_reference():
+    """Recognizer.py:72-75 (lm without model) and DanSpeechRecognizer.py:226-229 (show_all without an LM)."""
+    from danspeech_b200 import Recognizer
+    from danspeech_b200.errors.recognizer_errors import ModelNotInitialized
+    from danspeech_b200.DanSpeechRecognizer import NoLmInstantiatedWarning
+    from danspeech_b200.pretrained_models import build_model
+    with pytest.raises(ModelNotInitialized):
+        Recognizer(lm="some_lm.arpa")
+    r = Recognizer(model=build_model("TestModel", seed=0, rnn_hidden_size=64, rnn_layers=1))
+    with pytest.warns(NoLmInstantiatedWarning):
+        out = r.recognize(syn.synthetic_audio(8000, seed=1), show_all=True)
+    assert isinstance(out, list) and len(out) == 1 and isinstance(out[0], str)
