@@ -29,8 +29,8 @@ namespace tc {
 constexpr int RT_BK = 64;
 constexpr int RT_N = 64;                       // W_hh rows per CTA = 2 halves x 32 columns
 constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk (8 KB)
-constexpr int RT_GROUP = 4;        // K chunks handled per elected issue region
-constexpr int RT_MAX_GROUPS = 2;   // ring = RT_MAX_GROUPS x RT_GROUP stages
+constexpr int RT_GROUP = 4;        // K chunks handled per elected issue region (2 when only one group of 4 would fit)
+constexpr int RT_MAX_GROUPS = 4;   // barrier slots; the ring holds 2 groups of 4 chunks or up to 4 groups of 2
 // (Consecutive tcgen05.mma into the same accumulator do not stall each other -- tested with 4 independent
 // accumulators: no change -- so a single 64-column TMEM accumulator is used.)
 constexpr int RT_THREADS = 64 + 256;
@@ -43,7 +43,7 @@ constexpr int RT_SMEM_LIMIT = 227 * 1024;
 // of ~35 cycles per tcgen05.mma / TMA instruction (scripts/mma_microbench.py), so the producer and the MMA
 // warp work in groups of RT_GROUP chunks: one region issues 4 TMA loads, one region issues 16 MMAs.
 struct RtPlan {
-  int groups, stage_bytes, stage_off, stg_off, bar_off, total;
+  int groups, gsz, stage_bytes, stage_off, stg_off, bar_off, total;
 };
 __host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U) {
   RtPlan pl;
@@ -51,11 +51,18 @@ __host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U) {
   const int w_bytes = nkc * RT_W_BYTES;
   const int stg = BP * U * 2;                    // h (bf16) staging for coalesced stores
   const int stg_al = (stg + 1023) / 1024 * 1024;
-  int groups = (RT_SMEM_LIMIT - 2048 - 256 - w_bytes - stg_al) / (pl.stage_bytes * RT_GROUP);   // 1 KB align slack + 1 KB static
-  if (groups > RT_MAX_GROUPS) groups = RT_MAX_GROUPS;
+  const int room = RT_SMEM_LIMIT - 2048 - 256 - w_bytes - stg_al;   // 1 KB align slack + 1 KB static
+  int gsz = RT_GROUP, groups = room / (pl.stage_bytes * gsz);
+  if (groups > 2) groups = 2;
+  if (groups < 2) {   // a single group cannot overlap TMA with the MMAs: use smaller groups instead
+    gsz = 2;
+    groups = room / (pl.stage_bytes * gsz);
+    if (groups > RT_MAX_GROUPS) groups = RT_MAX_GROUPS;
+  }
   pl.groups = groups;
+  pl.gsz = gsz;
   pl.stage_off = w_bytes;
-  pl.stg_off = w_bytes + groups * RT_GROUP * pl.stage_bytes;
+  pl.stg_off = w_bytes + groups * gsz * pl.stage_bytes;
   pl.bar_off = pl.stg_off + stg_al;
   pl.total = pl.bar_off + 256 + 1024;
   return pl;
@@ -148,7 +155,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   uint64_t* dfull = wbar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
   const int n_groups = pl.groups;
-  const int gps = (p.nkc + RT_GROUP - 1) / RT_GROUP;   // group uses per step
+  const int gsz = pl.gsz;
+  const int gps = (p.nkc + gsz - 1) / gsz;   // group uses per step
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int set = blockIdx.x / p.cpd;          // (direction, slot)
@@ -202,7 +210,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       const int grp = (int)(u % n_groups);
       const uint32_t gphase = (uint32_t)((u / n_groups) & 1);
       if (!__all_sync(0xffffffffu, wait_abortable(&gempty[grp], gphase ^ 1, p.abort_flag))) return false;
-      if (elect_one_sync()) mbar_arrive_expect_tx(&full[grp], (uint32_t)(RT_GROUP * pl.stage_bytes));
+      if (elect_one_sync()) mbar_arrive_expect_tx(&full[grp], (uint32_t)(gsz * pl.stage_bytes));
       __syncwarp();
       return true;
     };
@@ -212,9 +220,9 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       if (gg >= gps) gg -= gps;
       if (elect_one_sync()) {
         if (CL == 1)
-          tma_load_3d(sA + grp * RT_GROUP * pl.stage_bytes, &tmap_h, &full[grp], 0, row0, gg * RT_GROUP);
+          tma_load_3d(sA + grp * gsz * pl.stage_bytes, &tmap_h, &full[grp], 0, row0, gg * gsz);
         else if (g % CL == crank)
-          tma_load_3d_mcast(sA + grp * RT_GROUP * pl.stage_bytes, &tmap_h, &full[grp], 0, row0, gg * RT_GROUP, cmask);
+          tma_load_3d_mcast(sA + grp * gsz * pl.stage_bytes, &tmap_h, &full[grp], 0, row0, gg * gsz, cmask);
       }
       __syncwarp();
     };
@@ -289,7 +297,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         const uint32_t fphase = (uint32_t)((use / n_groups) & 1);
         int gg = g + g_rot;
         if (gg >= gps) gg -= gps;
-        const int i0 = gg * RT_GROUP, i1 = min(p.nkc, i0 + RT_GROUP);
+        const int i0 = gg * gsz, i1 = min(p.nkc, i0 + gsz);
         long long w0 = clock64();
         ok = __all_sync(0xffffffffu, wait_abortable(&full[grp], fphase, p.abort_flag));
         if (!ok) break;
@@ -298,7 +306,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         tc_fence_after();
         if (elect_one_sync()) {
           if (p.dbg && s == 100 && g < 8) p.dbg[blockIdx.x * 128 + 40 + g] = clock64();
-          const uint32_t a0 = a_lo + (uint32_t)(grp * RT_GROUP) * stage16;
+          const uint32_t a0 = a_lo + (uint32_t)(grp * gsz) * stage16;
           const uint32_t b0 = w_lo + (uint32_t)i0 * (RT_W_BYTES >> 4);
           const int nch = i1 - i0;
 #pragma unroll
@@ -656,7 +664,8 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   // h exchange buffer as {64 k, rows, K chunks}: one box {64, BP, RT_GROUP} = RT_GROUP consecutive chunk tiles
   uint64_t dh[3] = {(uint64_t)RT_BK, (uint64_t)n_bgroups * 2 * L.dirs * BP, (uint64_t)nkc};
   uint64_t sh[3] = {2, (uint64_t)HP * 2, (uint64_t)RT_BK * 2};
-  uint32_t bh[3] = {RT_BK, (uint32_t)BP, RT_GROUP};
+  const int gsz = rt_plan(nkc, BP, 2 * (32 / L.gates)).gsz;
+  uint32_t bh[3] = {RT_BK, (uint32_t)BP, (uint32_t)gsz};
   if (int e = make_tmap_bf16(&th, hbuf, 3, dh, sh, bh, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
 
   RnnTcParams p{};
@@ -739,9 +748,9 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
       const unsigned long long* d = &h[c * 128];
       const long long t0 = (long long)d[66];
       fprintf(stderr, "   [cta %d] barrier passed %+lld | tma group issued:", c, (long long)d[15] - t0);
-      for (int i = 0; i < (nkc + RT_GROUP - 1) / RT_GROUP && i < 8; ++i) fprintf(stderr, " %lld", (long long)d[16 + i] - t0);
+      for (int i = 0; i < (nkc + gsz - 1) / gsz && i < 8; ++i) fprintf(stderr, " %lld", (long long)d[16 + i] - t0);
       fprintf(stderr, "\n   [cta %d] group ready:", c);
-      for (int i = 0; i < (nkc + RT_GROUP - 1) / RT_GROUP && i < 8; ++i) fprintf(stderr, " %lld", (long long)d[40 + i] - t0);
+      for (int i = 0; i < (nkc + gsz - 1) / gsz && i < 8; ++i) fprintf(stderr, " %lld", (long long)d[40 + i] - t0);
       fprintf(stderr, "\n   [cta %d] mma issued %+lld | epilogue saw dfull %+lld | published %+lld\n", c,
               (long long)d[64] - t0, (long long)d[65] - t0, (long long)d[67] - t0);
     }

@@ -490,3 +490,22 @@ def test_api_errors_mirror_reference():
     with pytest.warns(NoLmInstantiatedWarning):
         out = r.recognize(syn.synthetic_audio(8000, seed=1), show_all=True)
     assert isinstance(out, list) and len(out) == 1 and isinstance(out[0], str)
+
+
+def test_streaming_bf16_wide_model_uses_small_chunk_groups():
+    """H = 800 with 128-row batch groups leaves room for one group of four K chunks only; the recurrence then
+    runs its ring in groups of two (rt_plan).  bf16 kernels against the exact-fp32 kernels."""
+    kw = dict(rnn_hidden_size=800, rnn_layers=2)
+    m = _model("CPUStreamingRNN", kw, seed=7, precision="bf16")
+    f = _model("CPUStreamingRNN", kw, seed=7, precision="fp32")
+    S = 130
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    chunks = [torch.randn((S, 1, 161, k), generator=gen, device="cuda") for k in (53, 39, 39)]
+    for i, x in enumerate(chunks):
+        a, b = m(x, i == 0, i == 2), f(x, i == 0, i == 2)
+        if b is None:
+            assert a is None
+            continue
+        assert a.shape == b.shape
+        for s in (0, 64, 127, 128, 129):
+            assert logit_rel_err(a[s].cpu().numpy(), b[s].cpu().numpy()) < BF16_TOL
