@@ -3,16 +3,20 @@
 //
 // Activations are channels-last bf16 [B][D][T'][C].  An output tile is 128 consecutive frames of one
 // (utterance, output frequency row) x all output channels:  D[128, Cout] = sum over (kh, kw) of
-// A_{kh,kw}[128, Cin] * W_{kh,kw}[Cout, Cin]^T, where A_{kh,kw} is the TMA box
-// {Cin, 128 frames} at (t0 + kw - 5, 2d + kh - pad, b): the zero padding in time and frequency is the
-// TMA out-of-bounds fill, so there is no im2col buffer and no boundary code.
-// The first block has Cin = 1, which no MMA can use directly; its input is expanded once in time
-// ("x1[b,d,t,j] = spect[b,d,2t+j-5]", 11 taps padded to 16) so that it becomes a kH x 1 convolution
-// over 16 channels with unit time stride, and runs through the same kernel.
-// Warp roles as in gemm_tc.cu: TMA producer / single-thread tcgen05.mma issuer / 4 epilogue warps, with
-// the accumulator double-buffered in TMEM so that the epilogue of a tile overlaps the next tile's MMAs.
-// Bound: the SS-mode MMA operand fetch from shared memory (~64 B/clk/SM measured), i.e. tensor pipe
-// fed at (128 + Cout)/2 + ~30 cycles per K=16 slice; algorithmic flops = 2*T'*Cout*Dout*Cin*kH*kW per utterance.
+// A_{kh,kw}[128, Cin] * W_{kh,kw}[Cout, Cin]^T.  There is no im2col buffer and no boundary code: the zero padding
+// in time and frequency is the TMA out-of-bounds fill.
+//   * Blocks 2/3: per kh ONE box of 128 + 10 frames (coordinate t0 - 5) and one box with the 11 weight taps;
+//     the A operand of tap kw is the same shared-memory block read from row kw on (descriptor start address
+//     + kw rows), so the 11 overlapping windows cost one load instead of eleven.
+//   * Block 1 has Cin = 1, which no MMA can use directly; its input is expanded once in time
+//     ("x1[b,d,t,j] = spect[b,d,2t+j-5]", 11 taps padded to 16) so that it becomes a kH x 1 convolution over 16
+//     channels; a box {16, 128 frames, 4 rows} delivers four consecutive kh taps.
+// A TMA instruction costs the producer ~240 cycles, more than the MMAs of one (kh,kw) step take: with one step
+// per instruction the kernel was producer-bound; now it is bound by the MMA rate (~50-65 cycles per K=16 slice at
+// these tile shapes, scripts/mma_microbench.py).
+// Warp roles as in gemm_tc.cu: TMA producer / single-thread tcgen05.mma issuer / 4 epilogue warps, with the
+// accumulator double-buffered in TMEM so that the epilogue of a tile overlaps the next tile's MMAs.
+// Algorithmic flops = 2*T'*Cout*Dout*Cin*kH*kW per utterance.
 #include "tc_common.cuh"
 #include "model_types.cuh"
 
@@ -20,12 +24,12 @@ namespace dsb {
 namespace tc {
 
 constexpr int CV_BM = 128;
-constexpr int CV_GROUP = 4;     // (kh, kw) steps per elected issue region (~200 cycles fixed cost per region)
 constexpr int CV_THREADS = 192;
+constexpr int CV_G1 = 4;        // block 1: kh taps per box / per elected issue region
 
 struct ConvTcParams {
   const float* bias;          // [NOUT] folded
-  const int32_t* lens;        // [B] output frames per utterance
+  const int32_t* lens;        // [B] output frames per utterance (nullptr: no mask)
   __nv_bfloat16* out;
   int B, Tp, Din, Dout, KH, KW, sd, pd, pt;
   int rnn_layout;             // 0: [B][Dout][Tp][NOUT]   1: [(t*B+b)][Dout*NOUT] (feature = d*NOUT + co)
@@ -36,16 +40,21 @@ struct ConvTcParams {
   int seg_len, seg_off, seg_valid, nb;
 };
 
+// One ring slot = one "group": block 1: CV_G1 kh taps (A tiles + weight tiles); blocks 2/3: one kh = a block of
+// 128 + KW - 1 frames and the KW weight taps.
 template <int NOUT, int CIN>
 struct ConvSmem {
+  static constexpr bool FIRST = CIN == 16;
   static constexpr int ROW = CIN * 2;
-  static constexpr int A_BYTES = CV_BM * ROW;
-  static constexpr int B_BYTES = NOUT * ROW;
-  static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;
-  static constexpr int GROUPS = NOUT <= 32 ? 4 : 3;                 // ring depth in groups
-  static constexpr int STAGES = GROUPS * CV_GROUP;
-  static constexpr int BAR_OFF = STAGES * (A_STRIDE + B_STRIDE);
+  static constexpr int A_TILE = CV_BM * ROW;                                     // one 128-frame operand tile
+  static constexpr int A_ROWS = FIRST ? CV_BM : CV_BM + kConvKW - 1;             // frames per box
+  static constexpr int A_SLOT = FIRST ? CV_G1 * A_TILE : (A_ROWS * ROW + 1023) / 1024 * 1024;
+  static constexpr int A_TX = FIRST ? CV_G1 * A_TILE : A_ROWS * ROW;             // bytes one A box delivers
+  static constexpr int B_TILE = NOUT * ROW;
+  static constexpr int B_SLOT = (FIRST ? CV_G1 : kConvKW) * B_TILE;
+  static_assert(A_TILE % 1024 == 0 && B_TILE % 1024 == 0, "tiles must keep the swizzle phase");
+  static constexpr int GROUPS = FIRST ? 4 : (NOUT <= 32 ? 4 : 2);                // ring depth
+  static constexpr int BAR_OFF = GROUPS * (A_SLOT + B_SLOT);
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
@@ -54,6 +63,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvTcParams p) {
   using S = ConvSmem<NOUT, CIN>;
+  constexpr bool FIRST = S::FIRST;
   constexpr int TMEM_COLS = NOUT <= 32 ? 64 : 256;
   constexpr int ACC_STRIDE = NOUT <= 32 ? 32 : 128;
   constexpr uint32_t SWZ = CIN == 32 ? 4u : 6u;          // SWIZZLE_64B : SWIZZLE_32B
@@ -61,8 +71,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;
-  unsigned char* sB = smem + S::STAGES * S::A_STRIDE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // one per group
+  unsigned char* sB = smem + S::GROUPS * S::A_SLOT;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // one per ring slot
   uint64_t* empty = full + S::GROUPS;
   uint64_t* tfull = empty + S::GROUPS;
   uint64_t* tempty = tfull + 2;
@@ -99,27 +109,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     b = r / p.Dout;
     t0 = tb * CV_BM;
   };
+  // kh taps that fall inside the input rows for output row d; number of ring slots ("groups") the tile uses
+  auto tile_shape = [&](int d, int& kh_lo, int& n_kh, int& n_grp) {
+    kh_lo = max(0, p.pd - p.sd * d);
+    n_kh = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d) - kh_lo + 1;
+    n_grp = FIRST ? (n_kh + CV_G1 - 1) / CV_G1 : n_kh;
+  };
 
   if (warp == 0) {
-    // whole warp, warp-uniform control flow; one elected lane issues a group of steps (see elect_one_sync)
+    // whole warp, warp-uniform control flow; one elected lane issues the two boxes of a group (see elect_one_sync)
     int grp = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      int b, d, t0;
+      int b, d, t0, kh_lo, n_kh, n_grp;
       decode(tile, b, d, t0);
-      const int kh_lo = max(0, p.pd - p.sd * d), kh_hi = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d);
-      const int steps = (kh_hi - kh_lo + 1) * p.KW;
-      for (int s0 = 0; s0 < steps; s0 += CV_GROUP) {
-        const int n = min(CV_GROUP, steps - s0);
+      tile_shape(d, kh_lo, n_kh, n_grp);
+      for (int g = 0; g < n_grp; ++g) {
         mbar_wait(&empty[grp], phase ^ 1);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&full[grp], (uint32_t)n * (S::A_BYTES + S::B_BYTES));
-          for (int j = 0; j < n; ++j) {
-            const int st = s0 + j;
-            const int kh = kh_lo + st / p.KW, kw = st - (st / p.KW) * p.KW;
-            const int stage = grp * CV_GROUP + j;
-            tma_load_4d(sA + stage * S::A_STRIDE, &tmap_x, &full[grp], 0, t0 + kw - p.pt, p.sd * d + kh - p.pd, b);
-            tma_load_2d(sB + stage * S::B_STRIDE, &tmap_w, &full[grp], 0, (kh * p.KW + kw) * NOUT);
+          mbar_arrive_expect_tx(&full[grp], (uint32_t)(S::A_TX + S::B_SLOT));   // full boxes (out-of-range taps are zero fill)
+          if (FIRST) {
+            const int kh = kh_lo + g * CV_G1;
+            tma_load_4d(sA + grp * S::A_SLOT, &tmap_x, &full[grp], 0, t0, p.sd * d + kh - p.pd, b);
+            tma_load_3d(sB + grp * S::B_SLOT, &tmap_w, &full[grp], 0, 0, kh);
+          } else {
+            const int kh = kh_lo + g;
+            tma_load_4d(sA + grp * S::A_SLOT, &tmap_x, &full[grp], 0, t0 - p.pt, p.sd * d + kh - p.pd, b);
+            tma_load_3d(sB + grp * S::B_SLOT, &tmap_w, &full[grp], 0, 0, kh * p.KW);
           }
         }
         __syncwarp();
@@ -128,33 +144,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(CV_BM, NOUT);
+    const uint64_t desc0 = make_smem_desc(0, 16, SBO, SWZ);
+    const uint32_t a_lo = smem_u32(sA) >> 4, b_lo = smem_u32(sB) >> 4;
     int grp = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      int b, d, t0;
+      int b, d, t0, kh_lo, n_kh, n_grp;
       decode(tile, b, d, t0);
-      const int kh_lo = max(0, p.pd - p.sd * d), kh_hi = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d);
-      const int steps = (kh_hi - kh_lo + 1) * p.KW;
+      tile_shape(d, kh_lo, n_kh, n_grp);
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-      for (int s0 = 0; s0 < steps; s0 += CV_GROUP) {
-        const int n = min(CV_GROUP, steps - s0);
+      for (int g = 0; g < n_grp; ++g) {
         mbar_wait(&full[grp], phase);
         tc_fence_after();
         if (elect_one_sync()) {
-          for (int j = 0; j < n; ++j) {
-            const int stage = grp * CV_GROUP + j;
-            const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * S::A_STRIDE), 16, SBO, SWZ);
-            const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * S::B_STRIDE), 16, SBO, SWZ);
+          const uint32_t a0 = a_lo + (uint32_t)grp * (S::A_SLOT >> 4);
+          const uint32_t b0 = b_lo + (uint32_t)grp * (S::B_SLOT >> 4);
+          if (FIRST) {
+            const int n = min(CV_G1, n_kh - g * CV_G1);
 #pragma unroll
-            for (int k = 0; k < CIN / 16; ++k)
-              umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, ((s0 + j) | k) != 0);
+            for (int j = 0; j < CV_G1; ++j)
+              if (j < n)
+                umma_bf16(d_tmem, desc0 + (uint64_t)(a0 + (uint32_t)j * (S::A_TILE >> 4)),
+                          desc0 + (uint64_t)(b0 + (uint32_t)j * (S::B_TILE >> 4)), idesc, j ? 1u : (uint32_t)(g != 0));
+          } else {
+            // tap kw reads the block from row kw on: start address + kw * ROW bytes.  The swizzle XOR is a function
+            // of the shared-memory address bits, which the TMA write used as well, so a start that is not aligned
+            // to the 8-row pattern needs neither a re-layout nor the descriptor's base-offset field (measured:
+            // parity holds with the field left 0 and breaks when it is set to the row phase).
+#pragma unroll
+            for (int kw = 0; kw < kConvKW; ++kw) {
+              const uint32_t as = a0 + (uint32_t)kw * (S::ROW >> 4);
+              const uint64_t adesc = desc0 + (uint64_t)as;
+              const uint64_t bdesc = desc0 + (uint64_t)(b0 + (uint32_t)kw * (S::B_TILE >> 4));
+#pragma unroll
+              for (int k = 0; k < CIN / 16; ++k)
+                umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                          (kw | k) ? 1u : (uint32_t)(g != 0));
+            }
           }
           umma_commit(&empty[grp]);
-          if (s0 + n >= steps) umma_commit(&tfull[acc]);
+          if (g == n_grp - 1) umma_commit(&tfull[acc]);
         }
         __syncwarp();
         if (++grp == S::GROUPS) { grp = 0; phase ^= 1; }
@@ -269,13 +302,16 @@ static int launch_conv(const __nv_bfloat16* x, const ConvLayer& L, const ConvTcP
   using S = ConvSmem<NOUT, CIN>;
   CUtensorMap tx, tw;
   const CUtensorMapSwizzle swz = CIN == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const uint64_t frame = (uint64_t)CIN * 2;
   uint64_t dx[4] = {(uint64_t)CIN, (uint64_t)p.Tp, (uint64_t)p.Din, (uint64_t)p.B};
-  uint64_t sx[4] = {2, (uint64_t)CIN * 2, (uint64_t)p.Tp * CIN * 2, (uint64_t)p.Din * p.Tp * CIN * 2};
-  uint32_t bx[4] = {CIN, CV_BM, 1, 1};
+  uint64_t sx[4] = {2, frame, (uint64_t)p.Tp * frame, (uint64_t)p.Din * p.Tp * frame};
+  uint32_t bx[4] = {CIN, (uint32_t)S::A_ROWS, S::FIRST ? (uint32_t)CV_G1 : 1u, 1};
   if (int e = make_tmap_bf16(&tx, x, 4, dx, sx, bx, swz)) return e;
-  uint64_t dw[2] = {(uint64_t)CIN, (uint64_t)p.KH * p.KW * NOUT}, sw[2] = {2, (uint64_t)CIN * 2};
-  uint32_t bw[2] = {CIN, NOUT};
-  if (int e = make_tmap_bf16(&tw, L.w_tc, 2, dw, sw, bw, swz)) return e;
+  // weights [(kh*KW + kw)][NOUT][CIN]; taps past the last one are out-of-bounds zero fill
+  uint64_t dw[3] = {(uint64_t)CIN, (uint64_t)NOUT, (uint64_t)p.KH * p.KW};
+  uint64_t sw[3] = {2, frame, (uint64_t)NOUT * frame};
+  uint32_t bw[3] = {CIN, NOUT, S::FIRST ? (uint32_t)CV_G1 : (uint32_t)kConvKW};
+  if (int e = make_tmap_bf16(&tw, L.w_tc, 3, dw, sw, bw, swz)) return e;
   static bool attr = false;
   if (!attr) {
     DSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NOUT, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
