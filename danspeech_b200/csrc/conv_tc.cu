@@ -10,7 +10,9 @@
 //     + kw rows), so the 11 overlapping windows cost one load instead of eleven.
 //   * Block 1 has Cin = 1, which no MMA can use directly; its input is expanded once in time
 //     ("x1[b,d,t,j] = spect[b,d,2t+j-5]", 11 taps padded to 16) so that it becomes a kH x 1 convolution over 16
-//     channels; a box {16, 128 frames, 4 rows} delivers four consecutive kh taps.
+//     channels.  A TMA box with 32-byte rows moves one sector per row and was the bottleneck, so the expansion
+//     kernel writes x1 as ready-made operand tiles [b][128-frame block][d][128 x 32 B, 32B-swizzled]: four
+//     consecutive kh taps (= input rows) are ONE contiguous 16 KB bulk copy (cp.async.bulk, no tensor map).
 // A TMA instruction costs the producer ~240 cycles, more than the MMAs of one (kh,kw) step take: with one step
 // per instruction the kernel was producer-bound; now it is bound by the MMA rate (~50-65 cycles per K=16 slice at
 // these tile shapes, scripts/mma_microbench.py).
@@ -30,6 +32,7 @@ constexpr int CV_G1 = 4;        // block 1: kh taps per box / per elected issue 
 struct ConvTcParams {
   const float* bias;          // [NOUT] folded
   const int32_t* lens;        // [B] output frames per utterance (nullptr: no mask)
+  const __nv_bfloat16* x_tiles;   // block 1 only: operand tiles [B][t_blocks][Din][128 frames x 16]
   __nv_bfloat16* out;
   int B, Tp, Din, Dout, KH, KW, sd, pd, pt;
   int rnn_layout;             // 0: [B][Dout][Tp][NOUT]   1: [(t*B+b)][Dout*NOUT] (feature = d*NOUT + co)
@@ -127,12 +130,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       for (int g = 0; g < n_grp; ++g) {
         mbar_wait(&empty[grp], phase ^ 1);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&full[grp], (uint32_t)(S::A_TX + S::B_SLOT));   // full boxes (out-of-range taps are zero fill)
           if (FIRST) {
             const int kh = kh_lo + g * CV_G1;
-            tma_load_4d(sA + grp * S::A_SLOT, &tmap_x, &full[grp], 0, t0, p.sd * d + kh - p.pd, b);
-            tma_load_3d(sB + grp * S::B_SLOT, &tmap_w, &full[grp], 0, 0, kh);
+            const int n = min(CV_G1, n_kh - g * CV_G1);            // rows kh .. kh+n-1 are inside the input
+            const int row = p.sd * d + kh - p.pd;
+            mbar_arrive_expect_tx(&full[grp], (uint32_t)(n * S::A_TILE + S::B_SLOT));
+            bulk_load(sA + grp * S::A_SLOT,
+                      p.x_tiles + (((size_t)b * t_blocks + t0 / CV_BM) * p.Din + row) * (size_t)(CV_BM * CIN),
+                      (uint32_t)(n * S::A_TILE), &full[grp]);
+            tma_load_3d(sB + grp * S::B_SLOT, &tmap_w, &full[grp], 0, 0, kh);   // taps past KH are zero fill
           } else {
+            mbar_arrive_expect_tx(&full[grp], (uint32_t)(S::A_TX + S::B_SLOT));   // full boxes (out-of-range frames / rows are zero fill)
             const int kh = kh_lo + g;
             tma_load_4d(sA + grp * S::A_SLOT, &tmap_x, &full[grp], 0, t0 - p.pt, p.sd * d + kh - p.pd, b);
             tma_load_3d(sB + grp * S::B_SLOT, &tmap_w, &full[grp], 0, 0, kh * p.KW);
@@ -255,27 +263,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
 }
 
-// x1[b][d][t][j] = spect[b][d][2t + j - 5] (j < 11, zero outside [0,T) and for j >= 11)
+// Block-1 operand tiles: x1[b][d][t][j] = spect[b][d][2t + j - 5] (j < 11, zero outside [0,T) and for j >= 11),
+// stored as [b][t / 128][d][tile], tile = 128 rows (frames) x 32 bytes in the 32-byte-swizzled K-major order the
+// MMA reads (16-byte chunk c of row r at r*32 + ((c ^ ((r >> 2) & 1)) * 16); frames >= Tp of the last block are 0.
 __global__ void im2col_time_kernel(const float* __restrict__ spect, __nv_bfloat16* __restrict__ x1, int B, int D, int T,
-                                   int Tp) {
-  const int64_t total = (int64_t)B * D * Tp;
+                                   int Tp, int t_blocks) {
+  const int Tpad = t_blocks * CV_BM;
+  const int64_t total = (int64_t)B * D * Tpad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int t = (int)(i % Tp);
-    const int64_t bd = i / Tp;
+    const int t = (int)(i % Tpad);
+    const int64_t bd = i / Tpad;
+    const int d = (int)(bd % D);
+    const int64_t b = bd / D;
     const float* src = spect + bd * T;
     uint32_t w[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
       const int j0 = 2 * h, j1 = 2 * h + 1;
       const int s0 = 2 * t + j0 - 5, s1 = 2 * t + j1 - 5;
-      const float v0 = (j0 < kConvKW && s0 >= 0 && s0 < T) ? src[s0] : 0.f;
-      const float v1 = (j1 < kConvKW && s1 >= 0 && s1 < T) ? src[s1] : 0.f;
+      const float v0 = (t < Tp && j0 < kConvKW && s0 >= 0 && s0 < T) ? src[s0] : 0.f;
+      const float v1 = (t < Tp && j1 < kConvKW && s1 >= 0 && s1 < T) ? src[s1] : 0.f;
       __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
       w[h] = *reinterpret_cast<uint32_t*>(&pk);
     }
-    uint4* dst = reinterpret_cast<uint4*>(x1 + i * 16);
-    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    const int tb = t / CV_BM, tl = t % CV_BM, sw = (tl >> 2) & 1;
+    uint4* dst = reinterpret_cast<uint4*>(x1 + (((b * t_blocks + tb) * D + d) * (int64_t)CV_BM + tl) * 16);
+    dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[sw ^ 1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 
@@ -303,10 +317,12 @@ static int launch_conv(const __nv_bfloat16* x, const ConvLayer& L, const ConvTcP
   CUtensorMap tx, tw;
   const CUtensorMapSwizzle swz = CIN == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   const uint64_t frame = (uint64_t)CIN * 2;
-  uint64_t dx[4] = {(uint64_t)CIN, (uint64_t)p.Tp, (uint64_t)p.Din, (uint64_t)p.B};
-  uint64_t sx[4] = {2, frame, (uint64_t)p.Tp * frame, (uint64_t)p.Din * p.Tp * frame};
-  uint32_t bx[4] = {CIN, (uint32_t)S::A_ROWS, S::FIRST ? (uint32_t)CV_G1 : 1u, 1};
-  if (int e = make_tmap_bf16(&tx, x, 4, dx, sx, bx, swz)) return e;
+  if (!S::FIRST) {   // block 1 reads ready-made tiles with bulk copies (p.x_tiles)
+    uint64_t dx[4] = {(uint64_t)CIN, (uint64_t)p.Tp, (uint64_t)p.Din, (uint64_t)p.B};
+    uint64_t sx[4] = {2, frame, (uint64_t)p.Tp * frame, (uint64_t)p.Din * p.Tp * frame};
+    uint32_t bx[4] = {CIN, (uint32_t)S::A_ROWS, 1, 1};
+    if (int e = make_tmap_bf16(&tx, x, 4, dx, sx, bx, swz)) return e;
+  }
   // weights [(kh*KW + kw)][NOUT][CIN]; taps past the last one are out-of-bounds zero fill
   uint64_t dw[3] = {(uint64_t)CIN, (uint64_t)NOUT, (uint64_t)p.KH * p.KW};
   uint64_t sw[3] = {2, frame, (uint64_t)NOUT * frame};
@@ -321,17 +337,20 @@ static int launch_conv(const __nv_bfloat16* x, const ConvLayer& L, const ConvTcP
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.B * p.Dout * cdiv(p.Tp, CV_BM);
-  conv_tc_kernel<NOUT, CIN><<<tiles < sms ? tiles : sms, CV_THREADS, S::TOTAL, st>>>(tx, tw, p);
+  conv_tc_kernel<NOUT, CIN><<<tiles < sms ? tiles : sms, CV_THREADS, S::TOTAL, st>>>(S::FIRST ? tw : tx, tw, p);
   DSB_CHECK_LAUNCH();
   return 0;
 }
 
 }  // namespace tc
 
+size_t conv1_tiles_elems(int B, int Tp) { return (size_t)B * cdiv(Tp, tc::CV_BM) * kFreqBins * tc::CV_BM * 16; }
+
 int im2col_time_tc(const float* spect, __nv_bfloat16* x1, int B, int T, int Tp, cudaStream_t st) {
-  const int64_t total = (int64_t)B * kFreqBins * Tp;
+  const int t_blocks = cdiv(Tp, tc::CV_BM);
+  const int64_t total = (int64_t)B * kFreqBins * t_blocks * tc::CV_BM;
   tc::im2col_time_kernel<<<(int)(cdiv64(total, 256) < 148 * 16 ? cdiv64(total, 256) : 148 * 16), 256, 0, st>>>(
-      spect, x1, B, kFreqBins, T, Tp);
+      spect, x1, B, kFreqBins, T, Tp, t_blocks);
   DSB_CHECK_LAUNCH();
   return 0;
 }
@@ -344,7 +363,7 @@ int pack_conv_w_tc(const ConvLayer& L, bool first, __nv_bfloat16* out, cudaStrea
   return 0;
 }
 
-// x: block 0 -> time-expanded spectrogram [B][161][Tp][16]; later blocks -> [B][Din][Tp][32]
+// x: block 0 -> operand tiles of the time-expanded spectrogram (im2col_time_tc); later blocks -> [B][Din][Tp][32]
 // d_len == nullptr: no length mask.  seg != nullptr: segmented time axis {seg_len, seg_off, seg_valid, n_streams}.
 int conv_block_tc(const __nv_bfloat16* x, const ConvLayer& L, bool first, const int32_t* d_len, int B, int Tp,
                   __nv_bfloat16* out, bool rnn_layout, int64_t out_ld, cudaStream_t st, const int* seg) {
@@ -355,6 +374,7 @@ int conv_block_tc(const __nv_bfloat16* x, const ConvLayer& L, bool first, const 
   }
   p.bias = L.bias;
   p.lens = d_len;
+  p.x_tiles = first ? x : nullptr;
   p.out = out;
   p.B = B; p.Tp = Tp; p.Din = L.din; p.Dout = L.dout; p.KH = L.kh;
   p.KW = first ? 1 : kConvKW;

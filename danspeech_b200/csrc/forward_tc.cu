@@ -128,7 +128,7 @@ TcWorkspace carve_tc(const dsb_model* m, int B, int T, void* base) {
   const int Tp = dsb_model_out_frames(m, T);
   const int dirs = m->rnns[0].dirs, G = m->rnns[0].gates, H = d.rnn_hidden_size;
   const size_t act_elems = (size_t)Tp * B * H;   // fp32 scratch for the lookahead output
-  size_t cb0 = (size_t)B * kFreqBins * Tp * 16, cb1 = 0;
+  size_t cb0 = conv1_tiles_elems(B, Tp), cb1 = 0;
   for (size_t i = 0; i < m->convs.size(); ++i) {
     const ConvLayer& L = m->convs[i];
     const size_t e = (size_t)B * L.dout * Tp * L.cout;
@@ -244,8 +244,7 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
     if (int e = lookahead_htanh_f32(ws.xf, m->lookahead_w, ws.act[0], Tp, B, H, d.context, st)) return e;
     xt = ws.act[0];
   }
-  if (int e = gemm_bias_f32(xt, m->fc_w, m->fc_b, ws.logits, M, C, H, st)) return e;
-  if (int e = softmax_argmax_f32(ws.logits, probs, argmax, Tp, B, C, st)) return e;
+  if (int e = fc_softmax_argmax_f32(xt, m->fc_w, m->fc_b, probs, argmax, ws.logits, Tp, B, C, H, st)) return e;
   prof_end(ST_TAIL, st);
 
   if (used_tc_rnn) {

@@ -381,6 +381,5 @@ extern "C" int dsb_forward(dsb_model* m, const float* spect, const int32_t* leng
     x = ws.act[cur];
     cur ^= 1;
   }
-  if (int e = gemm_bias_f32(x, m->fc_w, m->fc_b, ws.logits, (int64_t)Tp * B, C, H, st)) return e;
-  return softmax_argmax_f32(ws.logits, probs, argmax, Tp, B, C, st);
+  return fc_softmax_argmax_f32(x, m->fc_w, m->fc_b, probs, argmax, ws.logits, Tp, B, C, H, st);
 }

@@ -67,10 +67,13 @@ int rnn_layer_f32(const dsb_model* m, const RnnLayer& L, const float* gates_x, c
                   int Trows, float* y, float* h_state, float* c_state, cudaStream_t st);
 int lookahead_htanh_f32(const float* x, const float* w, float* y, int T, int B, int H, int context, cudaStream_t st);
 int softmax_argmax_f32(const float* logits, float* probs, int32_t* argmax, int T, int B, int C, cudaStream_t st);
+int fc_softmax_argmax_f32(const float* x, const float* W, const float* bias, float* probs, int32_t* argmax,
+                          float* logits_scratch, int T, int B, int C, int H, cudaStream_t st);
 
 // ---- bf16 tensor-core path (tcgen05 / TMEM / TMA) ----
 int gemm_bias_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
                  float* C, int64_t ldc, int M, int N, int K, cudaStream_t st);
+size_t conv1_tiles_elems(int B, int Tp);   // bf16 elements of the block-1 operand tiles
 int im2col_time_tc(const float* spect, __nv_bfloat16* x1, int B, int T, int Tp, cudaStream_t st);
 int pack_conv_w_tc(const ConvLayer& L, bool first, __nv_bfloat16* out, cudaStream_t st);
 int conv_block_tc(const __nv_bfloat16* x, const ConvLayer& L, bool first, const int32_t* d_len, int B, int Tp,

@@ -64,28 +64,33 @@ __global__ void save_tail_kernel(const float* __restrict__ src, int T, float* __
   }
 }
 // ---- bf16 path helpers (channels-last, streams side by side on the time axis) ----
-// x1[d][s*t1 + t][j] = in1[s][d][2t + j - 5] (j < 11; zero outside [0, tin1) and for j >= 11)
+// Block-1 operand tiles for the streams laid side by side in time (frame u = s*t1 + t of one long "utterance"):
+// x1[u][j] = in1[s][d][2t + j - 5] (j < 11; zero outside [0, tin1) and for j >= 11), stored as
+// [u / 128][d][128 frames x 32 B, 32B-swizzled] like conv_tc.cu's im2col_time_kernel; frames >= S*t1 are 0.
 __global__ void im2col_time_stream_kernel(const float* __restrict__ in1, __nv_bfloat16* __restrict__ x1, int S, int D,
-                                          int tin1, int t1) {
-  const int64_t total = (int64_t)D * S * t1;
+                                          int tin1, int t1, int t_blocks) {
+  const int Upad = t_blocks * 128;
+  const int64_t total = (int64_t)D * Upad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int t = (int)(i % t1);
-    const int64_t r = i / t1;
-    const int s = (int)(r % S), d = (int)(r / S);
-    const float* src = in1 + ((int64_t)s * D + d) * tin1;
+    const int u = (int)(i % Upad);
+    const int d = (int)(i / Upad);
+    const int s = u / t1, t = u - s * t1;
+    const bool in = s < S;
+    const float* src = in1 + ((int64_t)(in ? s : 0) * D + d) * tin1;
     uint32_t w[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
       const int j0 = 2 * h, j1 = 2 * h + 1;
       const int s0 = 2 * t + j0 - 5, s1 = 2 * t + j1 - 5;
-      const float v0 = (j0 < kConvKW && s0 >= 0 && s0 < tin1) ? src[s0] : 0.f;
-      const float v1 = (j1 < kConvKW && s1 >= 0 && s1 < tin1) ? src[s1] : 0.f;
+      const float v0 = (in && j0 < kConvKW && s0 >= 0 && s0 < tin1) ? src[s0] : 0.f;
+      const float v1 = (in && j1 < kConvKW && s1 >= 0 && s1 < tin1) ? src[s1] : 0.f;
       __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
       w[h] = *reinterpret_cast<uint32_t*>(&pk);
     }
-    uint4* dst = reinterpret_cast<uint4*>(x1 + i * 16);
-    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    const int tb = u >> 7, tl = u & 127, sw = (tl >> 2) & 1;
+    uint4* dst = reinterpret_cast<uint4*>(x1 + ((((int64_t)tb * D + d) << 7) + tl) * 16);
+    dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[sw ^ 1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 // in2[d][s*seg + u][c], u in [0, seg = tin2 + 10): 5 zeros, then the tin2 logical frames
@@ -185,7 +190,7 @@ extern "C" int dsb_stream_state_create(dsb_model* m, int n_streams, int max_chun
     const RnnLayer& R0 = m->rnns[0];
     const int ld = R0.in_ld > (H + 7) / 8 * 8 ? R0.in_ld : (H + 7) / 8 * 8;
     SA(left2b, (int64_t)81 * S * 10 * 32);
-    SA(x1, (int64_t)kFreqBins * S * t1 * 16);
+    SA(x1, (int64_t)conv1_tiles_elems(1, S * t1));
     SA(c1b, (int64_t)81 * S * t1 * 32);
     SA(in2b, (int64_t)81 * S * (tin2 + 10) * 32);
     SA(xb, (int64_t)tin2 * S * ld);
@@ -257,7 +262,9 @@ extern "C" int dsb_streaming_forward(dsb_model* m, dsb_stream_state* s, const fl
   if (s->tc) {
     const int64_t rows2 = (int64_t)81 * S;
     const int seg = tin2 + 10;
-    im2col_time_stream_kernel<<<sgrid((int64_t)kFreqBins * S * t1), 256, 0, st>>>(s->in1, s->x1, S, kFreqBins, tin1, t1);
+    const int t_blocks1 = cdiv(S * t1, 128);
+    im2col_time_stream_kernel<<<sgrid((int64_t)kFreqBins * t_blocks1 * 128), 256, 0, st>>>(s->in1, s->x1, S, kFreqBins, tin1, t1,
+                                                                                       t_blocks1);
     DSB_CHECK_LAUNCH();
     if (int e = conv_block_tc(s->x1, m->convs[0], true, nullptr, 1, S * t1, s->c1b, false, 0, st)) return e;
     assemble_cl_kernel<<<sgrid(rows2 * seg * 4), 256, 0, st>>>(s->c1b, t1, s->left2b, is_first ? 0 : 10, is_first ? 5 : 0,
@@ -371,8 +378,7 @@ extern "C" int dsb_streaming_forward(dsb_model* m, dsb_stream_state* s, const fl
   if (is_last) s->look_init = false;
   if (n_out <= 0) return 0;
   if (int e = lookahead_htanh_f32(s->cat, m->lookahead_w, s->lo, L, S, H, ctx, st)) return e;
-  if (int e = gemm_bias_f32(s->lo, m->fc_w, m->fc_b, s->logits, (int64_t)n_out * S, C, H, st)) return e;
-  if (int e = softmax_argmax_f32(s->logits, probs, nullptr, n_out, S, C, st)) return e;
+  if (int e = fc_softmax_argmax_f32(s->lo, m->fc_w, m->fc_b, probs, nullptr, s->logits, n_out, S, C, H, st)) return e;
   *k_out = n_out;
   return 0;
 }

@@ -69,6 +69,119 @@ int softmax_argmax_f32(const float* logits, float* probs, int32_t* argmax, int T
   return 0;
 }
 
+// SequenceWise fc (BatchNorm1d folded into W, b; model.py:414-420) fused with InferenceBatchSoftmax, the transpose
+// to [B,T,C] and the argmax: the C x H weight matrix lives in shared memory for the whole (persistent) CTA, a warp
+// takes R rows at a time, every lane accumulates 4 consecutive k per 128 for all classes (one 128-bit shared load
+// feeds 4R FMAs; 16 warps of ~110 registers hide the load latencies better than 8 warps with R = 4 did), then the R*C sums are reduced across the warp and the softmax is done from a small staging
+// area.  HBM-bound in principle (H*4 bytes per row); replaces a narrow-N GEMM plus a second pass over the logits.
+constexpr int FC_WARPS = 16;
+template <int NC, int R>
+__global__ void __launch_bounds__(FC_WARPS * 32, 1)
+fc_softmax_argmax_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                         float* __restrict__ probs, int32_t* __restrict__ argmax, int T, int B, int C, int H, int Hp) {
+  extern __shared__ float fc_smem[];
+  float* sW = fc_smem;                          // [NC][Hp], zero padded
+  float* sL = fc_smem + (size_t)NC * Hp;        // [FC_WARPS][R][NC]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NC * Hp; i += blockDim.x) {
+    const int c = i / Hp, k = i - c * Hp;
+    sW[i] = (c < C && k < H) ? W[(size_t)c * H + k] : 0.f;
+  }
+  __syncthreads();
+  const int64_t rows = (int64_t)T * B;
+  const int64_t n_groups = (rows + R - 1) / R;
+  float* myL = sL + warp * R * NC;
+  for (int64_t grp = (int64_t)blockIdx.x * FC_WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * FC_WARPS) {
+    const int64_t row0 = grp * R;
+    float acc[R][NC];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[r][c] = 0.f;
+    // the x loads of the next 128-wide slice are issued before the FMAs of the current one (two warps per
+    // scheduler cannot hide a DRAM round trip otherwise)
+    auto load_x = [&](int k0, float4 (&xv)[R]) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        xv[r] = (k0 < H && row0 + r < rows) ? __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * H + k0))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 xn[R];
+    load_x(lane * 4, xn);
+    for (int k0 = lane * 4; k0 < H; k0 += 128) {
+      float4 xv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) xv[r] = xn[r];
+      load_x(k0 + 128, xn);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float4 w = *reinterpret_cast<const float4*>(sW + (size_t)c * Hp + k0);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          acc[r][c] = fmaf(xv[r].x, w.x, fmaf(xv[r].y, w.y, fmaf(xv[r].z, w.z, fmaf(xv[r].w, w.w, acc[r][c]))));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float v = warp_sum(acc[r][c]);
+        if (lane == 0) myL[r * NC + c] = v + ((bias && c < C) ? __ldg(bias + c) : 0.f);
+      }
+    __syncwarp();
+    for (int r = 0; r < R && row0 + r < rows; ++r) {
+      const int64_t row = row0 + r;
+      const int t = (int)(row / B), b = (int)(row - (int64_t)t * B);
+      const float* in = myL + r * NC;
+      float mx = -INFINITY;
+      for (int c = lane; c < C; c += 32) mx = fmaxf(mx, in[c]);
+      mx = warp_max(mx);
+      float sum = 0.0f;
+      for (int c = lane; c < C; c += 32) sum += expf(in[c] - mx);
+      sum = warp_sum(sum);
+      float* out = probs + ((int64_t)b * T + t) * C;
+      float best = -1.0f;
+      int besti = 0x7fffffff;
+      for (int c = lane; c < C; c += 32) {
+        const float pv = expf(in[c] - mx) / sum;
+        out[c] = pv;
+        if (pv > best) { best = pv; besti = c; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+      }
+      if (argmax && lane == 0) argmax[(int64_t)b * T + t] = besti;
+    }
+    __syncwarp();
+  }
+}
+
+// x [T*B][H] fp32 -> probs [B][T][C] (+ argmax).  Uses the fused kernel when C <= 33, H % 4 == 0 and the weights fit
+// in shared memory; otherwise the fp32 GEMM into `logits_scratch` [T*B][C] followed by softmax_argmax_f32.
+int fc_softmax_argmax_f32(const float* x, const float* W, const float* bias, float* probs, int32_t* argmax,
+                          float* logits_scratch, int T, int B, int C, int H, cudaStream_t st) {
+  constexpr int NC = 33, R = 2;
+  const int Hp = (H + 127) / 128 * 128;
+  const size_t smem = ((size_t)NC * Hp + FC_WARPS * R * NC) * sizeof(float);
+  if (C <= NC && (H & 3) == 0 && smem <= 227 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    static bool attr = false;
+    if (!attr) {
+      DSB_CUDA(cudaFuncSetAttribute(fc_softmax_argmax_kernel<NC, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr = true;
+    }
+    const int64_t groups = ((int64_t)T * B + R - 1) / R;
+    const int grid = (int)(cdiv64(groups, FC_WARPS) < 148 ? cdiv64(groups, FC_WARPS) : 148);
+    fc_softmax_argmax_kernel<NC, R><<<grid, FC_WARPS * 32, smem, st>>>(x, W, bias, probs, argmax, T, B, C, H, Hp);
+    DSB_CHECK_LAUNCH();
+    return 0;
+  }
+  if (int e = gemm_bias_f32(x, W, bias, logits_scratch, (int64_t)T * B, C, H, st)) return e;
+  return softmax_argmax_f32(logits_scratch, probs, argmax, T, B, C, st);
+}
+
 // One warp per utterance.
 __global__ void greedy_kernel(const float* __restrict__ probs, const int32_t* __restrict__ argmax,
                               const int32_t* __restrict__ sizes, int B, int T, int C, int blank,
