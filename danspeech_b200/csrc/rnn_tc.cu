@@ -45,7 +45,7 @@ constexpr int RT_SMEM_LIMIT = 227 * 1024;
 struct RtPlan {
   int groups, gsz, stage_bytes, stage_off, stg_off, bar_off, total;
 };
-__host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U) {
+__host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U, int small_groups = 0) {
   RtPlan pl;
   pl.stage_bytes = BP * RT_BK * 2;
   const int w_bytes = nkc * RT_W_BYTES;
@@ -54,7 +54,7 @@ __host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U) {
   const int room = RT_SMEM_LIMIT - 2048 - 256 - w_bytes - stg_al;   // 1 KB align slack + 1 KB static
   int gsz = RT_GROUP, groups = room / (pl.stage_bytes * gsz);
   if (groups > 2) groups = 2;
-  if (groups < 2) {   // a single group cannot overlap TMA with the MMAs: use smaller groups instead
+  if (groups < 2 || small_groups) {   // a single group cannot overlap TMA with the MMAs: use smaller groups instead
     gsz = 2;
     groups = room / (pl.stage_bytes * gsz);
     if (groups > RT_MAX_GROUPS) groups = RT_MAX_GROUPS;
@@ -87,6 +87,7 @@ struct RnnTcParams {
   int n_bgroups;   // the batch is processed in groups of BP rows ...
   int slots;       // ... by `slots` independent CTA sets per direction (set k takes groups k, k+slots, ...)
   int U;      // hidden units per CTA (2 * units per half)
+  int small_groups;   // ring in groups of 2 K chunks even when two groups of 4 fit (DSB_RNN_GSZ=2)
   int nkc;    // K chunks of 64 (HP / 64)
   unsigned long long* dbg;   // optional [grid][16] cycle counters (DSB_RNN_DEBUG=1)
 };
@@ -145,7 +146,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   constexpr int U = 2 * UH;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  const RtPlan pl = rt_plan(p.nkc, p.BP, U);
+  const RtPlan pl = rt_plan(p.nkc, p.BP, U, p.small_groups);
   unsigned char* sW = smem;
   unsigned char* sA = smem + pl.stage_off;
   unsigned char* sStg = smem + pl.stg_off;
@@ -198,24 +199,27 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     bool ok = true;
     const unsigned* ctr = p.counters + dir * p.slots + slot;
     unsigned long long d_spin = 0, d_fence = 0, d_issue = 0, d_empty = 0;
-    long long use = 0;   // group uses so far (ring position)
+    // ring positions of the next group to arm / to load (slot index + phase kept incrementally: a 64-bit
+    // modulo per group costs the single issuing warp hundreds of cycles)
+    int arm_slot = 0, load_slot = 0;
+    uint32_t arm_phase = 0;
     // Arming a group (waiting for its slot, arrive.expect_tx on its stages) does not depend on h, so the first
     // `n_groups` groups of a step are armed BEFORE the step barrier is polled; after the barrier only the
     // proxy fence and the TMA issues remain on the critical path.
     // One TMA per group: the h buffer is mapped as a 3-D tensor {64 k, BP rows, nkc chunks}, so a box
     // {64, BP, RT_GROUP} lands as RT_GROUP consecutive 128B-swizzled K-chunk tiles (a TMA instruction costs
     // ~240 cycles of issue; chunks beyond nkc are zero-filled and never used by the MMAs).
-    auto arm_group = [&](long long u, int g) -> bool {
-      (void)g;
-      const int grp = (int)(u % n_groups);
-      const uint32_t gphase = (uint32_t)((u / n_groups) & 1);
-      if (!__all_sync(0xffffffffu, wait_abortable(&gempty[grp], gphase ^ 1, p.abort_flag))) return false;
+    auto arm_group = [&]() -> bool {
+      const int grp = arm_slot;
+      if (!__all_sync(0xffffffffu, wait_abortable(&gempty[grp], arm_phase ^ 1, p.abort_flag))) return false;
       if (elect_one_sync()) mbar_arrive_expect_tx(&full[grp], (uint32_t)(gsz * pl.stage_bytes));
       __syncwarp();
+      if (++arm_slot == n_groups) { arm_slot = 0; arm_phase ^= 1; }
       return true;
     };
-    auto load_group = [&](long long u, int g, int row0) {
-      const int grp = (int)(u % n_groups);
+    auto load_group = [&](int g, int row0) {
+      const int grp = load_slot;
+      if (++load_slot == n_groups) load_slot = 0;
       int gg = g + g_rot;
       if (gg >= gps) gg -= gps;
       if (elect_one_sync()) {
@@ -231,7 +235,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     for (int s = 0; s < p.Tmax && ok; ++s) {
       long long c0 = clock64();
       const int pre = min(gps, n_groups);
-      for (int g = 0; g < pre && ok; ++g) ok = arm_group(use + g, g);
+      for (int g = 0; g < pre && ok; ++g) ok = arm_group();
       if (!ok) break;
       d_empty += clock64() - c0;
       c0 = clock64();
@@ -262,14 +266,13 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       for (int g = 0; g < gps && ok; ++g) {
         if (g >= pre) {
           long long w0 = clock64();
-          ok = arm_group(use + g, g);
+          ok = arm_group();
           d_empty += clock64() - w0;
           if (!ok) break;
         }
-        load_group(use + g, g, row0);
+        load_group(g, row0);
         if (p.dbg && s == 100 && g < 8 && lane == 0) p.dbg[blockIdx.x * 128 + 16 + g] = clock64();
       }
-      use += gps;
       d_issue += clock64() - c2;
     }
     if (p.dbg && lane == 0) {
@@ -288,13 +291,12 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     const uint32_t a_lo = smem_u32(sA) >> 4, w_lo = smem_u32(sW) >> 4, stage16 = (uint32_t)pl.stage_bytes >> 4;
     bool ok = __all_sync(0xffffffffu, wait_abortable(wbar, 0, p.abort_flag));
     unsigned long long d_wait0 = 0, d_rest = 0, d_waitn = 0;
-    long long use = 0;
+    int grp = 0;
+    uint32_t fphase = 0;
     for (int bg = slot; bg < p.n_bgroups && ok; bg += p.slots)
     for (int s = 0; s < p.Tmax && ok; ++s) {
       long long m0 = clock64();
-      for (int g = 0; g < gps; ++g, ++use) {
-        const int grp = (int)(use % n_groups);
-        const uint32_t fphase = (uint32_t)((use / n_groups) & 1);
+      for (int g = 0; g < gps; ++g) {
         int gg = g + g_rot;
         if (gg >= gps) gg -= gps;
         const int i0 = gg * gsz, i1 = min(p.nkc, i0 + gsz);
@@ -325,6 +327,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           if (g == gps - 1) umma_commit(dfull);
         }
         __syncwarp();
+        if (++grp == n_groups) { grp = 0; fphase ^= 1; }
       }
       if (p.dbg && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 64] = clock64();
       d_rest += clock64() - m0;
@@ -664,7 +667,8 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   // h exchange buffer as {64 k, rows, K chunks}: one box {64, BP, RT_GROUP} = RT_GROUP consecutive chunk tiles
   uint64_t dh[3] = {(uint64_t)RT_BK, (uint64_t)n_bgroups * 2 * L.dirs * BP, (uint64_t)nkc};
   uint64_t sh[3] = {2, (uint64_t)HP * 2, (uint64_t)RT_BK * 2};
-  const int gsz = rt_plan(nkc, BP, 2 * (32 / L.gates)).gsz;
+  static const int small_groups = (getenv("DSB_RNN_GSZ") && atoi(getenv("DSB_RNN_GSZ")) == 2) ? 1 : 0;
+  const int gsz = rt_plan(nkc, BP, 2 * (32 / L.gates), small_groups).gsz;
   uint32_t bh[3] = {RT_BK, (uint32_t)BP, (uint32_t)gsz};
   if (int e = make_tmap_bf16(&th, hbuf, 3, dh, sh, bh, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
 
@@ -680,7 +684,8 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.n_bgroups = n_bgroups; p.slots = slots;
   p.B = B; p.H = L.H; p.HP = HP; p.BP = BP; p.T = T; p.Tmax = Tmax;
   p.dirs = L.dirs; p.cpd = cpd; p.U = 2 * (32 / L.gates); p.nkc = nkc;
-  const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates)).total;
+  p.small_groups = small_groups;
+  const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates), small_groups).total;
   const void* fn = L.gates == 3 ? (const void*)rnn_tc_kernel<3>
                    : L.gates == 4 ? (const void*)rnn_tc_kernel<4> : (const void*)rnn_tc_kernel<1>;
   DSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
