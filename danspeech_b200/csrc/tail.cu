@@ -22,10 +22,47 @@ __global__ void lookahead_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+// Sliding-window variant for the usual context of 20: one thread per (batch, channel) column walks the time axis
+// with the window in registers, so every input element is read once (the generic kernel reads it `context` times).
+template <int CTX>
+__global__ void lookahead_window_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                                        int T, int BH, int H, int t_chunk) {
+  const int bc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bc >= BH) return;
+  const int t0 = blockIdx.y * t_chunk, t1 = min(T, t0 + t_chunk);
+  const int c = bc % H;
+  float wt[CTX], win[CTX];
+#pragma unroll
+  for (int j = 0; j < CTX; ++j) {
+    wt[j] = __ldg(w + c * CTX + j);
+    win[j] = (j > 0 && t0 + j - 1 < T) ? x[(int64_t)(t0 + j - 1) * BH + bc] : 0.f;   // win[j] = x[t + j - 1] before the shift
+  }
+  for (int t = t0; t < t1; ++t) {
+#pragma unroll
+    for (int j = 0; j < CTX - 1; ++j) win[j] = win[j + 1];
+    win[CTX - 1] = t + CTX - 1 < T ? x[(int64_t)(t + CTX - 1) * BH + bc] : 0.f;
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < CTX; ++j) acc = fmaf(wt[j], win[j], acc);
+    y[(int64_t)t * BH + bc] = fminf(fmaxf(acc, 0.0f), 20.0f);
+  }
+}
+
 int lookahead_htanh_f32(const float* x, const float* w, float* y, int T, int B, int H, int context, cudaStream_t st) {
+  const int BH = B * H;
+  if (context == 20) {
+    // enough (column, time-chunk) threads to fill the GPU; a chunk re-reads context-1 frames at its start
+    int chunks = 1;
+    while ((int64_t)BH * chunks < 148 * 2048 && chunks * 64 < T) chunks *= 2;
+    const int t_chunk = cdiv(T, chunks);
+    dim3 grid(cdiv(BH, 128), cdiv(T, t_chunk));
+    lookahead_window_kernel<20><<<grid, 128, 0, st>>>(x, w, y, T, BH, H, t_chunk);
+    DSB_CHECK_LAUNCH();
+    return 0;
+  }
   const int64_t total = (int64_t)T * B * H;
   int blocks = (int)(cdiv64(total, 256) < 148 * 8 ? cdiv64(total, 256) : 148 * 8);
-  lookahead_kernel<<<blocks, 256, 0, st>>>(x, w, y, T, B * H, H, context);
+  lookahead_kernel<<<blocks, 256, 0, st>>>(x, w, y, T, BH, H, context);
   DSB_CHECK_LAUNCH();
   return 0;
 }

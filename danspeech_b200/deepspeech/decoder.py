@@ -4,6 +4,7 @@ Interfaces mirror danspeech/deepspeech/decoder.py: Decoder (:24-88), BeamCTCDeco
 GreedyDecoder (:147-198).  ``wer``/``cer`` (decoder.py:45-74) are scoring utilities outside the
 inference path and are implemented here without the Levenshtein C dependency.
 """
+import numpy as np
 import torch
 
 from .. import _native as N
@@ -78,6 +79,16 @@ class GreedyDecoder(Decoder):
                                               N.ptr(offsets), N.ptr(out_len), N.current_stream()),
                     "dsb_greedy_decode")
         return tokens, offsets, out_len
+
+    def decode_strings(self, probs, sizes=None):
+        """Transcripts only (List[B] of str): the serving loops need no offsets, and building B offset tensors
+        costs more host time than the kernel."""
+        tokens, _, out_len = self.decode_device(probs, sizes)
+        packed = torch.cat([out_len.view(-1, 1), tokens], dim=1).cpu().numpy()
+        if not hasattr(self, "_char_arr"):
+            self._char_arr = np.array([self.int_to_char[i] for i in range(len(self.int_to_char))])
+        chars = self._char_arr[np.clip(packed[:, 1:], 0, len(self._char_arr) - 1)]   # entries past out_len are unwritten
+        return ["".join(chars[b, :n]) for b, n in enumerate(packed[:, 0].tolist())]
 
     def decode(self, probs, sizes=None):
         """Returns (strings: List[B][1] str, offsets: List[B][1] IntTensor) -- decoder.py:183-198."""

@@ -161,9 +161,9 @@ class MultiStreamRecognizer:
                 return out
             if self.decoder is not None and not isinstance(self.decoder, GreedyDecoder):
                 self.full_output.append(probs)
-            decoded, _ = self.greedy_decoder.decode(probs)
+            decoded = self.greedy_decoder.decode_strings(probs)
             for s in range(self.S):
-                transcript = decoded[s][0]
+                transcript = decoded[s]
                 it = self.iterating_transcript[s]
                 # "collapsing characters hack" (DanSpeechRecognizer.py:169-174)
                 if it and transcript and it[-1] == transcript[0]:
