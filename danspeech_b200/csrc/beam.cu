@@ -8,15 +8,19 @@
 // log(p + FLT_MIN) scores, prefix_compare ordering (score desc, then smaller last symbol), OOV = -1000,
 // final partial-word scoring, reported score = -(score - len*beta - alpha*sentence_log_prob).
 //
-// Mapping: one CTA per utterance (utterances are independent; a batch of 64 occupies 64 SMs).  The live
-// beam (<= 128 prefixes) and the step's candidates (beam x C) live in shared memory; a step is
-//   log-probs -> candidate scores (one thread per (prefix, symbol), LM probes into a device hash table)
-//   -> merge children that are already in the beam -> compaction -> bitonic sort by prefix_compare
-//   -> materialise the surviving prefixes in a per-utterance node arena (parent / symbol / timestep).
+// Mapping: one CTA of 512 threads per utterance (utterances are independent; a batch of 64 occupies 64 SMs).  The
+// live beam (<= 128 prefixes), the step's candidates (beam x C) and, with a word LM, the dictionary arcs of every
+// live prefix live in shared memory; a step is
+//   log-probs -> LM score of closing the current word for NEW prefixes only (cached with the prefix; the back-off
+//   chain's table probes issued together) -> candidate scores (pass A settles the symbols the dictionary does not
+//   allow and collects the rest per warp, pass B scores them on full warps) -> merge children that are already in
+//   the beam -> dense list of valid candidates (two passes, no shared counter) -> top-W in order by rank counting
+//   (few candidates) or bitonic sort -> materialise the surviving prefixes in a per-utterance node arena.
 // The work is latency / random-access bound, reported as utterances/s and steps/s.
 #include "model_types.cuh"
 #include <float.h>
 #include <math.h>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -28,7 +32,7 @@ namespace dsb {
 constexpr int BM_MAXW = 128;       // max beam width
 constexpr int BM_MAXC = 64;        // max classes
 constexpr int BM_HIST = 4;         // max LM order - 1
-constexpr int BM_THREADS = 256;
+constexpr int BM_THREADS = 512;   // measured: 10.2 ms per batch of 64 vs 12.5 ms with 256 threads
 constexpr float BM_NEG = -FLT_MAX;
 constexpr float BM_OOV = -1000.0f;
 constexpr float BM_LOGE = 0.4342944819f;
@@ -66,35 +70,63 @@ __host__ __device__ inline void pack_key(const int* ids, int n, uint64_t& k0, ui
 }
 __host__ __device__ inline uint32_t key_hash(uint64_t k0, uint64_t k1) { return (uint32_t)mix64(k0 ^ mix64(k1 + 0x9e3779b97f4a7c15ULL)); }
 
-__device__ __forceinline__ bool lm_find(const BeamTables& T, const int* ids, int n, float& prob, float& backoff) {
-  uint64_t k0, k1;
-  pack_key(ids, n, k0, k1);
-  uint32_t h = key_hash(k0, k1) & T.lm_mask;
+// continue a lookup whose first slot `e` (at index h) has already been loaded
+__device__ __forceinline__ bool lm_resolve(const LmEntry* __restrict__ lm, uint32_t mask, LmEntry e, uint32_t h, uint64_t k0,
+                                           uint64_t k1, float& prob, float& backoff) {
   for (;;) {
-    const LmEntry e = T.lm[h];
     if (!e.used) return false;
     if (e.k0 == k0 && e.k1 == k1) {
       prob = e.prob;
       backoff = e.backoff;
       return true;
     }
-    h = (h + 1) & T.lm_mask;
+    h = (h + 1) & mask;
+    e = lm[h];
   }
 }
 
-// Scorer::get_log_cond_prob: natural-log P(words[n-1] | words[0..n-2]) with KenLM back-off; OOV anywhere -> -1000
-__device__ float lm_log_cond_prob(const BeamTables& T, const int* words, int n) {
+// Scorer::get_log_cond_prob: natural-log P(words[n-1] | words[0..n-2]) with KenLM back-off; OOV anywhere -> -1000.
+// The back-off chain needs up to 2*order-1 table lookups; their keys do not depend on each other's results, so the
+// first probe of every one is issued up front (one L2 round trip instead of one per lookup) and the chain is then
+// walked over the loaded entries.  Not inlined, and fed with scalars instead of the table struct: as an inlined
+// function taking the kernel-parameter struct by reference it forced the parameters into local memory and the whole
+// kernel to 255 registers.
+__device__ __noinline__ float lm_log_cond_prob_impl(const LmEntry* __restrict__ lm, uint32_t mask, int order, float unk_prob,
+                                                    const int* words, int n) {
   for (int i = 0; i < n; ++i)
     if (words[i] == 0) return BM_OOV;
-  int first = n > T.order ? n - T.order : 0;   // keep order-1 context words
-  float bo = 0.f;
-  for (int start = first; start < n; ++start) {
-    float pr, b;
-    if (lm_find(T, words + start, n - start, pr, b)) return (bo + pr) / BM_LOGE;
-    if (start < n - 1 && lm_find(T, words + start, n - 1 - start, pr, b)) bo += b;
+  const int first = n > order ? n - order : 0;   // keep order-1 context words
+  constexpr int MAXQ = BM_HIST + 1;
+  const int nq = n - first;
+  uint64_t fk0[MAXQ], fk1[MAXQ], ck0[MAXQ], ck1[MAXQ];
+  uint32_t fh[MAXQ], ch[MAXQ];
+  LmEntry fe[MAXQ], ce[MAXQ];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) {
+    if (q < nq) {
+      const int start = first + q;
+      pack_key(words + start, n - start, fk0[q], fk1[q]);
+      fh[q] = key_hash(fk0[q], fk1[q]) & mask;
+      fe[q] = lm[fh[q]];
+      if (start < n - 1) {
+        pack_key(words + start, n - 1 - start, ck0[q], ck1[q]);
+        ch[q] = key_hash(ck0[q], ck1[q]) & mask;
+        ce[q] = lm[ch[q]];
+      }
+    }
   }
-  return (bo + T.unk_prob) / BM_LOGE;
+  float bo = 0.f;
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) {
+    if (q < nq) {
+      float pr, b;
+      if (lm_resolve(lm, mask, fe[q], fh[q], fk0[q], fk1[q], pr, b)) return (bo + pr) / BM_LOGE;
+      if (first + q < n - 1 && lm_resolve(lm, mask, ce[q], ch[q], ck0[q], ck1[q], pr, b)) bo += b;
+    }
+  }
+  return (bo + unk_prob) / BM_LOGE;
 }
+#define lm_log_cond_prob(T, words, n) lm_log_cond_prob_impl((T).lm, (T).lm_mask, (T).order, (T).unk_prob, words, n)
 
 __device__ __forceinline__ float lse2(float x, float y) {
   if (x <= BM_NEG) return y;
@@ -112,6 +144,11 @@ struct BeamState {   // one live-beam buffer (shared memory)
   int node[BM_MAXW], parent[BM_MAXW], ch[BM_MAXW], dstate[BM_MAXW], ts[BM_MAXW];
   int hist[BM_MAXW][BM_HIST];
   float bprev[BM_MAXW], nbprev[BM_MAXW], score[BM_MAXW], lpc[BM_MAXW];
+  // word LM: alpha * log P(word | history) of closing the current word with a space, cached with the prefix (it only
+  // depends on hist / dstate, which a surviving prefix keeps); lmok = 0 not computed yet, 1 valid, -1 no dictionary arc
+  float lmsp[BM_MAXW];
+  int lmwid[BM_MAXW], lmns[BM_MAXW], lmok[BM_MAXW];
+  int rowok[BM_MAXW];   // dictionary row of this prefix's state is in the row cache
 };
 
 struct BeamSmem {
@@ -121,6 +158,7 @@ struct BeamSmem {
   float selfb[BM_MAXW], selfnb[BM_MAXW], selfscore[BM_MAXW];
   int pidx[BM_MAXW];
   int count, arena_count;
+  int wsum[BM_THREADS / 32];
   float lpb_raw;
 };
 
@@ -128,19 +166,19 @@ struct BeamParams {
   const float* probs;        // [B,T,C]
   const int32_t* seq_lens;   // [B] device
   int B, T, C, W, blank, space, cutoff_top_n;
+  int n2;                    // capacity of the sort-key array (power of two >= W*C + W)
   float cutoff_prob;
   // arena [B][max_nodes]
   int32_t* a_parent;
   int32_t* a_info;           // ch | timestep << 8
   int32_t* a_wid;            // word id completed at this node (space nodes), else -1
   int max_nodes;
-  float* cand;               // [B][W*C] child candidate scores
-  int32_t* cand_aux;         // [B][W*C][2] next dictionary state, completed word id
   int32_t* words;            // [B][W][T+2] scratch for the sentence score
   int32_t* out_tokens;
   int32_t* out_ts;
   float* out_scores;
   int32_t* out_lens;
+  long long* dbg;            // optional [12] per-phase cycle sums of utterance 0 (DSB_BEAM_DEBUG=1)
   BeamTables tab;
 };
 
@@ -149,6 +187,11 @@ beam_kernel(const BeamParams p) {
   extern __shared__ __align__(16) unsigned char bsm_raw[];
   BeamSmem& sm = *reinterpret_cast<BeamSmem*>(bsm_raw);
   uint64_t* keys = reinterpret_cast<uint64_t*>(bsm_raw + ((sizeof(BeamSmem) + 15) & ~(size_t)15));
+  float* cand = reinterpret_cast<float*>(keys + p.n2);             // [W*C] child candidate scores
+  int32_t* cand_aux = reinterpret_cast<int32_t*>(cand + p.W * p.C);   // [W*C][2] next dictionary state, completed word id
+  // word LM: the dictionary arcs trans[dstate][:] of every live prefix, carried along with the prefix (two buffers like
+  // the beam state), so that only NEW prefixes touch the table in global memory
+  int32_t* rows0 = cand_aux + 2 * p.W * p.C;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int C = p.C, W = p.W;
   const BeamTables& T = p.tab;
@@ -157,8 +200,6 @@ beam_kernel(const BeamParams p) {
   int32_t* a_parent = p.a_parent + (size_t)b * p.max_nodes;
   int32_t* a_info = p.a_info + (size_t)b * p.max_nodes;
   int32_t* a_wid = p.a_wid + (size_t)b * p.max_nodes;
-  float* cand = p.cand + (size_t)b * W * C;
-  int32_t* cand_aux = p.cand_aux + (size_t)b * W * C * 2;
 
   int cur = 0, n_active = 1;
   if (tid == 0) {
@@ -166,12 +207,18 @@ beam_kernel(const BeamParams p) {
     s.node[0] = 0; s.parent[0] = -1; s.ch[0] = -1; s.dstate[0] = 0; s.ts[0] = 0;
     for (int h = 0; h < BM_HIST; ++h) s.hist[0][h] = T.id_bos;
     s.bprev[0] = 0.f; s.nbprev[0] = BM_NEG; s.score[0] = 0.f; s.lpc[0] = BM_NEG;
+    s.lmok[0] = 0; s.rowok[0] = 0;
     a_parent[0] = -1; a_info[0] = 0xFF; a_wid[0] = -1;
     sm.arena_count = 1;
   }
   __syncthreads();
 
+  const int i_first = tid / C, c_first = tid % C, i_step = BM_THREADS / C, c_step = BM_THREADS % C;
+  long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const bool dbg = p.dbg != nullptr && b == 0 && tid == 0;
   for (int t = 0; t < len; ++t) {
+    long long c0 = dbg ? clock64() : 0;
+    auto lap = [&](int i) { if (dbg) { const long long c1 = clock64(); ph[i] += c1 - c0; c0 = c1; } };
     BeamState& S = sm.st[cur];
     BeamState& Nx = sm.st[cur ^ 1];
     const float* pr = p.probs + ((size_t)b * p.T + t) * C;
@@ -213,42 +260,115 @@ beam_kernel(const BeamParams p) {
     }
     if (tid == 0) sm.count = 0;
     __syncthreads();
+    lap(0);
     const bool full_beam = T.has_lm && n_active == W;
     const float min_cutoff = T.has_lm ? S.score[n_active - 1] + sm.lpb_raw - fmaxf(0.f, T.beta) : BM_NEG;
 
     // ---- phase 2: which live prefixes are children of other live prefixes ----
-    for (int pair = tid; pair < n_active * n_active; pair += BM_THREADS) {
-      const int k = pair / n_active, i = pair - k * n_active;
-      if (S.parent[k] == S.node[i] && k != i) sm.pidx[k] = i;
+    for (int k = tid >> 3; k < n_active; k += BM_THREADS >> 3) {   // 8 threads per prefix k scan the beam for its parent
+      const int pk = S.parent[k];
+      for (int i = tid & 7; i < n_active; i += 8)
+        if (S.node[i] == pk && i != k) sm.pidx[k] = i;
     }
+    lap(1);
+    // ---- phase 2b (word LM): the LM score of closing the current word, one thread per prefix that has not got it
+    //      cached yet (new prefixes); the dependent hash probes of all prefixes run side by side instead of inside
+    //      the (prefix, symbol) loop ----
+    const bool word_lm = T.has_lm && !T.char_based;
+    int32_t* rowsS = rows0 + cur * W * C;
+    int32_t* rowsN = rows0 + (cur ^ 1) * W * C;
+    if (word_lm) {
+      for (int idx = tid; idx < n_active * C; idx += BM_THREADS) {
+        const int k = idx / C;
+        if (S.rowok[k] == 0) rowsS[idx] = T.trans[(size_t)S.dstate[k] * C + (idx - k * C)];
+      }
+      __syncthreads();
+    }
+    lap(2);
+    if (word_lm && p.space >= 0) {
+      for (int k = tid; k < n_active; k += BM_THREADS) {
+        if (S.lmok[k] == 0) {
+          const int ns = rowsS[k * C + p.space];
+          int ok = -1;
+          if (ns >= 0) {
+            int words[BM_HIST + 1];
+            for (int h = 0; h < HN; ++h) words[h] = S.hist[k][h];
+            const int wid = T.word_at[S.dstate[k]];
+            words[HN] = wid < 0 ? 0 : wid;
+            S.lmsp[k] = lm_log_cond_prob(T, words, HN + 1) * T.alpha;
+            S.lmwid[k] = wid;
+            ok = 1;
+          }
+          S.lmns[k] = ns;
+          S.lmok[k] = ok;
+        }
+      }
+      __syncthreads();
+    }
+    lap(3);
     // ---- phase 3: candidate scores, one thread per (prefix, symbol) ----
-    for (int idx = tid; idx < n_active * C; idx += BM_THREADS) {
+    // Pass A over all (prefix, symbol) items (indices advance without a division): a symbol the dictionary does not
+    // allow after this prefix (the common case with a word LM) is settled here; the others are collected in a work
+    // list so that pass B runs its long, branchy body on full warps instead of on one or two lanes of every warp.
+    // Every warp keeps its own list (no shared counter: same-address shared-memory atomics from 16 warps serialise at
+    // ~90 cycles each and were the largest item of the step) and runs pass B over it without a block barrier.
+    const int iters = (n_active * C + BM_THREADS - 1) / BM_THREADS;
+    int* wlist = reinterpret_cast<int*>(keys) + (tid >> 5) * (32 * iters);   // the key array is free until the compaction
+    int n_work = 0;
+    {
+      const unsigned lane = tid & 31, lt = (1u << lane) - 1u;
+      int i = i_first, c = c_first;
+      const int total = n_active * C;
+      for (int base = 0; base < total; base += BM_THREADS) {
+        const int idx = base + tid;
+        bool todo = false;
+        if (idx < total) {
+          todo = c == p.blank || c == S.ch[i] || !word_lm || (c == p.space ? S.lmns[i] : rowsS[idx]) >= 0;
+          if (!todo) cand[idx] = BM_NEG;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, todo);
+        if (todo) wlist[n_work + __popc(m & lt)] = idx;
+        n_work += __popc(m);
+        i += i_step;
+        c += c_step;
+        if (c >= C) { c -= C; ++i; }
+      }
+    }
+    __syncwarp();
+    lap(10);
+    if (dbg) ph[9] += n_work;   // items left for thread 0's warp
+    for (int li = tid & 31; li < n_work; li += 32) {
+      const int idx = wlist[li];
       const int i = idx / C, c = idx - i * C;
-      const float lpc = sm.lp[c];
-      const float sc = S.score[i];
+      const int ci = S.ch[i];
+      const float lpc = sm.lp[c], sc = S.score[i];
       const bool pass = sm.allowed[c] && !(full_beam && lpc + sc < min_cutoff);
-      float v = BM_NEG;
-      int next_state = 0, wid = -1;
       if (c == p.blank) {
         if (pass) sm.selfb[i] = lpc + sc;
-      } else if (pass) {
-        if (c == S.ch[i]) sm.selfnb[i] = lpc + S.nbprev[i];   // repeated symbol without a blank
-        bool ok = true;
-        if (T.has_lm && !T.char_based) {
-          next_state = T.trans[(size_t)S.dstate[i] * C + c];
-          ok = next_state >= 0;
-        }
-        if (ok) {
+        cand[idx] = BM_NEG;
+        continue;
+      }
+      const bool word_space = word_lm && c == p.space;
+      int next_state = 0, wid = -1;
+      if (word_lm) next_state = word_space ? S.lmns[i] : rowsS[idx];
+      float v = BM_NEG;
+      if (pass) {
+        if (c == ci) sm.selfnb[i] = lpc + S.nbprev[i];   // repeated symbol without a blank
+        if (next_state >= 0) {
           float log_p = BM_NEG;
-          if (c == S.ch[i]) {
+          if (c == ci) {
             if (S.bprev[i] > BM_NEG) log_p = lpc + S.bprev[i];
           } else {
             log_p = lpc + sc;
           }
-          if (T.has_lm && (c == p.space || T.char_based)) {
+          if (word_space) {
+            wid = S.lmwid[i];
+            log_p += S.lmsp[i];
+            log_p += T.beta;
+          } else if (T.has_lm && T.char_based) {
             int words[BM_HIST + 1];
             for (int h = 0; h < HN; ++h) words[h] = S.hist[i][h];
-            wid = T.char_based ? T.char_word[c] : T.word_at[S.dstate[i]];
+            wid = T.char_word[c];
             words[HN] = wid < 0 ? 0 : wid;
             const float lm = lm_log_cond_prob(T, words, HN + 1) * T.alpha;
             log_p += lm;
@@ -258,13 +378,15 @@ beam_kernel(const BeamParams p) {
           if (!(v > BM_NEG)) v = BM_NEG;
         }
       }
-      if (c != p.blank) {
-        cand[idx] = v;
+      cand[idx] = v;
+      if (v > BM_NEG) {
         cand_aux[idx * 2 + 0] = next_state;
         cand_aux[idx * 2 + 1] = wid;
       }
     }
+    lap(11);
     __syncthreads();
+    lap(4);
     // ---- phase 3b: a child that is already in the beam absorbs its parent's extension ----
     for (int k = tid; k < n_active; k += BM_THREADS) {
       const int i = sm.pidx[k];
@@ -287,44 +409,107 @@ beam_kernel(const BeamParams p) {
       sm.selfscore[k] = lse2(sm.selfb[k], nb);
     }
     __syncthreads();
+    lap(5);
     // ---- phase 4: compaction of the valid candidates + bitonic sort by prefix_compare ----
-    for (int k = tid; k < n_active; k += BM_THREADS) {
-      if (sm.selfscore[k] > BM_NEG) {
-        const int slot = atomicAdd(&sm.count, 1);
-        keys[slot] = ((uint64_t)f2o_desc(sm.selfscore[k]) << 32) | ((uint64_t)((S.ch[k] + 1) & 0xFF) << 16) | (uint64_t)k;
-      }
-    }
-    for (int idx = tid; idx < n_active * C; idx += BM_THREADS) {
-      const int c = idx % C;
-      if (c == p.blank) continue;
-      const float v = cand[idx];
-      if (v > BM_NEG) {
-        const int slot = atomicAdd(&sm.count, 1);
-        keys[slot] = ((uint64_t)f2o_desc(v) << 32) | ((uint64_t)((c + 1) & 0xFF) << 16) | (uint64_t)(BM_MAXW + idx);
-      }
-    }
-    __syncthreads();
-    const int count = sm.count;
-    int n2 = 64;
-    while (n2 < count) n2 <<= 1;
-    for (int i = count + tid; i < n2; i += BM_THREADS) keys[i] = ~0ULL;
-    __syncthreads();
-    for (int k2 = 2; k2 <= n2; k2 <<= 1) {
-      for (int j = k2 >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < n2; i += BM_THREADS) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const uint64_t a = keys[i], bb = keys[ixj];
-            const bool up = (i & k2) == 0;
-            if ((a > bb) == up) {
-              keys[i] = bb;
-              keys[ixj] = a;
-            }
+    {
+      // Dense list of the valid candidates without a shared counter: every warp counts its own (pass 1), the 16 warp
+      // totals give each warp its first slot, pass 2 writes the keys.  q in [0, BM_MAXW): live prefixes, then the children.
+      const unsigned lane = tid & 31, lt = (1u << lane) - 1u;
+      const int total = n_active * C;
+      auto item_key = [&](int q, uint64_t& key) -> bool {
+        if (q < BM_MAXW) {
+          if (q < n_active && sm.selfscore[q] > BM_NEG) {
+            key = ((uint64_t)f2o_desc(sm.selfscore[q]) << 32) | ((uint64_t)((S.ch[q] + 1) & 0xFF) << 16) | (uint64_t)q;
+            return true;
+          }
+        } else if (q - BM_MAXW < total) {
+          const int idx = q - BM_MAXW;
+          const float v = cand[idx];
+          if (v > BM_NEG) {
+            key = ((uint64_t)f2o_desc(v) << 32) | ((uint64_t)((idx % C + 1) & 0xFF) << 16) | (uint64_t)q;
+            return true;
           }
         }
-        __syncthreads();
+        return false;
+      };
+      int mine = 0;
+      for (int base = 0; base < BM_MAXW + total; base += BM_THREADS) {
+        uint64_t key;
+        mine += __popc(__ballot_sync(0xffffffffu, item_key(base + tid, key)));
+      }
+      if (lane == 0) sm.wsum[tid >> 5] = mine;
+      __syncthreads();
+      int slot = 0, all = 0;
+      for (int w2 = 0; w2 < BM_THREADS / 32; ++w2) {
+        const int v = sm.wsum[w2];
+        if (w2 < (tid >> 5)) slot += v;
+        all += v;
+      }
+      for (int base = 0; base < BM_MAXW + total; base += BM_THREADS) {
+        uint64_t key = 0;
+        const bool valid = item_key(base + tid, key);
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid) keys[slot + __popc(m & lt)] = key;
+        slot += __popc(m);
+      }
+      if (tid == 0) sm.count = all;
+    }
+    __syncthreads();
+    lap(6);
+    const int count = sm.count;
+    if (count <= BM_THREADS / 2) {
+      // few candidates (word LM: the dictionary leaves ~200): two threads rank each key by counting the smaller ones
+      // in one half of the list each (broadcast 128-bit reads, no barrier inside); the best W land in sorted order
+      const int ki = tid >> 1, part = tid & 1;
+      const uint64_t key = ki < count ? keys[ki] : ~0ULL;
+      const int pairs = (count + 1) >> 1, half = (pairs + 1) >> 1;   // the list as ulonglong2 pairs, split in two
+      int rank = 0;
+      if (ki < count) {
+        const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(keys);
+        const int q0 = part * half, q1 = min(pairs, q0 + half);
+#pragma unroll 8
+        for (int q = q0; q < q1; ++q) {
+          const ulonglong2 v = kp[q];
+          rank += (v.x < key) + ((2 * q + 1 < count) && v.y < key);
+        }
+      }
+      rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+      __syncthreads();
+      if (part == 0 && ki < count && rank < W) keys[rank] = key;
+      __syncthreads();
+    } else if (count <= BM_THREADS) {
+      const uint64_t key = tid < count ? keys[tid] : ~0ULL;
+      int rank = 0;
+      if (tid < count) {
+#pragma unroll 16
+        for (int q = 0; q < count; ++q) rank += keys[q] < key;
+      }
+      __syncthreads();
+      if (tid < count && rank < W) keys[rank] = key;
+      __syncthreads();
+    } else {
+      int n2 = 64;
+      while (n2 < count) n2 <<= 1;
+      for (int i = count + tid; i < n2; i += BM_THREADS) keys[i] = ~0ULL;
+      __syncthreads();
+      for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < n2; i += BM_THREADS) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const uint64_t a = keys[i], bb = keys[ixj];
+              const bool up = (i & k2) == 0;
+              if ((a > bb) == up) {
+                keys[i] = bb;
+                keys[ixj] = a;
+              }
+            }
+          }
+          __syncthreads();
+        }
       }
     }
+    lap(7);
     // ---- phase 5: the new live beam ----
     const int m = min(W, count);
     for (int r = tid; r < m; r += BM_THREADS) {
@@ -336,6 +521,9 @@ beam_kernel(const BeamParams p) {
         Nx.ts[r] = S.ts[k]; Nx.lpc[r] = S.lpc[k];
         for (int h = 0; h < BM_HIST; ++h) Nx.hist[r][h] = S.hist[k][h];
         Nx.bprev[r] = sm.selfb[k]; Nx.nbprev[r] = sm.selfnb[k]; Nx.score[r] = sm.selfscore[k];
+        Nx.lmsp[r] = S.lmsp[k]; Nx.lmwid[r] = S.lmwid[k]; Nx.lmns[r] = S.lmns[k]; Nx.lmok[r] = S.lmok[k];
+        Nx.rowok[r] = 1;
+        sm.pidx[r] = k;   // (pidx is free again here) source slot of the dictionary row, copied below by all threads
       } else {                // new prefix: parent i extended by symbol c
         const int idx = code - BM_MAXW;
         const int i = idx / C, c = idx - i * C;
@@ -351,6 +539,8 @@ beam_kernel(const BeamParams p) {
           Nx.hist[r][h] = hv;
         }
         Nx.bprev[r] = BM_NEG; Nx.nbprev[r] = v; Nx.score[r] = v;
+        Nx.lmok[r] = 0; Nx.rowok[r] = 0;
+        sm.pidx[r] = -1;
         if (id < p.max_nodes) {
           a_parent[id] = S.node[i];
           a_info[id] = (c & 0xFF) | (t << 8);
@@ -359,10 +549,20 @@ beam_kernel(const BeamParams p) {
       }
     }
     __syncthreads();
+    if (word_lm) {
+      for (int idx = tid; idx < m * C; idx += BM_THREADS) {
+        const int r = idx / C, k = sm.pidx[r];
+        if (k >= 0) rowsN[idx] = rowsS[k * C + (idx - r * C)];
+      }
+      __syncthreads();
+    }
+    lap(8);
     n_active = m;
     cur ^= 1;
     if (n_active == 0) break;
   }
+  if (dbg)
+    for (int i = 0; i < 12; ++i) p.dbg[i] = ph[i];
 
   // ---- final: score the unfinished last word (word LM), order, approximate CTC score, back-trace ----
   BeamState& S = sm.st[cur];
@@ -700,7 +900,7 @@ extern "C" int64_t dsb_beam_lm_num_ngrams(const dsb_beam* d) { return d ? d->n_n
 
 namespace {
 struct BeamWs {
-  size_t o_len, o_parent, o_info, o_wid, o_cand, o_aux, o_words, total;
+  size_t o_len, o_parent, o_info, o_wid, o_words, total;
   int max_nodes;
 };
 BeamWs beam_ws(const dsb_beam* d, int B, int T) {
@@ -716,8 +916,6 @@ BeamWs beam_ws(const dsb_beam* d, int B, int T) {
   w.o_parent = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
   w.o_info = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
   w.o_wid = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
-  w.o_cand = take(sizeof(float) * (size_t)B * d->W * d->C);
-  w.o_aux = take(sizeof(int32_t) * (size_t)B * d->W * d->C * 2);
   w.o_words = take(sizeof(int32_t) * (size_t)B * d->W * (T + 2));
   w.total = off;
   return w;
@@ -754,21 +952,41 @@ extern "C" int dsb_beam_decode(dsb_beam* d, const float* probs, const int32_t* s
   p.a_info = reinterpret_cast<int32_t*>(base + w.o_info);
   p.a_wid = reinterpret_cast<int32_t*>(base + w.o_wid);
   p.max_nodes = w.max_nodes;
-  p.cand = reinterpret_cast<float*>(base + w.o_cand);
-  p.cand_aux = reinterpret_cast<int32_t*>(base + w.o_aux);
   p.words = reinterpret_cast<int32_t*>(base + w.o_words);
   p.out_tokens = out_tokens;
   p.out_ts = out_timesteps;
   p.out_scores = out_scores;
   p.out_lens = out_lens;
   p.tab = d->tab;
-  int n2 = 64;
-  while (n2 < d->W * C + d->W) n2 <<= 1;
-  const size_t smem = ((sizeof(BeamSmem) + 15) & ~(size_t)15) + sizeof(uint64_t) * n2;
+  static const bool debug = getenv("DSB_BEAM_DEBUG") != nullptr;
+  long long* dbg = nullptr;
+  if (debug) {
+    DSB_CUDA(cudaMalloc(&dbg, 12 * sizeof(long long)));
+    DSB_CUDA(cudaMemsetAsync(dbg, 0, 12 * sizeof(long long), st));
+  }
+  p.dbg = dbg;
+  int n2 = BM_THREADS;   // capacity of the key array: also holds the per-warp work lists of the candidate pass
+  while (n2 < BM_MAXW + d->W * C + BM_THREADS) n2 <<= 1;
+  p.n2 = n2;
+  const size_t smem = ((sizeof(BeamSmem) + 15) & ~(size_t)15) + sizeof(uint64_t) * n2 +
+                      (size_t)d->W * C * (sizeof(float) + 2 * sizeof(int32_t)) +
+                      ((d->tab.has_lm && !d->tab.char_based) ? 2 * (size_t)d->W * C * sizeof(int32_t) : 0);
+  if (smem > 227 * 1024)
+    return set_error(DSB_ERR_UNSUPPORTED, "dsb_beam_decode: beam width %d x %d classes needs %zu bytes of shared memory", d->W, C, smem);
   DSB_CUDA(cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DSB_CUDA(cudaMemsetAsync(out_tokens, 0, sizeof(int32_t) * (size_t)B * d->W * T, st));
   DSB_CUDA(cudaMemsetAsync(out_timesteps, 0, sizeof(int32_t) * (size_t)B * d->W * T, st));
   beam_kernel<<<B, BM_THREADS, smem, st>>>(p);
   DSB_CHECK_LAUNCH();
+  if (debug) {
+    long long h[12];
+    DSB_CUDA(cudaStreamSynchronize(st));
+    DSB_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    const double n = seq_lens[0] > 0 ? seq_lens[0] : 1;
+    fprintf(stderr, "[beam debug] utterance 0, %d steps, cycles/step: prep %.0f | pairs %.0f | rows %.0f | lm %.0f | candidates %.0f | "
+            "merge %.0f | compact %.0f | select %.0f | new beam %.0f | work items of warp 0 %.0f | candidates = pass A %.0f + pass B %.0f + barrier\n",
+            (int)n, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n);
+  }
   return 0;
 }
