@@ -214,6 +214,10 @@ beam_kernel(const BeamParams p) {
   __syncthreads();
 
   const int i_first = tid / C, c_first = tid % C, i_step = BM_THREADS / C, c_step = BM_THREADS % C;
+  // x / C for x < 2^16 by a multiply-high (exact: C <= 64); a runtime division is ~25 instructions, three of them on
+  // the quarter-rate conversion pipe, and sat in most of the per-item loops
+  const unsigned magicC = 0xFFFFFFFFu / (unsigned)C + 1u;
+  auto divC = [&](int x) -> int { return C > 1 ? (int)__umulhi((unsigned)x, magicC) : x; };
   long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const bool dbg = p.dbg != nullptr && b == 0 && tid == 0;
   for (int t = 0; t < len; ++t) {
@@ -279,7 +283,7 @@ beam_kernel(const BeamParams p) {
     int32_t* rowsN = rows0 + (cur ^ 1) * W * C;
     if (word_lm) {
       for (int idx = tid; idx < n_active * C; idx += BM_THREADS) {
-        const int k = idx / C;
+        const int k = divC(idx);
         if (S.rowok[k] == 0) rowsS[idx] = T.trans[(size_t)S.dstate[k] * C + (idx - k * C)];
       }
       __syncthreads();
@@ -339,7 +343,7 @@ beam_kernel(const BeamParams p) {
     if (dbg) ph[9] += n_work;   // items left for thread 0's warp
     for (int li = tid & 31; li < n_work; li += 32) {
       const int idx = wlist[li];
-      const int i = idx / C, c = idx - i * C;
+      const int i = divC(idx), c = idx - i * C;
       const int ci = S.ch[i];
       const float lpc = sm.lp[c], sc = S.score[i];
       const bool pass = sm.allowed[c] && !(full_beam && lpc + sc < min_cutoff);
@@ -426,7 +430,7 @@ beam_kernel(const BeamParams p) {
           const int idx = q - BM_MAXW;
           const float v = cand[idx];
           if (v > BM_NEG) {
-            key = ((uint64_t)f2o_desc(v) << 32) | ((uint64_t)((idx % C + 1) & 0xFF) << 16) | (uint64_t)q;
+            key = ((uint64_t)f2o_desc(v) << 32) | ((uint64_t)((idx - divC(idx) * C + 1) & 0xFF) << 16) | (uint64_t)q;
             return true;
           }
         }
@@ -526,7 +530,7 @@ beam_kernel(const BeamParams p) {
         sm.pidx[r] = k;   // (pidx is free again here) source slot of the dictionary row, copied below by all threads
       } else {                // new prefix: parent i extended by symbol c
         const int idx = code - BM_MAXW;
-        const int i = idx / C, c = idx - i * C;
+        const int i = divC(idx), c = idx - i * C;
         const int id = atomicAdd(&sm.arena_count, 1);
         const float v = cand[idx];
         const int wid = cand_aux[idx * 2 + 1];
@@ -551,7 +555,7 @@ beam_kernel(const BeamParams p) {
     __syncthreads();
     if (word_lm) {
       for (int idx = tid; idx < m * C; idx += BM_THREADS) {
-        const int r = idx / C, k = sm.pidx[r];
+        const int r = divC(idx), k = sm.pidx[r];
         if (k >= 0) rowsN[idx] = rowsS[k * C + (idx - r * C)];
       }
       __syncthreads();
