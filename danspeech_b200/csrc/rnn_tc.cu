@@ -8,13 +8,18 @@
 // Decomposition: a CTA owns U hidden units of ONE direction (all gates: N = 64 rows of W_hh) for
 // the whole layer.  Its W_hh slice (bf16, K padded to a multiple of 64) is loaded ONCE by TMA into
 // 128B-swizzled shared memory and stays resident for all T steps.  Per step:
-//   producer warp : waits for the direction-wide step barrier, then TMA-streams h_{t-1} (bf16,
-//                   [B, H]) through a 3-stage mbarrier ring in K-chunks of 64,
-//   MMA warp      : tcgen05.mma  D[batch(128 lanes), 64 gate columns] += h_chunk * W_chunk^T, fp32 in TMEM,
+//   producer warp : arms the ring, polls the step barrier of its CTA set (ld.acquire on a counter every CTA of
+//                   the set bumps with red.release), then TMA-streams h_{t-1} (bf16, [rows, H]) into the ring in
+//                   3-D boxes of four K-chunks of 64 (two such groups in flight),
+//   MMA warp      : tcgen05.mma  D[batch rows (M = 64 or 128), 64 gate columns] += h_chunk * W_chunk^T, fp32 in
+//                   TMEM, 16 MMAs per elected issue region,
 //   8 epilogue warps: prefetch the input-projection pre-activations of the step while the MMAs run,
 //                   tcgen05.ld the accumulators, apply the gate non-linearities with the fp32 hidden
-//                   state kept in registers, store h_t (bf16, for the next step's MMA) and y_t (fp32),
-//                   then arrive on the direction-wide barrier (one atomicAdd per CTA per step).
+//                   state kept in registers, stage h_t (bf16) in shared memory, store it coalesced for the next
+//                   step's TMA, publish (one red.release per CTA per step), then store y_t (fp32).
+// Batches above 128 rows run as groups inside the same launch (W_hh stays resident); groups can run side by side
+// on independent CTA sets ("slots") when a direction's CTAs leave SMs free, and an initial / final hidden state
+// can be carried (streaming).
 // The step is latency-bound (grid barrier + L2 round trips), not tensor-bound: algorithmic work is
 // 2*B*3H*H flop per step per direction and is reported against the tensor roof.
 //
