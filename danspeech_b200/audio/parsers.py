@@ -86,7 +86,10 @@ class SpectrogramAudioParser(AudioParser):
         stride = (max(ns) + 3) // 4 * 4
         need = len(ns) * stride
         if not hasattr(self, "_staging"):
-            self._staging = {}
+            self._staging, self._staging_busy = {}, {}
+        busy = self._staging_busy.pop(slot, None)
+        if busy is not None:
+            busy.synchronize()   # the previous host->device copy out of this buffer must have finished
         buf = self._staging.get(slot)
         if buf is None or buf.numel() < need:
             buf = torch.empty((max(need, 1),), dtype=torch.float32, pin_memory=torch.cuda.is_available())
@@ -112,6 +115,11 @@ class SpectrogramAudioParser(AudioParser):
         if not ns or min(ns) <= 0:
             raise ValueError("can't extend empty axis 0 using modes other than 'constant' or 'empty'")
         audio = host_audio.to(dev, non_blocking=True)
+        for slot, buf in getattr(self, "_staging", {}).items():
+            if buf.untyped_storage().data_ptr() == host_audio.untyped_storage().data_ptr():
+                evt = torch.cuda.Event()
+                evt.record()
+                self._staging_busy[slot] = evt   # stage_batch waits for it before it reuses the buffer
         n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
         out, _ = self.parse_device(audio, n_dev, max(ns))
         lengths = torch.IntTensor([1 + n // self.hop_length for n in ns])

@@ -509,3 +509,20 @@ def test_streaming_bf16_wide_model_uses_small_chunk_groups():
         assert a.shape == b.shape
         for s in (0, 64, 127, 128, 129):
             assert logit_rel_err(a[s].cpu().numpy(), b[s].cpu().numpy()) < BF16_TOL
+
+
+def test_back_to_back_parse_batch_does_not_reuse_a_busy_staging_buffer():
+    """parse_batch stages through a cached pinned buffer; a second call right behind the first must wait for the
+    first host->device copy instead of overwriting its source."""
+    from danspeech_b200.audio.parsers import SpectrogramAudioParser
+    p = SpectrogramAudioParser()
+    a = [syn.synthetic_audio(16000 * 20, seed=700 + i) for i in range(16)]
+    b = [syn.synthetic_audio(16000 * 20, seed=800 + i) for i in range(16)]
+    ref_a = p.parse_batch(a)[0].clone()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        sa, _ = p.parse_batch(a)
+        sb, _ = p.parse_batch(b)          # no synchronisation in between
+        torch.cuda.synchronize()
+        assert torch.equal(sa, ref_a)
+        assert not torch.equal(sb, ref_a)
