@@ -143,7 +143,11 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f,
 // exp-based form below is accurate to ~1e-6 and still a handful of instructions.
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
-template <int GATES>
+// SPLITM (GRU, batch groups of 64 rows): an M = 64 accumulator quarter only fills TMEM lanes 0-15, so lanes 16-31 of
+// every epilogue warp would idle through the MUFU-bound gate math.  Lane l+16 computes the second half of lane l's
+// hidden units on values handed over by shuffle and hands h back; loads, stores and the recurrent state stay with
+// lanes 0-15 (splitting those as well doubled the number of memory requests and was measured slower).
+template <int GATES, bool SPLITM = false>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
               const RnnTcParams p) {
@@ -408,6 +412,42 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       tmem_ld32(t_addr, r);
       tmem_ld_wait();
       tc_fence_before();
+      if constexpr (SPLITM && GATES == 3) {
+        constexpr int UL = UH / 2;
+        const int src = lane & 15;
+        const bool hi = lane >= 16;
+        const bool act2 = __shfl_sync(0xffffffffu, (int)(ok && active), src) != 0;
+        float hn[UL];
+#pragma unroll
+        for (int u = 0; u < UL; ++u) {
+          // unit u of the lower half stays, unit UL+u travels to lane+16
+          float av[3], gv[3];
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const float a_hi = __shfl_sync(0xffffffffu, __uint_as_float(r[(UL + u) * 3 + g]), src);
+            const float g_hi = __shfl_sync(0xffffffffu, gxv[g][UL + u], src);
+            av[g] = hi ? a_hi : __uint_as_float(r[u * 3 + g]);
+            gv[g] = hi ? g_hi : gxv[g][u];
+          }
+          const float h_hi = __shfl_sync(0xffffffffu, hprev[UL + u], src);
+          const float hp = hi ? h_hi : hprev[u];
+          const float bh = hi ? bhn[UL + u] : bhn[u];
+          const float rg = fast_sigmoid(gv[0] + av[0]);
+          const float zg = fast_sigmoid(gv[1] + av[1]);
+          const float ng = fast_tanh(gv[2] + rg * (av[2] + bh));
+          hn[u] = (1.0f - zg) * ng + zg * hp;
+        }
+        __nv_bfloat16* sh = sH + (size_t)(q * rpq + src) * U + half * UH + (hi ? UL : 0);
+#pragma unroll
+        for (int u = 0; u < UL; ++u) {
+          const float back = __shfl_sync(0xffffffffu, hn[u], src + 16);
+          if (act2) sh[u] = __float2bfloat16_rn(hn[u]);
+          if (ok && active) {   // lanes 0-15: the state of all UH units
+            hprev[u] = hn[u];
+            hprev[UL + u] = back;
+          }
+        }
+      } else
       if (ok && active) {
         __nv_bfloat16* sh = sH + (size_t)lrow * U + half * UH;
 #pragma unroll
@@ -691,7 +731,8 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.dirs = L.dirs; p.cpd = cpd; p.U = 2 * (32 / L.gates); p.nkc = nkc;
   p.small_groups = small_groups;
   const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates), small_groups).total;
-  const void* fn = L.gates == 3 ? (const void*)rnn_tc_kernel<3>
+  static const int split_env = getenv("DSB_RNN_SPLIT") ? atoi(getenv("DSB_RNN_SPLIT")) : 1;
+  const void* fn = L.gates == 3 ? ((BP == 64 && split_env) ? (const void*)rnn_tc_kernel<3, true> : (const void*)rnn_tc_kernel<3>)
                    : L.gates == 4 ? (const void*)rnn_tc_kernel<4> : (const void*)rnn_tc_kernel<1>;
   DSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int dirs_per_launch = L.dirs / launches;
