@@ -257,6 +257,7 @@ beam_kernel(const BeamParams p) {
       }
       sm.allowed[tid] = allowed;
     }
+#pragma unroll 1
     for (int k = tid; k < n_active; k += BM_THREADS) {
       sm.pidx[k] = -1;
       sm.selfnb[k] = BM_NEG;
@@ -282,6 +283,7 @@ beam_kernel(const BeamParams p) {
     int32_t* rowsS = rows0 + cur * W * C;
     int32_t* rowsN = rows0 + (cur ^ 1) * W * C;
     if (word_lm) {
+#pragma unroll 1
       for (int idx = tid; idx < n_active * C; idx += BM_THREADS) {
         const int k = divC(idx);
         if (S.rowok[k] == 0) rowsS[idx] = T.trans[(size_t)S.dstate[k] * C + (idx - k * C)];
@@ -290,6 +292,7 @@ beam_kernel(const BeamParams p) {
     }
     lap(2);
     if (word_lm && p.space >= 0) {
+#pragma unroll 1
       for (int k = tid; k < n_active; k += BM_THREADS) {
         if (S.lmok[k] == 0) {
           const int ns = rowsS[k * C + p.space];
@@ -323,6 +326,7 @@ beam_kernel(const BeamParams p) {
       const unsigned lane = tid & 31, lt = (1u << lane) - 1u;
       int i = i_first, c = c_first;
       const int total = n_active * C;
+#pragma unroll 1
       for (int base = 0; base < total; base += BM_THREADS) {
         const int idx = base + tid;
         bool todo = false;
@@ -340,7 +344,7 @@ beam_kernel(const BeamParams p) {
     }
     __syncwarp();
     lap(10);
-    if (dbg) ph[9] += n_work;   // items left for thread 0's warp
+#pragma unroll 1
     for (int li = tid & 31; li < n_work; li += 32) {
       const int idx = wlist[li];
       const int i = divC(idx), c = idx - i * C;
@@ -392,6 +396,7 @@ beam_kernel(const BeamParams p) {
     __syncthreads();
     lap(4);
     // ---- phase 3b: a child that is already in the beam absorbs its parent's extension ----
+#pragma unroll 1
     for (int k = tid; k < n_active; k += BM_THREADS) {
       const int i = sm.pidx[k];
       float nb = sm.selfnb[k];
@@ -437,6 +442,7 @@ beam_kernel(const BeamParams p) {
         return false;
       };
       int mine = 0;
+#pragma unroll 1
       for (int base = 0; base < BM_MAXW + total; base += BM_THREADS) {
         uint64_t key;
         mine += __popc(__ballot_sync(0xffffffffu, item_key(base + tid, key)));
@@ -449,6 +455,7 @@ beam_kernel(const BeamParams p) {
         if (w2 < (tid >> 5)) slot += v;
         all += v;
       }
+#pragma unroll 1
       for (int base = 0; base < BM_MAXW + total; base += BM_THREADS) {
         uint64_t key = 0;
         const bool valid = item_key(base + tid, key);
@@ -471,7 +478,7 @@ beam_kernel(const BeamParams p) {
       if (ki < count) {
         const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(keys);
         const int q0 = part * half, q1 = min(pairs, q0 + half);
-#pragma unroll 8
+#pragma unroll 2
         for (int q = q0; q < q1; ++q) {
           const ulonglong2 v = kp[q];
           rank += (v.x < key) + ((2 * q + 1 < count) && v.y < key);
@@ -485,7 +492,7 @@ beam_kernel(const BeamParams p) {
       const uint64_t key = tid < count ? keys[tid] : ~0ULL;
       int rank = 0;
       if (tid < count) {
-#pragma unroll 16
+#pragma unroll 4
         for (int q = 0; q < count; ++q) rank += keys[q] < key;
       }
       __syncthreads();
@@ -516,6 +523,7 @@ beam_kernel(const BeamParams p) {
     lap(7);
     // ---- phase 5: the new live beam ----
     const int m = min(W, count);
+#pragma unroll 1
     for (int r = tid; r < m; r += BM_THREADS) {
       const uint64_t key = keys[r];
       const int code = (int)(key & 0xFFFF);
@@ -554,6 +562,7 @@ beam_kernel(const BeamParams p) {
     }
     __syncthreads();
     if (word_lm) {
+#pragma unroll 1
       for (int idx = tid; idx < m * C; idx += BM_THREADS) {
         const int r = divC(idx), k = sm.pidx[r];
         if (k >= 0) rowsN[idx] = rowsS[k * C + (idx - r * C)];
