@@ -57,7 +57,7 @@ def _compare(gpu, ref, probs, lens, min_match=0.995):
     return same
 
 
-@pytest.mark.parametrize("beam", [1, 16, 64])
+@pytest.mark.parametrize("beam", [1, 16, 64, 100])
 def test_beam_without_lm_matches_oracle(beam):
     from danspeech_b200.deepspeech.decoder import BeamCTCDecoder
     rng = np.random.default_rng(10 + beam)
