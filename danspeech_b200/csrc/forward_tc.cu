@@ -210,11 +210,16 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
 
   const int Tmax = h_out_len[0];
   bool used_tc_rnn = false;
+  int dev_id = 0, dev_sms = 148;
+  cudaGetDevice(&dev_id);
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev_id);
   for (size_t l = 0; l < m->rnns.size(); ++l) {
     const RnnLayer& R = m->rnns[l];
     const bool last = l + 1 == m->rnns.size();
     const int N = R.dirs * R.gates * R.H;
-    const bool tc_rnn = R.tc_recurrence;
+    // the persistent kernel's shared-memory plan depends on the batch-group size (64 or 128 rows): wide layers that
+    // fit with 64 rows may not fit with 128, in which case this batch takes the per-step fp32 recurrence
+    const bool tc_rnn = R.tc_recurrence && rnn_tc_supported(R, B, dev_sms, nullptr, nullptr);
     prof_begin(ST_PROJ, st);
     if (int e = gemm_bias_tc(ws.xb, R.in_ld, R.w_ih_tc, R.in_ld, tc_rnn ? R.b_ih_tc : R.b_ih, ws.gates, N, (int)M, N,
                              R.in_size, st))

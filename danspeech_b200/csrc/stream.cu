@@ -285,19 +285,23 @@ extern "C" int dsb_streaming_forward(dsb_model* m, dsb_stream_state* s, const fl
     DSB_CUDA(cudaMemsetAsync(s->sync_words, 0, sizeof(unsigned int) * (kRnnSyncCounters + 1), st));
     const int next_ld = (H + 7) / 8 * 8;
     bool used_tc_rnn = false;
+    int dev_id = 0, dev_sms = 148;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev_id);
     for (size_t l = 0; l < m->rnns.size(); ++l) {
       const RnnLayer& R = m->rnns[l];
       const bool last = l + 1 == m->rnns.size();
       const int N = R.gates * R.H;
+      const bool tc_rnn = R.tc_recurrence && rnn_tc_supported(R, S, dev_sms, nullptr, nullptr);   // plan depends on the group size
       float* h_io = s->h + (int64_t)l * S * H;
       float* c_io = R.gates == 4 ? s->c + (int64_t)l * S * H : nullptr;
       prof_begin(ST_PROJ, st);
-      if (int e = gemm_bias_tc(s->xb, R.in_ld, R.w_ih_tc, R.in_ld, R.tc_recurrence ? R.b_ih_tc : R.b_ih, s->gates, N,
+      if (int e = gemm_bias_tc(s->xb, R.in_ld, R.w_ih_tc, R.in_ld, tc_rnn ? R.b_ih_tc : R.b_ih, s->gates, N,
                                T2 * S, N, R.in_size, st))
         return e;
       prof_end(ST_PROJ, st);
       prof_begin(ST_RNN, st);
-      if (R.tc_recurrence) {
+      if (tc_rnn) {
         used_tc_rnn = true;
         if (int e = rnn_layer_tc(R, s->gates, nullptr, S, T2, T2, s->ya, s->hbuf, s->sync_words, st,
                                  s->h_init ? h_io : nullptr, (s->h_init && c_io) ? c_io : nullptr, h_io, c_io))

@@ -526,3 +526,23 @@ def test_back_to_back_parse_batch_does_not_reuse_a_busy_staging_buffer():
         torch.cuda.synchronize()
         assert torch.equal(sa, ref_a)
         assert not torch.equal(sb, ref_a)
+
+
+def test_wide_layer_small_ring_and_large_batch_fallback():
+    """H = 1600: the resident W_hh slice leaves room for one group of two K chunks with 64-row groups (persistent
+    kernel, degenerate ring) and for none with 128-row groups (batch 70 -> per-step fp32 recurrence)."""
+    kw = dict(rnn_hidden_size=1600, rnn_layers=1)
+    cfg = case_config("TestModel", kw)
+    sd = syn.make_state_dict(seed=21, **cfg)
+    m = _model("TestModel", kw, seed=21, precision="bf16")
+    p = osp.SpectrogramOracle()
+    spec = p.parse_audio(syn.synthetic_audio(6000, seed=410))
+    one = spec.view(1, 1, 161, -1)
+    ref, rs = om.forward(sd, one, torch.IntTensor([one.size(3)]), cfg["conv_layers"], cfg["rnn_layers"])
+    for B in (2, 70):
+        x = one.repeat(B, 1, 1, 1)
+        probs, sizes = m(x.cuda(), torch.IntTensor([one.size(3)] * B))
+        L = int(sizes[0])
+        assert L == int(rs[0])
+        for b in (0, B - 1):
+            assert logit_rel_err(probs[b, :L].cpu().numpy(), ref[0, :L].numpy()) < BF16_TOL, (B, b)
