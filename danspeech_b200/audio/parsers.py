@@ -9,6 +9,7 @@ Differences that are deliberate and documented in INTEGRATION.md:
     immediately moves with ``.to(device)``, DanSpeechRecognizer.py:220-221);
   * ``parse_batch`` is an addition: the reference engine is batch-1 only.
 """
+import threading
 from abc import ABC, abstractmethod
 
 import numpy as np
@@ -54,6 +55,7 @@ class SpectrogramAudioParser(AudioParser):
         self.device = device
         # fp32 FFT (the bf16 model mode's 2e-2 bar) instead of the fp64 transform that matches the reference to 1e-4
         self.fast_fft = bool(fast_fft)
+        self._staging, self._staging_busy, self._staging_lock = {}, {}, threading.Lock()
 
     def _dev(self):
         N.require_cuda()
@@ -85,15 +87,15 @@ class SpectrogramAudioParser(AudioParser):
             raise ValueError("can't extend empty axis 0 using modes other than 'constant' or 'empty'")
         stride = (max(ns) + 3) // 4 * 4
         need = len(ns) * stride
-        if not hasattr(self, "_staging"):
-            self._staging, self._staging_busy = {}, {}
-        busy = self._staging_busy.pop(slot, None)
+        with self._staging_lock:   # transcribe_batches stages on a helper thread
+            busy = self._staging_busy.pop(slot, None)
+            buf = self._staging.get(slot)
         if busy is not None:
             busy.synchronize()   # the previous host->device copy out of this buffer must have finished
-        buf = self._staging.get(slot)
         if buf is None or buf.numel() < need:
             buf = torch.empty((max(need, 1),), dtype=torch.float32, pin_memory=torch.cuda.is_available())
-            self._staging[slot] = buf
+            with self._staging_lock:
+                self._staging[slot] = buf
         host = buf[:need].view(len(ns), stride)
         host_np = host.numpy()
         for i, r in enumerate(recordings):
@@ -115,11 +117,12 @@ class SpectrogramAudioParser(AudioParser):
         if not ns or min(ns) <= 0:
             raise ValueError("can't extend empty axis 0 using modes other than 'constant' or 'empty'")
         audio = host_audio.to(dev, non_blocking=True)
-        for slot, buf in getattr(self, "_staging", {}).items():
-            if buf.untyped_storage().data_ptr() == host_audio.untyped_storage().data_ptr():
-                evt = torch.cuda.Event()
-                evt.record()
-                self._staging_busy[slot] = evt   # stage_batch waits for it before it reuses the buffer
+        with self._staging_lock:
+            for slot, buf in self._staging.items():
+                if buf.untyped_storage().data_ptr() == host_audio.untyped_storage().data_ptr():
+                    evt = torch.cuda.Event()
+                    evt.record()
+                    self._staging_busy[slot] = evt   # stage_batch waits for it before it reuses the buffer
         n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
         out, _ = self.parse_device(audio, n_dev, max(ns))
         lengths = torch.IntTensor([1 + n // self.hop_length for n in ns])
