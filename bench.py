@@ -9,8 +9,9 @@ Workload (BASELINE.json configs[1]): DanSpeechPrimary-shaped bi-GRU DeepSpeech2 
 bi-GRU, random-init), batch 64 x 15 s synthetic 16 kHz audio, greedy decode.  Metric: audio-seconds
 per wall-second (RTFx).
   value : device-timed (CUDA events), audio already resident in HBM
-  e2e   : through Recognizer.recognize_batch with HOST (pinned) audio: H2D copy, kernels, D2H of the
-          token/offset tensors and transcript string building inside the timed region
+  e2e   : through Recognizer.recognize_batches with HOST (pinned) audio: every step's H2D copy, kernels, D2H of
+          the token/offset tensors and transcript string building inside the timed region (the copy of step k+1
+          runs on a side stream under the kernels of step k)
 ``--impl reference`` times the oracle's CPU restatement of the reference path (torch CPU, all host
 threads) on a bounded sample of the same workload.
 """
@@ -260,11 +261,13 @@ def run_ours(args):
     value = audio_s * args.steps / (ms_max / 1e3)
 
     # ---- end-to-end through the public API with host buffers ----
+    # every step copies its batch from pinned host memory and reads its transcripts back; Recognizer.recognize_batches
+    # runs the steps back to back with the copy of step k+1 (side stream) overlapping the kernels of step k
     texts = step_e2e()
+    rec.recognize_batches([(host, [n] * BATCH)] * 2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        texts = step_e2e()
+    texts = rec.recognize_batches([(host, [n] * BATCH)] * args.steps)[-1]
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

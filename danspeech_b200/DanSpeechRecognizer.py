@@ -190,21 +190,49 @@ class DanSpeechRecognizer(object):
         return results
 
     def transcribe_batches(self, batches, show_all=False):
-        """Several batches back to back: a helper thread converts and stages batch k+1 into pinned memory while the
-        GPU works on batch k (two staging buffers).  Returns one result list per batch."""
+        """Several batches back to back.  A helper thread converts batch k+1 into one of two cached pinned buffers and
+        starts its host->device copy on a side stream while the GPU works on batch k, so neither the float64->float32
+        conversion nor the PCIe copy sits between two batches.  A batch is a list of recordings or a
+        (pinned f32 tensor [B, stride], n_samples) tuple sorted by length descending.  Returns one result list per batch."""
         import concurrent.futures
+
+        dev = torch.device(self.device if isinstance(self.device, (str, torch.device)) else "cuda")
+        if dev.type != "cuda":
+            dev = torch.device("cuda")
+        copy_stream = torch.cuda.Stream(device=dev)
 
         def stage(k):
             recs = batches[k]
-            order = sorted(range(len(recs)), key=lambda i: -len(recs[i]))
-            host, ns = self.audio_parser.stage_batch([recs[i] for i in order], slot=k & 1)
-            return host, ns, order
+            if isinstance(recs, tuple):
+                host, ns = recs
+                ns = [int(v) for v in ns]
+                order = list(range(len(ns)))
+            else:
+                order = sorted(range(len(recs)), key=lambda i: -len(recs[i]))
+                host, ns = self.audio_parser.stage_batch([recs[i] for i in order], slot=k & 1)
+            with torch.cuda.device(dev), torch.cuda.stream(copy_stream):
+                audio = host.to(dev, non_blocking=True)
+                n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            self.audio_parser.mark_staging_busy(host, done)
+            return audio, n_dev, ns, order, done
 
         results = []
         with concurrent.futures.ThreadPoolExecutor(max_workers=1) as ex:
             nxt = ex.submit(stage, 0) if batches else None
             for k in range(len(batches)):
-                host, ns, order = nxt.result()
+                audio, n_dev, ns, order, done = nxt.result()
                 nxt = ex.submit(stage, k + 1) if k + 1 < len(batches) else None
-                results.append(self._transcribe_staged(host, ns, order, show_all))
+                torch.cuda.current_stream(dev).wait_event(done)
+                audio.record_stream(torch.cuda.current_stream(dev))
+                n_dev.record_stream(torch.cuda.current_stream(dev))
+                spect, _ = self.audio_parser.parse_device(audio, n_dev, max(ns))
+                input_sizes = torch.IntTensor([1 + n // self.audio_parser.hop_length for n in ns])
+                out, output_sizes = self.model(spect.view(len(ns), 1, 161, spect.shape[2]), input_sizes)
+                decoded_output, _ = self.decoder.decode(out, output_sizes)
+                res = [None] * len(order)
+                for pos, i in enumerate(order):
+                    res[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
+                results.append(res)
         return results

@@ -108,6 +108,14 @@ class SpectrogramAudioParser(AudioParser):
         host, ns = self.stage_batch(recordings)
         return self.parse_packed(host, ns)
 
+    def mark_staging_busy(self, host_audio, event):
+        """``event`` completes when the host->device copy out of ``host_audio`` has finished; if that tensor lives in one
+        of the staging buffers, stage_batch waits for the event before it reuses the buffer."""
+        with self._staging_lock:
+            for slot, buf in self._staging.items():
+                if buf.untyped_storage().data_ptr() == host_audio.untyped_storage().data_ptr():
+                    self._staging_busy[slot] = event
+
     def parse_packed(self, host_audio, n_samples):
         """host_audio: (pinned) CPU f32 tensor [B, stride] already sorted by length descending."""
         dev = self._dev()
@@ -117,12 +125,9 @@ class SpectrogramAudioParser(AudioParser):
         if not ns or min(ns) <= 0:
             raise ValueError("can't extend empty axis 0 using modes other than 'constant' or 'empty'")
         audio = host_audio.to(dev, non_blocking=True)
-        with self._staging_lock:
-            for slot, buf in self._staging.items():
-                if buf.untyped_storage().data_ptr() == host_audio.untyped_storage().data_ptr():
-                    evt = torch.cuda.Event()
-                    evt.record()
-                    self._staging_busy[slot] = evt   # stage_batch waits for it before it reuses the buffer
+        evt = torch.cuda.Event()
+        evt.record()
+        self.mark_staging_busy(host_audio, evt)
         n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
         out, _ = self.parse_device(audio, n_dev, max(ns))
         lengths = torch.IntTensor([1 + n // self.hop_length for n in ns])
