@@ -546,3 +546,23 @@ def test_wide_layer_small_ring_and_large_batch_fallback():
         assert L == int(rs[0])
         for b in (0, B - 1):
             assert logit_rel_err(probs[b, :L].cpu().numpy(), ref[0, :L].numpy()) < BF16_TOL, (B, b)
+
+
+@pytest.mark.parametrize("name", ["u0042008", "u0042012", "u0042017", "u0042019"])
+def test_recognize_more_example_wavs_matches_reference(name):
+    """End to end on further example WAVs of the reference: transcripts of Recognizer.recognize bit-exact in fp32 mode,
+    spectrogram rows and softmax rows within 1e-4 of what the unmodified reference produced (reference_wavs.npz)."""
+    import os
+    from danspeech_b200 import Recognizer
+    from danspeech_b200.audio.parsers import SpectrogramAudioParser
+    from danspeech_b200.pretrained_models import build_model
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_wavs.npz"))
+    a = g["wav_" + name].astype(np.float64)
+    m = build_model("TestModel", seed=0).set_precision("fp32")
+    r = Recognizer(model=m)
+    assert r.recognize(a) == str(g["text_" + name])
+    spect = SpectrogramAudioParser().parse_audio(a)
+    assert tuple(spect.shape) == tuple(g["spect_shape_" + name])
+    assert rel_err(spect[[3, 80]].cpu().numpy(), g["spect_rows_" + name]) < FP32_TOL
+    probs, sizes = m.cuda()(spect.view(1, 1, 161, -1), torch.IntTensor([spect.size(1)]))
+    assert logit_rel_err(probs[0, [0, -1]].cpu().numpy(), g["probs_ends_" + name]) < FP32_TOL

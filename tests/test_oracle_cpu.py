@@ -188,3 +188,25 @@ def test_vad_repin_against_live_reference():
     rows = gen_vad_golden.reference_yields(ov.fixture_pcm())
     ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "vad_reference.npz"))["yields"]
     assert np.array_equal(rows, ref)
+
+
+# ------------------------------------------------------------------ more real audio (tests/golden/reference_wavs.npz)
+WAV_NAMES = ("u0042008", "u0042012", "u0042017", "u0042019")
+
+
+def test_oracle_on_more_example_wavs():
+    """Oracle spectrogram + model + greedy against the unmodified reference on four further example WAVs."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_wavs.npz"))
+    cfg = case_config("TestModel", {})
+    sd = syn.make_state_dict(seed=0, **cfg)
+    p = osp.SpectrogramOracle()
+    for name in WAV_NAMES[:2]:   # two of the four keep the CPU suite short; the GPU suite checks all of them
+        a = g["wav_" + name].astype(np.float64)
+        spect = p.parse_audio(a)
+        assert tuple(spect.shape) == tuple(g["spect_shape_" + name])
+        assert rel_err(spect[[3, 80]].numpy(), g["spect_rows_" + name]) < 1e-5
+        probs, sizes = om.forward(sd, spect.view(1, 1, 161, -1), torch.IntTensor([spect.size(1)]), cfg["conv_layers"],
+                                  cfg["rnn_layers"])
+        assert rel_err(probs[0, [0, -1]].numpy(), g["probs_ends_" + name]) < 1e-5
+        text = og.greedy_decode(probs.numpy(), sizes.tolist())[0][0][0]
+        assert text == str(g["text_" + name])
