@@ -40,6 +40,7 @@ class DanSpeechRecognizer(object):
         self.beta = beta
         self.beam_width = beam_width
         self.secondary_model = None
+        self._copy_streams = {}     # device -> side stream of transcribe_batches
         if model_name:
             self.update_model(model_name)
         if lm_name:
@@ -199,7 +200,11 @@ class DanSpeechRecognizer(object):
         dev = torch.device(self.device if isinstance(self.device, (str, torch.device)) else "cuda")
         if dev.type != "cuda":
             dev = torch.device("cuda")
-        copy_stream = torch.cuda.Stream(device=dev)
+        # one side stream per recognizer and device: the caching allocator keeps a pool per stream, so a fresh stream
+        # per call would pay a cudaMalloc (a device-wide synchronisation) for the first batches of every call
+        copy_stream = self._copy_streams.get(str(dev))
+        if copy_stream is None:
+            copy_stream = self._copy_streams[str(dev)] = torch.cuda.Stream(device=dev)
 
         def stage(k):
             recs = batches[k]
