@@ -210,3 +210,28 @@ def test_oracle_on_more_example_wavs():
         assert rel_err(probs[0, [0, -1]].numpy(), g["probs_ends_" + name]) < 1e-5
         text = og.greedy_decode(probs.numpy(), sizes.tolist())[0][0][0]
         assert text == str(g["text_" + name])
+
+
+def test_stft_restatement_against_independent_implementations():
+    """librosa is absent (the STFT is "parity unpinned"), so the restatement of its documented definition -- centred
+    frames with reflect padding, scipy's symmetric Hamming window, one-sided FFT -- is cross-checked against two
+    independent implementations of the same transform: torch.stft and scipy.signal.stft (undoing scipy's window-sum
+    scaling).  Bounds the restatement error; the fixtures above pin everything the reference does around it."""
+    import scipy.signal
+    import scipy.signal.windows
+    for i, n in enumerate((161, 4000, 66944)):
+        a = syn.synthetic_audio(n, seed=300 + i)
+        D = osp.stft(a)
+        assert D.dtype == np.complex64 and D.shape == (161, 1 + n // 160)
+        w = scipy.signal.windows.hamming(320, sym=True)
+        assert np.array_equal(w, osp.hamming_sym(320)) or np.abs(w - osp.hamming_sym(320)).max() < 1e-15
+        Dt = torch.stft(torch.from_numpy(a), n_fft=320, hop_length=160, win_length=320, window=torch.from_numpy(w),
+                        center=True, pad_mode="reflect", return_complex=True).numpy()
+        assert Dt.shape == D.shape
+        assert np.abs(Dt - D).max() / np.abs(Dt).max() < 1e-6          # complex64 storage of a float64 transform
+        ap = np.pad(a, 160, mode="reflect")
+        _, _, Ds = scipy.signal.stft(ap, window=w, nperseg=320, noverlap=160, nfft=320, boundary=None, padded=False,
+                                     return_onesided=True, detrend=False)
+        Ds = Ds * w.sum()
+        assert Ds.shape == D.shape
+        assert np.abs(Ds - D).max() / np.abs(Ds).max() < 1e-6
