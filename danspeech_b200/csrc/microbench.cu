@@ -9,6 +9,18 @@ namespace tc {
 // variant bit 1: tcgen05.fence::after_thread_sync before every group
 // variant bit 2: mbarrier.try_wait on an already-completed barrier before every group
 // variant bit 3: warp-uniform control flow with elect_one_sync instead of a divergent `lane == 0` region
+// variant bit 4: (with bit 3) the A operand comes from tensor memory (TS form) instead of a shared-memory descriptor
+// D[tmem] (+)= A[tmem] * B[smem desc]: the TS form of tcgen05.mma (A: M lanes x 8 columns of packed bf16 pairs per K = 16)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 template <int M, int N>
 __global__ void __launch_bounds__(128, 1) mma_issue_bench_kernel(int n_mma, int group, int variant, long long* out) {
   extern __shared__ unsigned char smem_dyn[];
@@ -24,7 +36,7 @@ __global__ void __launch_bounds__(128, 1) mma_issue_bench_kernel(int n_mma, int 
     fence_mbar_init();
     mbar_arrive(&bars[2]);
   }
-  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -41,8 +53,13 @@ __global__ void __launch_bounds__(128, 1) mma_issue_bench_kernel(int n_mma, int 
       if (variant & 4) mbar_wait(&bars[2], 0);
       if (variant & 2) tc_fence_after();
       if (elect_one_sync()) {
-        for (int k = 0; k < group; ++k)
-          umma_bf16(tb, adesc + (uint64_t)((k & 3) * 2), bdesc + (uint64_t)((k & 3) * 2), idesc, 1);
+        if (variant & 16) {
+          for (int k = 0; k < group; ++k)
+            umma_bf16_ts(tb, tb + 256u + (uint32_t)((k & 15) * 8), bdesc + (uint64_t)((k & 3) * 2), idesc, 1);
+        } else {
+          for (int k = 0; k < group; ++k)
+            umma_bf16(tb, adesc + (uint64_t)((k & 3) * 2), bdesc + (uint64_t)((k & 3) * 2), idesc, 1);
+        }
         if (variant & 1) umma_commit(&bars[0]);
       }
       __syncwarp();
@@ -79,7 +96,7 @@ __global__ void __launch_bounds__(128, 1) mma_issue_bench_kernel(int n_mma, int 
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
