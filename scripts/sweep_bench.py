@@ -31,6 +31,7 @@ from danspeech_b200.utils import synthetic as syn  # noqa: E402
 
 N_UTT = int(os.environ.get("UTTERANCES", "256"))
 PRECISION = os.environ.get("PRECISION", "bf16")
+MAX_BATCH = int(os.environ.get("MAX_BATCH", "64"))
 rng = np.random.default_rng(1234)
 lens = rng.integers(5 * 16000, 30 * 16000, size=N_UTT)
 # every rank synthesises only what it owns (deterministic by utterance id)
@@ -41,7 +42,7 @@ audio_s_total = float(lens.sum()) / 16000.0
 
 def run(rec):
     out = {}
-    batches = sharding.make_batches(mine, lens.tolist(), max_batch=64)
+    batches = sharding.make_batches(mine, lens.tolist(), max_batch=MAX_BATCH)
     for batch, texts in zip(batches, rec.recognize_batches([[recs[i] for i in b] for b in batches])):
         for i, t in zip(batch, texts):
             out[i] = t
@@ -67,7 +68,7 @@ def timed(rec):
 
 model = build_model("DanSpeechPrimary", seed=0).set_precision(PRECISION)
 res = {"workload": "%d utterances of 5-30 s (%.0f audio-s), DanSpeechPrimary-shaped, %s mode, LPT shards over %d GPU(s), "
-                   "batches <= 64" % (N_UTT, audio_s_total, PRECISION, world), "n_gpus": world}
+                   "batches <= %d" % (N_UTT, audio_s_total, PRECISION, world, MAX_BATCH), "n_gpus": world}
 rec = Recognizer(model=model)
 dt, texts = timed(rec)
 res["greedy"] = {"seconds": dt, "rtfx": audio_s_total / dt, "utt_per_s": N_UTT / dt, "transcripts": len(texts)}
