@@ -127,6 +127,17 @@ def model_flops(B, Tp, conv_layers=3, layers=9, H=1200):
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_rtfx(n_utts, reps, warmup, threads=None):
     """Oracle CPU restatement of the reference path (spectrogram -> DeepSpeech.forward -> greedy)."""
     from danspeech_b200.utils import synthetic as syn
@@ -172,7 +183,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 1)), "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "reference_step": "%d of the 64 utterances per step" % nb},
-        "cpu_baseline": {"value": rtfx, "unit": "audio-s/s", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": rtfx, "unit": "audio-s/s", "cores": threads, "kind": "port", "cpu_model": cpu_model_name(),
                          "sample": "%d x 15 s utterances per step (oracle restatement of parsers.py:50-72 + "
                                    "model.py:496-515 + decoder.py:183-198 on torch CPU fp32)" % nb},
         "e2e": {"value": rtfx, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -343,7 +354,7 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline:
         v, sec, threads = cpu_reference_rtfx(args.cpu_sample, 2, 1)
-        cpu = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
+        cpu = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port", "cpu_model": cpu_model_name(),
                "sample": "%d x 15 s utterance(s) per repetition, 1 warm-up + 2 timed, oracle CPU restatement "
                          "(torch CPU fp32, %d threads)" % (args.cpu_sample, threads)}
 
