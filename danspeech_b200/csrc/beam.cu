@@ -238,7 +238,6 @@ beam_kernel(const BeamParams p) {
           const float q = pr[c2];
           rank += (q > pv) || (q == pv && c2 < tid);
         }
-        int cutoff_len = C;
         if (p.cutoff_prob < 1.0f) {
           // upstream accumulates log_sum_exp(cum, log p) from cum = 0.0 and stops at cum >= cutoff_prob
           // (i.e. log(1 + sum p) >= cutoff_prob); reproduce on the sorted order
@@ -251,7 +250,6 @@ beam_kernel(const BeamParams p) {
           // cum after rank r-1 = log(1 + sum_{rank<r}) < cutoff
           const double prev = sum_before - (double)pv;
           allowed = (rank == 0) || (log(1.0 + prev) < (double)p.cutoff_prob);
-          (void)cutoff_len;
         }
         if (rank >= p.cutoff_top_n) allowed = 0;
       }

@@ -135,7 +135,6 @@ TcWorkspace carve_tc(const dsb_model* m, int B, int T, void* base) {
     if (i % 2 == 0) cb1 = max(cb1, e); else cb0 = max(cb0, e);
   }
   const int ld = max((m->rnn_input + 7) / 8 * 8, (H + 7) / 8 * 8);
-  const int HP = (H + 63) / 64 * 64;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
