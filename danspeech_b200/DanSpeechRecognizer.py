@@ -13,6 +13,7 @@ from . import _native as N
 from .audio.parsers import InferenceSpectrogramAudioParser, SpectrogramAudioParser
 from .deepspeech.decoder import BeamCTCDecoder, GreedyDecoder
 from .errors.recognizer_errors import ModelNotInitialized
+from .utils.stitch import stitch_transcript
 
 
 class NoLmInstantiatedWarning(Warning):
@@ -60,33 +61,27 @@ class DanSpeechRecognizer(object):
         self.update_decoder(labels=self.labels)
 
     def update_decoder(self, lm=None, alpha=None, beta=None, labels=None, beam_width=None):
-        """Same update rules as DanSpeechRecognizer.py:58-95."""
-        update = False
-        if not self.lm and not self.decoder:
-            update = True
+        """Update rules of DanSpeechRecognizer.py:58-95: a falsy argument means "keep"; the decoder is rebuilt only when
+        one of lm / alpha / beta / labels / beam_width really changes, or when there is none yet (then lm = "greedy")."""
+        rebuild = not self.lm and not self.decoder
+        if rebuild:
             self.lm = "greedy"
-        if lm and self.lm != lm:
-            update = True
-            self.lm = lm
-        if alpha and self.alpha != alpha:
-            update = True
-            self.alpha = alpha
-        if beta and self.beta != beta:
-            update = True
-            self.beta = beta
-        if labels and labels != self.labels:
-            update = True
-            self.labels = labels
-        if beam_width and beam_width != self.beam_width:
-            update = True
-            self.beam_width = beam_width
-        if update:
-            if self.lm != "greedy":
-                self.decoder = BeamCTCDecoder(labels=self.labels, lm_path=self.lm, alpha=self.alpha, beta=self.beta,
-                                              beam_width=self.beam_width, num_processes=6, cutoff_prob=1.0,
-                                              cutoff_top_n=40, blank_index=self.labels.index("_"))
-            else:
-                self.decoder = GreedyDecoder(labels=self.labels, blank_index=self.labels.index("_"))
+        for field, value in (("lm", lm), ("alpha", alpha), ("beta", beta), ("labels", labels),
+                             ("beam_width", beam_width)):
+            if value and getattr(self, field) != value:
+                setattr(self, field, value)
+                rebuild = True
+        if rebuild:
+            self.decoder = self._make_decoder()
+
+    def _make_decoder(self):
+        blank = self.labels.index("_")
+        if self.lm == "greedy":
+            return GreedyDecoder(labels=self.labels, blank_index=blank)
+        # constructor arguments as DanSpeechRecognizer.py:89-92
+        return BeamCTCDecoder(labels=self.labels, lm_path=self.lm, alpha=self.alpha, beta=self.beta,
+                              beam_width=self.beam_width, num_processes=6, cutoff_prob=1.0, cutoff_top_n=40,
+                              blank_index=blank)
 
     # ------------------------------------------------------------------ streaming (DanSpeechRecognizer.py:98-216)
     def enable_streaming(self, secondary_model=None, return_string_parts=True):
@@ -116,47 +111,37 @@ class DanSpeechRecognizer(object):
         self.spectrograms = []
 
     def streaming_transcribe(self, recording, is_last, is_first):
-        recording = self.audio_parser.parse_audio(recording, is_last)
+        """One chunk of one stream (DanSpeechRecognizer.py:144-216): returns the new string part (or the iterating
+        transcript when string parts are off), "" for the first chunk, and on the last chunk the final transcript --
+        re-decoded by the secondary model or the LM decoder when there is one."""
+        spect = self.audio_parser.parse_audio(recording, is_last)
         out = ""
-        if len(recording) != 0:
+        if len(spect) != 0:
             if self.secondary_model:
-                self.spectrograms.append(recording)
-            recording = recording.view(1, 1, recording.size(0), recording.size(1))
-            out = self.model(recording, is_first, is_last)
+                self.spectrograms.append(spect)
+            probs = self.model(spect.view(1, 1, spect.size(0), spect.size(1)), is_first, is_last)
             if is_first:
                 return ""
-            self.full_output.append(out)
-            decoded_out, _ = self.greedy_decoder.decode(out)
-            transcript = decoded_out[0][0]
-            # "collapsing characters hack" (DanSpeechRecognizer.py:169-174)
-            if self.iterating_transcript and transcript and self.iterating_transcript[-1] == transcript[0]:
-                self.iterating_transcript = self.iterating_transcript + transcript[1:]
-                transcript = transcript[1:]
-            else:
-                self.iterating_transcript += transcript
-            out = transcript if self.string_parts else self.iterating_transcript
+            self.full_output.append(probs)
+            decoded, _ = self.greedy_decoder.decode(probs)
+            self.iterating_transcript, part = stitch_transcript(self.iterating_transcript, decoded[0][0])
+            out = part if self.string_parts else self.iterating_transcript
+        return self._finish_stream() if is_last else out
 
-        if is_last:
-            if len(self.iterating_transcript) > 1:
-                if self.secondary_model:
-                    final = torch.cat(self.spectrograms, dim=1)
-                    self.spectrograms = []
-                    final = final.view(1, 1, final.size(0), final.size(1))
-                    input_sizes = torch.IntTensor([final.size(3)]).int()
-                    out, _ = self.secondary_model(final, input_sizes)
-                    decoded_out, _ = self.decoder.decode(out)
-                    self.reset_streaming_params()
-                    return decoded_out[0][0]
-                if self.lm != "greedy":
-                    final_out = torch.cat(self.full_output, dim=1)
-                    decoded_out, _ = self.decoder.decode(final_out)
-                    self.reset_streaming_params()
-                    return decoded_out[0][0]
-                out = self.iterating_transcript
-                self.reset_streaming_params()
-                return out
-            return ""
-        return out
+    def _finish_stream(self):
+        heard = len(self.iterating_transcript) > 1
+        final = ""
+        if heard and self.secondary_model:
+            full = torch.cat(self.spectrograms, dim=1)
+            probs, _ = self.secondary_model(full.view(1, 1, full.size(0), full.size(1)), torch.IntTensor([full.size(1)]))
+            final = self.decoder.decode(probs)[0][0][0]
+        elif heard and self.lm != "greedy":
+            final = self.decoder.decode(torch.cat(self.full_output, dim=1))[0][0][0]
+        elif heard:
+            final = self.iterating_transcript
+        if heard:
+            self.reset_streaming_params()
+        return final
 
     # ------------------------------------------------------------------ offline (DanSpeechRecognizer.py:218-231)
     def transcribe(self, recording, show_all=False):

@@ -1,13 +1,21 @@
-"""Exception types raised on the model path (names kept from danspeech/errors/model_errors.py:1-10)."""
+"""Exception types of the model path.  The names are part of the drop-in surface (the reference keeps them in
+danspeech/errors/model_errors.py); they share the ``ModelError`` base, an addition."""
 
 
-class ConvError(Exception):
-    """Unsupported number of convolutional layers (reference: deepspeech/model.py:344-348)."""
+class ModelError(Exception):
+    """Base of the model-path exceptions."""
 
 
-class ModelDoesNotExistError(Exception):
-    pass
+class ConvError(ModelError):
+    """conv_layers outside 1..3 (raised where the reference raises it: deepspeech/model.py:344-348)."""
 
 
-class FreezingMoreLayersThanExist(Exception):
-    pass
+class FreezingMoreLayersThanExist(ModelError):
+    """Kept for name compatibility: a training-side error, never raised on the inference path."""
+
+
+class ModelDoesNotExistError(ModelError):
+    """A pretrained-model name that `get_model_from_string` does not know."""
+
+
+__all__ = ["ModelError", "ConvError", "FreezingMoreLayersThanExist", "ModelDoesNotExistError"]

@@ -20,6 +20,7 @@ import torch
 
 from . import _native as N
 from .deepspeech.decoder import GreedyDecoder
+from .utils.stitch import stitch_transcript
 
 SILENCE, PHRASE_START, SPEECH, PHRASE_END, PHRASE_DROPPED = 0, 1, 2, 3, 4
 
@@ -163,15 +164,9 @@ class MultiStreamRecognizer:
                 self.full_output.append(probs)
             decoded = self.greedy_decoder.decode_strings(probs)
             for s in range(self.S):
-                transcript = decoded[s]
-                it = self.iterating_transcript[s]
-                # "collapsing characters hack" (DanSpeechRecognizer.py:169-174)
-                if it and transcript and it[-1] == transcript[0]:
-                    it, transcript = it + transcript[1:], transcript[1:]
-                else:
-                    it = it + transcript
+                it, part = stitch_transcript(self.iterating_transcript[s], decoded[s])
                 self.iterating_transcript[s] = it
-                out[s] = transcript if self.string_parts else it
+                out[s] = part if self.string_parts else it
         if is_last:
             heard = [len(it) > 1 for it in self.iterating_transcript]
             final = list(self.iterating_transcript)

@@ -143,3 +143,94 @@ def test_sharded_transcription_world_size_2_gloo():
     single = sharding.transcribe_sharded(lambda b: ["len%d" % len(a) for a in b],
                                          [np.zeros(int(n)) for n in np.random.default_rng(1).integers(100, 3000, size=37)])
     assert single == expect                               # shard invariance: same answer for world size 1
+
+
+def test_stitch_transcript_is_the_reference_rule():
+    """utils.stitch against the inline rule of DanSpeechRecognizer.py:169-174 on exhaustive small cases."""
+    import itertools
+    from danspeech_b200.utils.stitch import stitch_transcript
+
+    def inline(it, transcript):
+        if it and transcript and it[-1] == transcript[0]:
+            it = it + transcript[1:]
+            transcript = transcript[1:]
+        else:
+            it += transcript
+        return it, transcript
+
+    words = ["".join(w) for n in range(0, 4) for w in itertools.product("ab ", repeat=n)]
+    for it in words:
+        for t in words:
+            assert stitch_transcript(it, t) == inline(it, t)
+
+
+def test_update_decoder_rules_without_a_gpu():
+    """DanSpeechRecognizer.update_decoder (reference DanSpeechRecognizer.py:58-95): falsy arguments keep the field, a
+    decoder is built when there is none (lm becomes "greedy") and rebuilt only on a real change."""
+    from danspeech_b200.DanSpeechRecognizer import DanSpeechRecognizer
+    r = object.__new__(DanSpeechRecognizer)
+    r.lm, r.decoder, r.alpha, r.beta, r.beam_width, r.labels = None, None, 1.3, 0.2, 64, ["_", "a", " "]
+    built = []
+    r._make_decoder = lambda: built.append((r.lm, r.alpha, r.beta, r.beam_width, tuple(r.labels))) or len(built)
+    r.update_decoder(labels=r.labels)                       # first call: greedy decoder
+    assert r.lm == "greedy" and built == [("greedy", 1.3, 0.2, 64, ("_", "a", " "))]
+    r.update_decoder(labels=r.labels)                       # nothing changes -> no rebuild
+    r.update_decoder(alpha=1.3, beta=0.2, beam_width=64)
+    r.update_decoder(alpha=0, beta=None, lm="")             # falsy = keep
+    assert len(built) == 1
+    r.update_decoder(lm="/x/lm.arpa", alpha=1.5)
+    assert r.lm == "/x/lm.arpa" and r.alpha == 1.5 and len(built) == 2
+    r.update_decoder(lm="/x/lm.arpa", beam_width=32)
+    assert r.beam_width == 32 and len(built) == 3 and r.decoder == 3
+    r.update_decoder(labels=["_", "b", " "])
+    assert r.labels == ["_", "b", " "] and len(built) == 4
+
+
+def test_streaming_transcribe_control_flow_without_a_gpu():
+    """DanSpeechRecognizer.streaming_transcribe (reference :144-216) with stub parser / model / decoders: first chunk
+    returns "", parts are stitched, an empty last part still finishes, nothing heard returns "" and keeps the state."""
+    import torch
+    from danspeech_b200.DanSpeechRecognizer import DanSpeechRecognizer
+
+    class Dec:
+        def __init__(self, texts):
+            self.texts = list(texts)
+
+        def decode(self, probs, sizes=None):
+            return [[self.texts.pop(0)]], None
+
+    def engine(texts, secondary=None, lm="greedy", final=None, string_parts=True):
+        r = object.__new__(DanSpeechRecognizer)
+        r.secondary_model, r.lm, r.string_parts = secondary, lm, string_parts
+        r.iterating_transcript, r.full_output, r.spectrograms = "", [], []
+        r.audio_parser = type("P", (), {"parse_audio": staticmethod(lambda rec, last: rec)})()
+        r.model = lambda x, first, last: torch.zeros(1, x.size(3), 3)
+        r.greedy_decoder = Dec(texts)
+        r.decoder = Dec([final]) if final is not None else r.greedy_decoder
+        return r
+
+    sp = torch.zeros(161, 4)
+    r = engine(["ab", "bc", "cd"])
+    assert r.streaming_transcribe(sp, False, True) == ""
+    assert r.streaming_transcribe(sp, False, False) == "ab"
+    assert r.streaming_transcribe(sp, False, False) == "c"          # "bc" loses its first character
+    assert r.streaming_transcribe(sp, True, False) == "abcd"        # last: the whole stitched transcript
+    assert r.iterating_transcript == "" and r.full_output == []
+    r = engine(["ab", "b"], string_parts=False)
+    r.streaming_transcribe(sp, False, True)
+    assert r.streaming_transcribe(sp, False, False) == "ab"
+    assert r.streaming_transcribe([], True, False) == "ab"          # empty last part (parser returned [])
+    r = engine(["a"])
+    r.streaming_transcribe(sp, False, True)
+    assert r.streaming_transcribe(sp, True, False) == ""            # one character: "nothing heard"
+    assert r.iterating_transcript == "a"                            # and, as in the reference, no reset
+    r = engine(["ab", "c"], lm="/x/lm.arpa", final="ab c")
+    r.streaming_transcribe(sp, False, True)
+    r.streaming_transcribe(sp, False, False)
+    assert r.streaming_transcribe(sp, True, False) == "ab c"        # LM decoder over the concatenated outputs
+    sec = lambda x, sizes: (torch.zeros(1, int(sizes[0]), 3), sizes)
+    r = engine(["ab", "c"], secondary=sec, final="abc!")
+    r.streaming_transcribe(sp, False, True)
+    r.streaming_transcribe(sp, False, False)
+    assert len(r.spectrograms) == 2
+    assert r.streaming_transcribe(sp, True, False) == "abc!" and r.spectrograms == []
