@@ -234,3 +234,47 @@ def test_streaming_transcribe_control_flow_without_a_gpu():
     r.streaming_transcribe(sp, False, False)
     assert len(r.spectrograms) == 2
     assert r.streaming_transcribe(sp, True, False) == "abc!" and r.spectrograms == []
+
+
+def test_multistream_push_control_flow_without_a_gpu():
+    """MultiStreamRecognizer.push with stub parser / model / decoders: per stream it must behave like
+    DanSpeechRecognizer.streaming_transcribe (first chunk "", stitched parts, final transcript or "" when nothing was
+    heard; one batched secondary pass at the end)."""
+    import torch
+    from danspeech_b200.streaming import MultiStreamRecognizer
+
+    class Greedy:
+        def __init__(self, per_chunk):
+            self.per_chunk = list(per_chunk)
+
+        def decode_strings(self, probs):
+            return self.per_chunk.pop(0)
+
+        def decode(self, probs, sizes=None):
+            return [[t] for t in self.final], None
+
+    def engine(per_chunk, S, secondary=None, string_parts=True):
+        e = object.__new__(MultiStreamRecognizer)
+        e.S, e.string_parts, e.secondary_model, e.decoder = S, string_parts, secondary, None
+        e.greedy_decoder = Greedy(per_chunk)
+        e.audio_parser = type("P", (), {"parse_audio": staticmethod(lambda parts, last: parts)})()
+        e.model = lambda x, first, last: torch.zeros(S, x.size(3), 3)
+        e.reset_streaming_params()
+        return e
+
+    sp = torch.zeros(3, 161, 4)
+    e = engine([["ab", "", "x"], ["bc", "q", ""]], S=3)
+    assert e.push(sp, True, False) == ["", "", ""]
+    assert e.push(sp, False, False) == ["ab", "", "x"]
+    assert e.push(sp, False, True) == ["abc", "", ""]            # stream 1: one character, stream 2: "x" -> nothing heard
+    assert e.iterating_transcript == ["", "", ""]
+    e = engine([["ab", "cd"], ["b", "d"]], S=2, string_parts=False)
+    e.push(sp[:2], True, False)
+    assert e.push(sp[:2], False, False) == ["ab", "cd"]
+    assert e.push(None, False, True) == ["ab", "cd"]             # parser had nothing for the last part
+    sec = lambda x, sizes: (torch.zeros(2, int(sizes[0]), 3), sizes)
+    e = engine([["ab", "c"]], S=2, secondary=sec)
+    e.greedy_decoder.final = ["AB!", "ignored"]
+    e.push(sp[:2], True, False)
+    assert e.push(sp[:2], False, True) == ["AB!", ""]            # secondary pass for all, "" where nothing was heard
+    assert e.spectrograms == []
