@@ -3,7 +3,8 @@
 
 Contract: ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line (rank 0).  Under
 torchrun (N > 1) every rank processes its own batch of 64 utterances (utterance sharding, no
-collective on the data path; "scaling": "weak").
+collective on the data path; "scaling": "weak"); without a launcher environment, ``--gpus N`` with N > 1
+starts the N ranks itself the same way (``torch.distributed.run``, rendezvous on 127.0.0.1).
 
 Workload (BASELINE.json configs[1]): DanSpeechPrimary-shaped bi-GRU DeepSpeech2 (3 conv + 9 x 1200
 bi-GRU, random-init), batch 64 x 15 s synthetic 16 kHz audio, greedy decode.  Metric: audio-seconds
@@ -376,8 +377,22 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def relaunch_under_torchrun(args):
+    """`python bench.py --gpus N` with N > 1 and no launcher environment: start the N ranks ourselves, the way the
+    driver does (one process per GPU, rendezvous on 127.0.0.1)."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    os.execv(sys.executable, cmd)
+
+
 def main():
     args = parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        relaunch_under_torchrun(args)
     if args.impl == "reference":
         run_reference(args)
     else:
