@@ -78,3 +78,19 @@ def test_kenlm_binary_is_recognised_and_refused(lib, tmp_path):
     rc = lib.dsb_beam_create(labels, len(syn.LABELS), str(p).encode(), 1.3, 0.2, 40, 1.0, 64, 0, 0, ctypes.byref(h))
     msg = lib.dsb_last_error().decode()
     assert rc != 0 and "KenLM binary" in msg and "trie" in msg and "order 3" in msg and "12345 unigrams" in msg
+
+
+def test_public_header_is_plain_c_and_cxx(tmp_path):
+    """include/danspeech_b200.h is what a foreign-function binding reads: it must compile on its own as C99 and as
+    C++11 (no torch / CUDA types in the signatures)."""
+    import shutil
+    import subprocess
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    src = tmp_path / "t.c"
+    src.write_text('#include "danspeech_b200.h"\nint main(void) { return 0; }\n')
+    if shutil.which("gcc"):
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                       check=True)
+    if shutil.which("g++"):
+        subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)],
+                       check=True)
