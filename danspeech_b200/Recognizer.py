@@ -1,19 +1,22 @@
 """User-facing Recognizer (API shell of danspeech/Recognizer.py: __init__ :39-80, recognize :82-95,
-update_model :97-107, update_decoder :109-130, enable_real_time_streaming :499-533).
+update_model :97-107, update_decoder :109-130, enable_real_time_streaming :499-533,
+disable_real_time_streaming :535-558).
 
-The microphone / VAD / background-thread loops of the reference (Recognizer.py:133-497, :560-715) are
-host-side I/O pacing and out of scope; ``recognize`` and the streaming
-entry points they would call are all here.
+The listening API of the reference -- energy VAD over a stream source, background capture and the ``streaming`` /
+``real_time_streaming`` generators (Recognizer.py:133-497, :560-818) -- is host logic and lives in
+``listening.PhraseListener``, which this class mixes in; only live microphone capture (PyAudio) is outside the
+package's environment.
 """
 from .DanSpeechRecognizer import DanSpeechRecognizer
 from .errors.recognizer_errors import ModelNotInitialized
+from .listening import PhraseListener
 
 
-class Recognizer(object):
+class Recognizer(PhraseListener):
 
     def __init__(self, model=None, lm=None, with_gpu=True, **kwargs):
+        self._init_listening()
         self.danspeech_recognizer = DanSpeechRecognizer(with_gpu=with_gpu, **kwargs)
-        self.stream = False
         if model:
             self.update_model(model)
         if lm:
@@ -48,8 +51,14 @@ class Recognizer(object):
         self.stream = True
 
     def disable_real_time_streaming(self, keep_secondary_model_loaded=False):
-        self.danspeech_recognizer.disable_streaming(keep_secondary_model=keep_secondary_model_loaded)
+        if not self.stream:
+            print("No stream is running for the Recognizer")
+            return
+        print("Stopping microphone stream...")
         self.stream = False
+        if self.stream_thread_stopper is not None:     # no capture thread when chunks were pushed by hand
+            self.stream_thread_stopper(wait_for_stop=False)
+        self.danspeech_recognizer.disable_streaming(keep_secondary_model=keep_secondary_model_loaded)
 
     def streaming_transcribe(self, chunk, is_last, is_first):
         """One chunk of the real-time path (what Recognizer.real_time_streaming feeds, Recognizer.py:560-715)."""

@@ -278,3 +278,48 @@ def test_multistream_push_control_flow_without_a_gpu():
     e.push(sp[:2], True, False)
     assert e.push(sp[:2], False, True) == ["AB!", ""]            # secondary pass for all, "" where nothing was heard
     assert e.spectrograms == []
+
+
+def test_recognizer_shell_wires_the_listening_api(monkeypatch):
+    """Recognizer = PhraseListener + engine calls; with a stub engine the whole shell runs without a GPU."""
+    import importlib
+    R = importlib.import_module("danspeech_b200.Recognizer")   # the package attribute of that name is the class
+
+    class Engine:
+        def __init__(self, with_gpu=True, **kw):
+            self.kw, self.log = kw, []
+
+        def update_model(self, m):
+            self.log.append(("model", m.model_name))
+
+        def update_decoder(self, **kw):
+            self.log.append(("decoder", kw))
+
+        def enable_streaming(self, secondary, parts):
+            self.log.append(("enable", secondary, parts))
+
+        def disable_streaming(self, keep_secondary_model=False):
+            self.log.append(("disable", keep_secondary_model))
+
+        def transcribe(self, audio, show_all=False):
+            return "text:%d" % len(audio)
+
+    monkeypatch.setattr(R, "DanSpeechRecognizer", Engine)
+    model = type("M", (), {"model_name": "stub"})()
+    r = R.Recognizer(model=model, alpha=1.0)
+    assert r.danspeech_recognizer.kw == {"alpha": 1.0} and r.danspeech_recognizer.log == [("model", "stub")]
+    assert (r.energy_threshold, r.pause_threshold, r.phrase_threshold, r.non_speaking_duration) == (1000, 0.8, 0.3, 0.35)
+    assert r.stream is False and r.stream_thread_stopper is None and r.microphone is None
+    assert r.recognize([0.0] * 5) == "text:5"
+    r.disable_real_time_streaming()                        # nothing running: a message, no engine call
+    assert r.danspeech_recognizer.log == [("model", "stub")]
+    r.enable_real_time_streaming(model, secondary_model=None, string_parts=False)
+    assert r.stream is True and r.danspeech_recognizer.log[-1] == ("enable", None, False)
+    r.disable_real_time_streaming(keep_secondary_model_loaded=True)   # chunks were pushed by hand: no capture thread
+    assert r.stream is False and r.danspeech_recognizer.log[-1] == ("disable", True)
+    with pytest.raises(R.ModelNotInitialized):
+        R.Recognizer(lm="x.arpa")
+    for name in ("listen", "listen_stream", "listen_in_background", "get_audio_data", "streaming", "real_time_streaming",
+                 "enable_streaming", "disable_streaming", "adjust_for_speech", "adjust_for_ambient_noise",
+                 "update_stream_parameters"):
+        assert callable(getattr(r, name))
