@@ -56,6 +56,30 @@ class GreedyDecoder(Decoder):
     def __init__(self, labels, blank_index=0):
         super().__init__(labels, blank_index)
 
+    # ---- host-side helpers of the reference's interface, for callers that already hold index sequences
+    def process_string(self, sequence, size, remove_repetitions=False):
+        """Index sequence -> (string, IntTensor of the frame of every emitted character): blanks are dropped and,
+        with ``remove_repetitions``, a symbol equal to the previous FRAME's symbol (decoder.py:166-181)."""
+        ids = sequence.detach().cpu().numpy() if torch.is_tensor(sequence) else np.asarray(sequence)
+        ids = ids.reshape(-1)[:int(size)].astype(np.int64)
+        keep = ids != self.blank_index
+        if remove_repetitions and ids.size > 1:
+            keep[1:] &= ids[1:] != ids[:-1]
+        frames = np.nonzero(keep)[0]
+        text = "".join(self.int_to_char[i] for i in ids[frames].tolist())
+        return text, torch.from_numpy(frames.astype(np.int32))
+
+    def convert_to_strings(self, sequences, sizes=None, remove_repetitions=False, return_offsets=False):
+        """Batch form of ``process_string``: List[B] of [string] (one path), plus List[B] of [offsets] on request
+        (decoder.py:151-164)."""
+        strings, offsets = [], []
+        for b in range(len(sequences)):
+            n = sizes[b] if sizes is not None else len(sequences[b])
+            text, frames = self.process_string(sequences[b], n, remove_repetitions)
+            strings.append([text])
+            offsets.append([frames])
+        return (strings, offsets) if return_offsets else strings
+
     def decode_device(self, probs, sizes=None):
         """Returns device tensors (tokens[B,T], offsets[B,T], out_len[B]) without synchronising."""
         N.require_cuda()

@@ -323,3 +323,46 @@ def test_recognizer_shell_wires_the_listening_api(monkeypatch):
                  "enable_streaming", "disable_streaming", "adjust_for_speech", "adjust_for_ambient_noise",
                  "update_stream_parameters"):
         assert callable(getattr(r, name))
+
+
+def test_greedy_host_helpers_match_the_reference_and_the_oracle():
+    """GreedyDecoder.process_string / convert_to_strings (decoder.py:151-181) on index sequences."""
+    from danspeech_b200.deepspeech.decoder import GreedyDecoder
+    from oracle import greedy as og, refharness
+    labels = list("_abcdefghijklmnopqrstuvwxyzæøåéü ")
+    d = GreedyDecoder(labels, blank_index=0)
+    rng = np.random.default_rng(0)
+    seqs = torch.from_numpy(rng.integers(0, 6, size=(5, 40))).int()
+    seqs[seqs == 5] = labels.index(" ")
+    sizes = torch.IntTensor([40, 33, 1, 0, 17])
+    got = d.convert_to_strings(seqs, sizes, remove_repetitions=True, return_offsets=True)
+    onehot = np.eye(len(labels), dtype=np.float32)[seqs.numpy()]
+    want_s, want_o = og.greedy_decode(onehot, sizes.tolist(), labels="".join(labels))
+    assert [g[0] for g in got[0]] == [w[0] for w in want_s]
+    assert all(np.array_equal(g[0].numpy(), np.asarray(w[0])) for g, w in zip(got[1], want_o))
+    assert d.convert_to_strings(seqs[:2]) == d.convert_to_strings(seqs[:2], [40, 40])
+    assert d.process_string(torch.tensor([1, 1, 0, 1, 2, 2]), 6)[0] == "aaabb"
+    assert d.process_string(torch.tensor([1, 1, 0, 1, 2, 2]), 6, remove_repetitions=True)[0] == "aab"
+    if refharness.reference_available():
+        refharness.import_reference()
+        from danspeech.deepspeech.decoder import GreedyDecoder as RefGreedy
+        r = RefGreedy(labels, blank_index=0)
+        for rep in (False, True):
+            a = d.convert_to_strings(seqs, sizes, remove_repetitions=rep, return_offsets=True)
+            b = r.convert_to_strings(seqs, sizes, remove_repetitions=rep, return_offsets=True)
+            assert a[0] == b[0]
+            assert all(torch.equal(x[0], y[0]) and x[0].dtype == y[0].dtype for x, y in zip(a[1], b[1]))
+
+
+def test_language_model_factories_return_cached_paths_and_never_download(tmp_path):
+    from danspeech_b200 import language_models as lm
+    assert lm.CustomLanguageModel("/x/y.arpa") == "/x/y.arpa"
+    with pytest.raises(FileNotFoundError, match="does not download"):
+        lm.DSL3gram(cache_dir=str(tmp_path))
+    (tmp_path / "dsl_3gram.klm").write_bytes(b"x")
+    assert lm.DSL3gram(cache_dir=str(tmp_path)) == str(tmp_path / "dsl_3gram.klm")
+    (tmp_path / "dsl_3gram.arpa").write_text("\\data\\\n")
+    assert lm.DSL3gram(cache_dir=str(tmp_path)) == str(tmp_path / "dsl_3gram.arpa")     # the readable form wins
+    assert set(lm.__all__) >= {"DSL5gram", "DSLWiki3gram", "DSLWiki5gram", "DSLWikiLeipzig3gram", "Wiki3gram", "Wiki5gram",
+                               "Folketinget3gram", "DSL3gramWithNames"}
+    assert lm.Wiki5gram.__name__ == "Wiki5gram"
