@@ -174,6 +174,29 @@ class AudioData(object):
                                       "models require)")
         return self.frame_data
 
+    def get_segment(self, start_ms=None, end_ms=None):
+        """The samples between two times (milliseconds; None = the respective end) as a new AudioData."""
+        if start_ms is not None and start_ms < 0:
+            raise AssertionError("start_ms must not be negative")
+        if end_ms is not None and end_ms < (start_ms or 0):
+            raise AssertionError("end_ms must not lie before start_ms")
+        to_byte = lambda ms: int((ms * self.sample_rate * self.sample_width) // 1000)   # noqa: E731
+        lo = 0 if start_ms is None else to_byte(start_ms)
+        hi = len(self.frame_data) if end_ms is None else to_byte(end_ms)
+        return AudioData(self.frame_data[lo:hi], self.sample_rate, self.sample_width)
+
+    def get_wav_data(self, convert_rate=None, convert_width=None):
+        """The audio as the bytes of a mono PCM WAV file."""
+        import io
+        raw = self.get_raw_data(convert_rate, convert_width)
+        with io.BytesIO() as buf:
+            with wave.open(buf, "wb") as w:
+                w.setnchannels(1)
+                w.setsampwidth(self.sample_width)
+                w.setframerate(self.sample_rate)
+                w.writeframes(raw)
+            return buf.getvalue()
+
     def get_array_data(self, convert_rate=None, convert_width=None):
         """float64 array at raw integer sample scale -- what ``Recognizer.recognize`` takes."""
         raw = self.get_raw_data(convert_rate, convert_width)

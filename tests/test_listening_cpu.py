@@ -172,6 +172,12 @@ def test_threshold_adjustment_and_array_conversion_equal_the_live_reference():
         raw = rng.integers(0, 255, 64 * width, dtype=np.uint8).tobytes()
         assert np.array_equal(AudioData(raw, 16000, width).get_array_data(), RefAudioData(raw, 16000, width).get_array_data())
         np.frombuffer(raw, dtype=dt)
+    mine, ref = AudioData(pcm[:5000].tobytes(), 16000, 2), RefAudioData(pcm[:5000].tobytes(), 16000, 2)
+    assert mine.get_wav_data() == ref.get_wav_data()
+    for lo, hi in ((None, None), (10, None), (None, 100), (12.5, 250), (0, 0)):
+        assert mine.get_segment(lo, hi).frame_data == ref.get_segment(lo, hi).frame_data
+    with pytest.raises(AssertionError):
+        mine.get_segment(50, 10)
     frames = [pcm[:1024].tobytes(), pcm[1024:1500].tobytes()]
     src = make_source(pcm)
     assert np.array_equal(PhraseListener.get_audio_data(frames, src), reference_listener().get_audio_data(frames, src))
