@@ -235,3 +235,33 @@ def test_stft_restatement_against_independent_implementations():
         Ds = Ds * w.sum()
         assert Ds.shape == D.shape
         assert np.abs(Ds - D).max() / np.abs(Ds).max() < 1e-6
+
+
+@pytest.mark.skipif(not refharness.reference_available(), reason="reference tree only exists in the build container")
+def test_oracle_equals_live_reference_recognize_on_all_13_example_wavs():
+    """end-to-end ``Recognizer.recognize`` of the UNMODIFIED reference on every WAV of its
+    example_files against the oracle pipeline (spectrogram -> model -> greedy), and this package's loader against the
+    reference's ``load_audio`` (stereo s16 -> clip(L+R))."""
+    import glob
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import gen_golden
+    ref = refharness.import_reference()
+    from danspeech import Recognizer
+    from danspeech.audio.resources import load_audio as ref_load_audio
+    from danspeech_b200.audio.resources import load_audio
+    wavs = sorted(glob.glob(os.path.join(refharness.REFERENCE_ROOT, "example_files", "*.wav")))
+    assert len(wavs) == 13
+    cfg = case_config("TestModel", {})
+    sd = syn.make_state_dict(seed=0, **cfg)
+    p = osp.SpectrogramOracle()
+    with torch.no_grad():
+        r = Recognizer(model=gen_golden.ref_model(ref, "TestModel", seed=0))
+        for path in wavs:
+            a = ref_load_audio(path)
+            assert np.array_equal(load_audio(path), a)
+            spect = p.parse_audio(a)
+            probs, sizes = om.forward(sd, spect.view(1, 1, 161, -1), torch.IntTensor([spect.size(1)]), cfg["conv_layers"],
+                                      cfg["rnn_layers"])
+            text = og.greedy_decode(probs.numpy(), sizes.tolist())[0][0][0]
+            assert text == r.recognize(a), os.path.basename(path)
+            assert len(text) > 0
