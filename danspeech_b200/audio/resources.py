@@ -125,13 +125,26 @@ class Microphone(SpeechSource):
     without it fails loudly.  With PyAudio present it opens a 16-bit mono input stream with the reference's defaults
     (danspeech/audio/resources.py:385-423)."""
 
-    def __init__(self, device_index=None, sampling_rate=16000, chunk_size=1024):
+    @staticmethod
+    def _pyaudio_module():
         try:
             import pyaudio
         except ImportError as e:
             raise ImportError("danspeech_b200.audio.Microphone needs the PyAudio package (not installed); "
                               "use ArraySource / SpeechFile, or push chunks into streaming.MultiStreamRecognizer") from e
-        self._pyaudio = pyaudio
+        return pyaudio
+
+    @staticmethod
+    def list_microphone_names():
+        """Names of the audio devices, indexed as ``device_index`` expects them."""
+        audio = Microphone._pyaudio_module().PyAudio()
+        try:
+            return [audio.get_device_info_by_index(i).get("name") for i in range(audio.get_device_count())]
+        finally:
+            audio.terminate()
+
+    def __init__(self, device_index=None, sampling_rate=16000, chunk_size=1024):
+        self._pyaudio = self._pyaudio_module()
         self.device_index, self.sampling_rate, self.chunk, self.sampling_width = device_index, sampling_rate, chunk_size, 2
         self.stream = self._audio = None
 
