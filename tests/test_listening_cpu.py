@@ -275,3 +275,103 @@ def test_real_time_streaming_feeds_the_model_in_lookahead_sized_passes():
     captured = np.frombuffer(b"".join(blob for _, blob, _ in rows), "<i2").astype(float)
     fed = np.concatenate([c[3] for c in calls])
     assert np.array_equal(fed, captured[:len(fed)])
+
+
+def _scripted_run(make, script, context=20, empty=NoDataInBuffer):
+    """Drives a ``real_time_streaming`` generator with a scripted capture queue (no threads, no sleeping): every
+    ``get_data`` call consumes one script entry -- None = queue empty, (is_last, n) = n samples.  When the script is
+    used up the stream flag drops, which ends the generator after the consumer has handled what it holds."""
+    obj = make()
+    obj.stream = True
+    eng = FakeEngine(context=context)
+    obj.danspeech_recognizer = eng
+    todo = list(script)
+    counter = [0]
+
+    def get_data():
+        if not todo:
+            obj.stream = False
+            raise empty
+        item = todo.pop(0)
+        if item is None:
+            raise empty
+        is_last, n = item
+        counter[0] += 1
+        return is_last, np.full(n, float(counter[0]))
+
+    obj.listen_in_background = lambda source: (lambda wait_for_stop=True: None, get_data)
+    source = type("S", (), {"sampling_rate": 16000, "chunk": 1024, "sampling_width": 2})()
+    yields = [(bool(last), text) for last, text in obj.real_time_streaming(source)]
+    calls = [(n, last, first, float(a.sum())) for n, last, first, a in eng.calls]
+    return yields, calls
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree only exists in the build container")
+def test_real_time_streaming_equals_the_live_reference_on_scripted_queues(monkeypatch):
+    """Differential test of the consumer state machine (Recognizer.py:560-715): same scripted queue, same fake
+    engine -> the same ``streaming_transcribe`` calls (sizes, flags, content) and the same yields, including the
+    reference's quirk that a phrase ending before its first pass stays queued in front of the next one."""
+    refharness.import_reference()
+    import importlib
+    ref_module = importlib.import_module("danspeech.Recognizer")     # (the package attribute of that name is the class)
+    from danspeech.errors.recognizer_errors import NoDataInBuffer as RefNoData
+    mine_module = importlib.import_module("danspeech_b200.listening")
+    monkeypatch.setattr(ref_module.time, "sleep", lambda s: None)     # the same `time` module object: both are patched
+    assert mine_module.time.sleep(0) is None
+
+    make_ref = reference_listener
+
+    rng = np.random.default_rng(42)
+    n_checked = 0
+    for trial in range(300):
+        script = []
+        for _ in range(int(rng.integers(3, 40))):
+            u = rng.random()
+            if u < 0.35:
+                script.append(None)
+            else:
+                script.append((bool(rng.random() < 0.15), int(rng.integers(0, 9)) * 1024))
+        script.append((bool(rng.random() < 0.5), 1024))                # end on data: the reference's poll loop only
+        want = _scripted_run(make_ref, script, empty=RefNoData)        # leaves on data-then-empty or a phrase end
+        got = _scripted_run(listener, script)
+        assert got == want, (trial, script)
+        n_checked += 1
+    assert n_checked == 300
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree only exists in the build container")
+def test_streaming_generator_equals_the_live_reference_on_scripted_queues(monkeypatch):
+    """``streaming`` (Recognizer.py:433-497): phrases are collected up to their last part and recognised when longer
+    than ``mininum_required_speaking_seconds``; same scripted queue -> same clips in the same order."""
+    import importlib
+    refharness.import_reference()
+    ref_module = importlib.import_module("danspeech.Recognizer")
+    from danspeech.errors.recognizer_errors import NoDataInBuffer as RefNoData
+    monkeypatch.setattr(ref_module.time, "sleep", lambda s: None)
+
+    def run(make, script, empty):
+        obj = make()
+        obj.stream = True
+        obj.recognize = lambda clip: (len(clip), float(np.sum(clip)))
+        todo, counter = list(script), [0]
+
+        def get_data():
+            item = todo.pop(0)
+            if not todo:
+                obj.stream = False            # the script ends on a phrase end: the generator finishes after it
+            if item is None:
+                raise empty
+            counter[0] += 1
+            return item[0], np.full(item[1], float(counter[0]))
+
+        obj.listen_in_background = lambda source: (lambda wait_for_stop=True: None, get_data)
+        source = type("S", (), {"sampling_rate": 16000, "chunk": 1024, "sampling_width": 2})()
+        return list(obj.streaming(source))
+
+    rng = np.random.default_rng(7)
+    for trial in range(200):
+        script = []
+        for _ in range(int(rng.integers(1, 30))):
+            script.append(None if rng.random() < 0.3 else (bool(rng.random() < 0.25), int(rng.integers(0, 8)) * 1024))
+        script.append((True, int(rng.integers(0, 16)) * 1024))
+        assert run(listener, script, NoDataInBuffer) == run(reference_listener, script, RefNoData), (trial, script)
