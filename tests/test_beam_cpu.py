@@ -127,3 +127,25 @@ def test_empty_and_short_inputs():
     out, scores, ts, lens = d.decode(probs, [0, 1])
     assert lens[0, 0] == 0 and scores[0, 0] == pytest.approx(0.0)      # only the empty prefix, log p = 0
     assert lens[1].max() <= 1
+
+
+def test_beam_scores_are_ctc_likelihoods_by_torch_ctc_loss():
+    """Independent check of the prefix bookkeeping (blank / non-blank masses, repeat handling) on sequences too long
+    for brute force: without an LM the score of a hypothesis is -log P(string | probs) summed over all alignments,
+    which torch.nn.functional.ctc_loss computes by the forward algorithm."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(11)
+    labels = "_abc"
+    for T in (9, 14, 20):
+        probs = rng.dirichlet(np.ones(4) * 0.6, size=T).astype(np.float32)
+        d = CTCBeamDecoderOracle(labels, None, 0, 0, 40, 1.0, 1024, 1, 0)
+        out, scores, _, lens = d.decode(probs[None])
+        logp = torch.log(torch.from_numpy(probs.astype(np.float64))).unsqueeze(1)       # [T, 1, C]
+        assert np.all(np.diff(scores[0][:50]) >= -1e-6)                                  # best first (scores = -log p)
+        for rank in ((0, 1, 2, 5, 17) if T <= 14 else (0, 1, 2)):    # deep ranks of long inputs lose pruned mass
+            n = int(lens[0, rank])
+            target = torch.from_numpy(out[0, rank, :n].astype(np.int64)).unsqueeze(0)
+            nll = F.ctc_loss(logp, target, torch.tensor([T]), torch.tensor([n]), blank=0, reduction="sum",
+                             zero_infinity=False)
+            assert float(scores[0, rank]) == pytest.approx(float(nll), rel=2e-3, abs=2e-3), (T, rank)
