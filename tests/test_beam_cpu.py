@@ -149,3 +149,58 @@ def test_beam_scores_are_ctc_likelihoods_by_torch_ctc_loss():
             nll = F.ctc_loss(logp, target, torch.tensor([T]), torch.tensor([n]), blank=0, reduction="sum",
                              zero_infinity=False)
             assert float(scores[0, rank]) == pytest.approx(float(nll), rel=2e-3, abs=2e-3), (T, rank)
+
+
+def _read_arpa(path):
+    """Minimal independent ARPA reader: {n-gram tuple: (log10 prob, log10 back-off)}, order."""
+    grams, order, n = {}, 0, 0
+    with open(path, encoding="utf-8") as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if line.endswith("-grams:") and line.startswith("\\"):
+                n = int(line[1:line.index("-")])
+                order = max(order, n)
+            elif n and line and not line.startswith("\\"):
+                cols = line.split("\t")
+                words = tuple(cols[1].split(" "))
+                assert len(words) == n
+                grams[words] = (float(cols[0]), float(cols[2]) if len(cols) > 2 else 0.0)
+    return grams, order
+
+
+def _backoff_log10(grams, order, words):
+    """Textbook back-off: p(w | ctx) = p(ctx w) if listed, else backoff(ctx) + p(w | ctx minus its first word)."""
+    ctx, w = list(words[:-1])[-(order - 1):], words[-1]
+    total = 0.0
+    while True:
+        hit = grams.get(tuple(ctx) + (w,))
+        if hit is not None:
+            return total + hit[0]
+        assert ctx, "unigrams list every word"
+        total += grams.get(tuple(ctx), (0.0, 0.0))[1]
+        ctx = ctx[1:]
+
+
+def test_lm_scores_equal_an_independent_backoff_implementation(tmp_path):
+    """oracle/ctc_beam.cpp's ARPA scorer against a 15-line textbook back-off over the same synthetic 3-gram file, on
+    random in-vocabulary word windows (hits at every order and every back-off depth) and on out-of-vocabulary words."""
+    arpa = syn.write_synthetic_arpa(str(tmp_path / "w.arpa"), n_words=300, seed=4)
+    grams, order = _read_arpa(arpa)
+    assert order == 3
+    d = CTCBeamDecoderOracle(syn.LABELS, arpa, 1.0, 0.0, 40, 1.0, 8, 1, 0)
+    vocab = [w[0] for w in grams if len(w) == 1 and w[0] not in ("<s>", "</s>", "<unk>")]
+    tri = [w for w in grams if len(w) == 3]
+    bi = [w for w in grams if len(w) == 2]
+    rng = np.random.default_rng(0)
+    windows = [list(t) for t in tri[:100]] + [list(b) for b in bi[:100]]
+    windows += [["<s>"] + list(b) for b in bi[:50]] + [list(t[:2]) + [vocab[int(rng.integers(len(vocab)))]] for t in tri[:100]]
+    for _ in range(400):
+        k = int(rng.integers(1, 5))
+        windows.append([vocab[int(rng.integers(len(vocab)))] for _ in range(k)])
+    depths = set()
+    for wds in windows:
+        want = _backoff_log10(grams, order, wds) / 0.4342944819
+        assert d.lm_cond_log_prob(wds) == pytest.approx(want, rel=1e-5, abs=1e-6), wds
+        depths.add(sum(1 for n in range(min(len(wds), order), 0, -1) if tuple(wds[-n:]) in grams))
+    assert len(depths) >= 3                                   # trigram hits, bigram hits and unigram fall-backs all occurred
+    assert d.lm_cond_log_prob([vocab[0], "qqqqqq"]) == -1000.0 and d.lm_cond_log_prob(["qqqqqq", vocab[0]]) == -1000.0
