@@ -366,3 +366,53 @@ def test_language_model_factories_return_cached_paths_and_never_download(tmp_pat
     assert set(lm.__all__) >= {"DSL5gram", "DSLWiki3gram", "DSLWiki5gram", "DSLWikiLeipzig3gram", "Wiki3gram", "Wiki5gram",
                                "Folketinget3gram", "DSL3gramWithNames"}
     assert lm.Wiki5gram.__name__ == "Wiki5gram"
+
+
+def test_public_api_surface_covers_the_reference():
+    """Drop-in check by introspection of the imported reference: every public name of the classes on the path exists
+    here, with the same parameter names in the same order (defaults may differ only where INTEGRATION.md says so)."""
+    import importlib
+    import inspect
+    from oracle import refharness
+    if not refharness.reference_available():
+        pytest.skip("reference tree only exists in the build container")
+    refharness.import_reference()
+    allowed_missing = {"DeepSpeech": {"freeze_layers", "streaming_init"},                     # training / module-internal
+                       "SpeechFile": {"SpeechFileStream"}, "Microphone": {"MicrophoneStream"}}  # nested helper classes
+    classes = [("Recognizer", "Recognizer"), ("DanSpeechRecognizer", "DanSpeechRecognizer"),
+               ("deepspeech.model", "DeepSpeech"), ("deepspeech.decoder", "Decoder"),
+               ("deepspeech.decoder", "GreedyDecoder"), ("deepspeech.decoder", "BeamCTCDecoder"),
+               ("audio.parsers", "AudioParser"), ("audio.parsers", "SpectrogramAudioParser"),
+               ("audio.parsers", "InferenceSpectrogramAudioParser"), ("audio.resources", "AudioData"),
+               ("audio.resources", "SpeechFile"), ("audio.resources", "Microphone")]
+    module_base = {n for n, _ in inspect.getmembers(torch.nn.Module)}
+    for mod, cls in classes:
+        R = getattr(importlib.import_module("danspeech." + mod), cls)
+        M = getattr(importlib.import_module("danspeech_b200." + mod), cls)
+        names = {n for n, _ in inspect.getmembers(R) if not n.startswith("_")}
+        if issubclass(R, torch.nn.Module):
+            names -= module_base
+        missing = {n for n in names if not hasattr(M, n)} - allowed_missing.get(cls, set())
+        assert not missing, (cls, sorted(missing))
+        for n in sorted(names | {"__init__"}):
+            a, b = getattr(R, n, None), getattr(M, n, None)
+            if b is None or not callable(a) or inspect.isclass(a):
+                continue
+            pa = [p for p in inspect.signature(a).parameters.values()]
+            pb = [p for p in inspect.signature(b).parameters.values()]
+            if any(p.kind in (p.VAR_POSITIONAL, p.VAR_KEYWORD) for p in pb[:2 + 1]) and n in ("load_state_dict",):
+                continue
+            assert [p.name for p in pa] == [p.name for p in pb][:len(pa)], (cls, n)
+    for mod, names in (("pretrained_models", ["DanSpeechPrimary", "TestModel", "Baseline", "CPUStreamingRNN", "GPUStreamingRNN",
+                                              "Folketinget", "TransferLearned", "EnglishLibrispeech", "CustomModel",
+                                              "get_model_from_string"]),
+                       ("language_models", ["DSL3gram", "DSL5gram", "DSLWiki3gram", "DSLWiki5gram", "DSLWikiLeipzig3gram",
+                                            "Wiki3gram", "Wiki5gram", "Folketinget3gram", "DSL3gramWithNames",
+                                            "CustomLanguageModel"]),
+                       ("audio", ["load_audio", "load_audio_wavPCM", "Microphone", "SpectrogramAudioParser",
+                                  "InferenceSpectrogramAudioParser"])):
+        R, M = importlib.import_module("danspeech." + mod), importlib.import_module("danspeech_b200." + mod)
+        for n in names:
+            assert hasattr(R, n) and hasattr(M, n), (mod, n)
+            pa, pb = list(inspect.signature(getattr(R, n)).parameters), list(inspect.signature(getattr(M, n)).parameters)
+            assert pa == pb[:len(pa)], (mod, n, pa, pb)
