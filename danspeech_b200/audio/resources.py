@@ -79,6 +79,10 @@ class _BytesStream(object):
                 time.sleep(self._due - now)
         return out
 
+    def tell(self):
+        """Samples handed out so far."""
+        return self._pos // self._width
+
     def close(self):
         self._pos = len(self._data)
 

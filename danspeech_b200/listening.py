@@ -105,6 +105,11 @@ class PhraseListener(object):
     def listen(self, source, timeout=None, phrase_time_limit=None):
         """Blocks until one phrase has been heard and returns it as ``AudioData`` (with up to
         ``non_speaking_duration`` of quiet on both sides)."""
+        kept, _ = self._listen_buffers(source, timeout, phrase_time_limit)
+        return AudioData(b"".join(kept), source.sampling_rate, source.sampling_width)
+
+    def _listen_buffers(self, source, timeout=None, phrase_time_limit=None):
+        """The loop of ``listen``: (buffers of the phrase, number of trailing quiet buffers read but not kept)."""
         _check_source(source, "listening")
         spb, pause_n, phrase_n, keep_n = self._buffer_counts(source)
         clock = 0.0
@@ -142,9 +147,10 @@ class PhraseListener(object):
                     break
             if heard - quiet >= phrase_n or not len(chunk):
                 break                                     # long enough, or the stream ended
-        for _ in range(quiet - keep_n):                   # trailing quiet beyond what is kept
+        dropped = max(0, quiet - keep_n)                  # trailing quiet beyond what is kept
+        for _ in range(dropped):
             kept.pop()
-        return AudioData(b"".join(kept), source.sampling_rate, source.sampling_width)
+        return kept, dropped
 
     # ------------------------------------------------------------------ one phrase, buffer by buffer
     def listen_stream(self, source, timeout=None, phrase_time_limit=None):
@@ -192,6 +198,41 @@ class PhraseListener(object):
         yield True, (chunk if len(chunk) else [])
         raise WrongUsageOfListen("Wrong usage of stream. Overwrite the listen generator with a new generator instance"
                                  "since this instance has completed a full listen.")
+
+    # ------------------------------------------------------------------ long recordings (an addition)
+    def segment_audio(self, samples, sampling_rate=16000, chunk_size=1024, phrase_time_limit=None):
+        """Phrases of an in-memory recording as ``[(first_sample, end_sample)]``, found by the same ``listen`` loop a
+        live source goes through (including its drifting energy threshold).  The reference's long-audio example
+        (example_scripts/video_transcribe_simulation.py:93-143) re-implements this loop around ``recognize``."""
+        from .audio.resources import ArraySource
+        spans = []
+        with ArraySource(samples, sampling_rate=sampling_rate, chunk_size=chunk_size) as src:
+            total = len(np.asarray(samples))
+            while src.stream.tell() < total:
+                kept, dropped = self._listen_buffers(src, phrase_time_limit=phrase_time_limit)
+                n = sum(len(b) for b in kept) // src.sampling_width
+                end = min(src.stream.tell(), total) - dropped * src.chunk
+                if n and self._is_phrase(kept, src):
+                    spans.append((end - n, end))
+        return spans
+
+    def _is_phrase(self, kept, source):
+        """``listen`` also returns when the source ends; such a tail counts only if it holds speech."""
+        return any(pcm_rms(b, source.sampling_width) > self.energy_threshold for b in kept)
+
+    def recognize_long(self, samples, sampling_rate=16000, max_batch=64, phrase_time_limit=None, show_all=False):
+        """Long recording -> ``[(start_seconds, end_seconds, transcript)]``: segmented by ``segment_audio`` and then
+        recognised as length-sorted batches (``recognize_batches``) instead of one utterance at a time."""
+        a = np.asarray(samples)
+        spans = self.segment_audio(a, sampling_rate=sampling_rate, phrase_time_limit=phrase_time_limit)
+        order = sorted(range(len(spans)), key=lambda i: spans[i][0] - spans[i][1])          # longest first
+        batches = [order[i:i + max_batch] for i in range(0, len(order), max_batch)]
+        texts = [None] * len(spans)
+        clips = [[a[spans[i][0]:spans[i][1]].astype(float) for i in batch] for batch in batches]
+        for batch, out in zip(batches, self.recognize_batches(clips, show_all=show_all) if clips else []):
+            for i, t in zip(batch, out):
+                texts[i] = t
+        return [(lo / float(sampling_rate), hi / float(sampling_rate), t) for (lo, hi), t in zip(spans, texts)]
 
     @staticmethod
     def get_audio_data(frames, source):

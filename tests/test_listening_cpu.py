@@ -375,3 +375,32 @@ def test_streaming_generator_equals_the_live_reference_on_scripted_queues(monkey
             script.append(None if rng.random() < 0.3 else (bool(rng.random() < 0.25), int(rng.integers(0, 8)) * 1024))
         script.append((True, int(rng.integers(0, 16)) * 1024))
         assert run(listener, script, NoDataInBuffer) == run(reference_listener, script, RefNoData), (trial, script)
+
+
+def test_segment_audio_and_recognize_long_batch_the_phrases_of_a_recording():
+    pcm = ov.fixture_pcm()
+    lst = listener(dynamic_energy_threshold=False)
+    spans = lst.segment_audio(pcm)
+    # the same phrases `listen` returns from a live source, located in the recording
+    ref, src = listener(dynamic_energy_threshold=False), make_source(pcm, short_tail=True)
+    want = []
+    while src.pos < len(pcm):
+        want.append(np.frombuffer(ref.listen(src).frame_data, "<i2"))
+    want = [w for w in want if len(w) and np.sqrt(np.mean(w.astype(float) ** 2)) > 300]
+    assert len(spans) == 2 and all(0 <= lo < hi <= len(pcm) for lo, hi in spans) and spans[0][1] <= spans[1][0]
+    assert all(np.array_equal(pcm[lo:hi], w) for (lo, hi), w in zip(spans, want[:2]))
+    # speech of the fixture: buffers 20-45 (with a short internal pause) and 100-130; pre-roll and tail are kept
+    assert spans[0][0] <= 20 * 1024 and spans[0][1] >= 45 * 1024 and spans[1][0] <= 100 * 1024 and spans[1][1] >= 130 * 1024
+
+    batches_seen = []
+
+    def recognize_batches(batches, show_all=False):
+        batches_seen.append([[len(c) for c in b] for b in batches])
+        return [["clip of %d" % len(c) for c in b] for b in batches]
+
+    lst.recognize_batches = recognize_batches
+    out = lst.recognize_long(pcm, max_batch=1)
+    assert [(round(a * 16000), round(b * 16000)) for a, b, _ in out] == spans
+    assert [t for _, _, t in out] == ["clip of %d" % (hi - lo) for lo, hi in spans]
+    assert batches_seen == [[[max(hi - lo for lo, hi in spans)], [min(hi - lo for lo, hi in spans)]]]   # longest first
+    assert lst.recognize_long(np.zeros(40 * 1024, np.int16)) == []
