@@ -6,7 +6,6 @@ unchanged.  The torch modules below are *containers for parameters only*: ``forw
 them -- it hands raw device pointers to dsb_forward / dsb_streaming_forward (C ABI), which run the
 hand-written sm_100a kernels.  There is no CPU or eager-PyTorch fallback.
 """
-import json
 import os
 from collections import OrderedDict
 
@@ -41,8 +40,10 @@ def _wrap(name, module):
 
 
 def _default_labels():
-    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "labels.json"), "r", encoding="utf-8") as f:
-        return str("".join(json.load(f)))
+    """The default symbol inventory of the reference models (its deepspeech/labels.json, read at model.py:321-323):
+    CTC blank, a-z, the Danish letters and two accented ones, space.  Index = column of the fc output."""
+    import string
+    return "_" + string.ascii_lowercase + "\u00e6\u00f8\u00e5\u00e9\u00fc" + " "
 
 
 class DeepSpeech(nn.Module):
