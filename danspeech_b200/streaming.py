@@ -15,7 +15,6 @@ need N recognisers.  Here the same per-stream behaviour runs for S lock-step str
 import ctypes
 import math
 
-import numpy as np
 import torch
 
 from . import _native as N

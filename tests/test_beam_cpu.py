@@ -1,7 +1,6 @@
 """CPU: known-answer tests of the beam-search oracle (C++ restatement of ctcdecode, parity unpinned)."""
 import itertools
 import math
-import os
 
 import numpy as np
 import pytest

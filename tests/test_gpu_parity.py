@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import BATCH_CASES, BATCH_LENS, batch_inputs, case_config, logit_rel_err, rel_err
+from conftest import BATCH_CASES, batch_inputs, case_config, logit_rel_err, rel_err
 from oracle import greedy as og
 from oracle import model as om
 from oracle import spectrogram as osp
