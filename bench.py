@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--precision", default=os.environ.get("DANSPEECH_B200_PRECISION", "bf16"),
                     choices=["fp32", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=1, help="utterances in the cpu_baseline sample")
-    ap.add_argument("--ref-batch", type=int, default=8, help="utterances per reference-arm step")
+    ap.add_argument("--ref-batch", type=int, default=0,
+                    help="utterances per reference-arm step (0 = as many as keep the whole run near three minutes, <= 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true")
     return ap.parse_args()
@@ -176,7 +177,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nb = args.ref_batch
+    # bounded sample: a 15 s utterance costs the host ~1.3 s, so size the step for ~150 s over steps + warm-up
+    nb = args.ref_batch or max(1, min(8, int(150.0 / (max(1, args.steps) + 1) / 1.3)))
     steps = max(1, args.steps)
     rtfx, sec, threads = cpu_reference_rtfx(nb, steps, max(1, min(args.warmup, 1)))
     line = {
