@@ -278,6 +278,7 @@ class PhraseListener(object):
             except IndexError:
                 raise NoDataInBuffer
 
+        get_data.capture_ended = lambda: not worker.is_alive()   # finite sources only: a microphone never ends
         worker.start()
         return stopper, get_data
 
@@ -300,11 +301,15 @@ class PhraseListener(object):
         is collected until the capture thread reports its end and then goes through ``recognize`` if it is longer
         than ``mininum_required_speaking_seconds``."""
         self.stream_thread_stopper, get_data = self.listen_in_background(source)
+        capture_ended = getattr(get_data, "capture_ended", lambda: False)
         parts = []
         while self.stream:
+            done = capture_ended()                        # read BEFORE polling: then an empty queue is final
             try:
                 is_last, samples = get_data()
             except NoDataInBuffer:
+                if done:
+                    return                                # a finite source has been consumed (an addition)
                 time.sleep(0.2)
                 continue
             parts.append(samples)
@@ -329,12 +334,14 @@ class PhraseListener(object):
         need_first = need_later + per_10ms * 15
 
         self.stream_thread_stopper, get_data = self.listen_in_background(source)
+        capture_ended = getattr(get_data, "capture_ended", lambda: False)
         time.sleep(0.2)                                   # let the capture thread start
         pending, first_pass, ended = [], True, False
         got_some, misses = False, 0
         while self.stream:
             # drain the queue; stop draining at a phrase end, or once a run of data is followed by an empty queue
             while not ended:
+                done = capture_ended()                    # read BEFORE polling: then an empty queue is final
                 try:
                     ended, samples = get_data()
                     pending.append(samples)
@@ -343,6 +350,8 @@ class PhraseListener(object):
                     if got_some:
                         got_some, misses = False, 0
                         break
+                    if done:
+                        return                            # a finite source has been consumed (an addition)
                     if not pending:
                         time.sleep(0.4)
                     else:
