@@ -109,7 +109,7 @@ class PhraseListener(object):
         return AudioData(b"".join(kept), source.sampling_rate, source.sampling_width)
 
     def _listen_buffers(self, source, timeout=None, phrase_time_limit=None):
-        """The loop of ``listen``: (buffers of the phrase, number of trailing quiet buffers read but not kept)."""
+        """The loop of ``listen``: (buffers of the phrase, bytes of trailing quiet that were read but not kept)."""
         _check_source(source, "listening")
         spb, pause_n, phrase_n, keep_n = self._buffer_counts(source)
         clock = 0.0
@@ -147,9 +147,9 @@ class PhraseListener(object):
                     break
             if heard - quiet >= phrase_n or not len(chunk):
                 break                                     # long enough, or the stream ended
-        dropped = max(0, quiet - keep_n)                  # trailing quiet beyond what is kept
-        for _ in range(dropped):
-            kept.pop()
+        dropped = 0                                       # bytes of trailing quiet beyond what is kept
+        for _ in range(quiet - keep_n):
+            dropped += len(kept.pop())
         return kept, dropped
 
     # ------------------------------------------------------------------ one phrase, buffer by buffer
@@ -211,7 +211,7 @@ class PhraseListener(object):
             while src.stream.tell() < total:
                 kept, dropped = self._listen_buffers(src, phrase_time_limit=phrase_time_limit)
                 n = sum(len(b) for b in kept) // src.sampling_width
-                end = min(src.stream.tell(), total) - dropped * src.chunk
+                end = min(src.stream.tell(), total) - dropped // src.sampling_width
                 if n and self._is_phrase(kept, src):
                     spans.append((end - n, end))
         return spans

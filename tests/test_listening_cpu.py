@@ -400,3 +400,8 @@ def test_segment_audio_and_recognize_long_batch_the_phrases_of_a_recording():
     assert [t for _, _, t in out] == ["clip of %d" % (hi - lo) for lo, hi in spans]
     assert batches_seen == [[[max(hi - lo for lo, hi in spans)], [min(hi - lo for lo, hi in spans)]]]   # longest first
     assert lst.recognize_long(np.zeros(40 * 1024, np.int16)) == []
+    # a recording that stops a few samples into the pause after a phrase: spans still index the samples exactly
+    cut = pcm[:58 * 1024 + 300]
+    (lo, hi), = listener(dynamic_energy_threshold=False).segment_audio(cut)
+    src = make_source(cut, short_tail=True)
+    assert np.array_equal(cut[lo:hi], np.frombuffer(listener(dynamic_energy_threshold=False).listen(src).frame_data, "<i2"))
