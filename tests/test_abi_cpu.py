@@ -94,3 +94,23 @@ def test_public_header_is_plain_c_and_cxx(tmp_path):
     if shutil.which("g++"):
         subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)],
                        check=True)
+
+
+def test_integration_doc_names_only_symbols_the_header_declares():
+    """INTEGRATION.md is the binding recipe: every ``dsb_*`` function it mentions must be declared in the header,
+    and its Python snippets must at least parse."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md"), encoding="utf-8").read()
+    header = open(os.path.join(root, "include", "danspeech_b200.h"), encoding="utf-8").read()
+    declared = set(re.findall(r"\b(dsb_[a-z0-9_]+)\s*\(", header))
+    types_and_consts = set(re.findall(r"\b(dsb_[a-z0-9_]+)\b", header)) - declared
+    mentioned = set(re.findall(r"\b(dsb_[a-z0-9_]+)\b", doc))
+    wildcard = {m for m in mentioned if m.endswith("_")}          # e.g. "dsb_profile_enable/reset/read" prefixes
+    unknown = {m for m in mentioned - wildcard if m not in declared and m not in types_and_consts}
+    assert not unknown, sorted(unknown)
+    assert len(mentioned & declared) >= 15
+    for block in re.findall(r"```python\n(.*?)```", doc, flags=re.S):
+        if "# reference" in block and "# danspeech_b200" in block:
+            continue                                               # the two-column import comparison is not code
+        ast.parse(block)
