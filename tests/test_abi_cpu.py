@@ -114,3 +114,43 @@ def test_integration_doc_names_only_symbols_the_header_declares():
         if "# reference" in block and "# danspeech_b200" in block:
             continue                                               # the two-column import comparison is not code
         ast.parse(block)
+
+
+def test_reference_citations_resolve():
+    """Every ``file.py:line(-line)`` citation in the header, the docs and the sources points into an existing file of
+    the reference checkout (build container only) with that many lines."""
+    import glob
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "danspeech")):
+        pytest.skip("reference tree only exists in the build container")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = {}
+    for d, _, files in os.walk(ref):
+        for f in files:
+            if f.endswith((".py", ".rst", ".txt", ".json")):
+                with open(os.path.join(d, f), encoding="utf-8", errors="ignore") as fh:
+                    lines.setdefault(f, []).append((os.path.join(d, f), sum(1 for _ in fh)))
+    ours = ["include/danspeech_b200.h", "DESIGN.md", "INTEGRATION.md", "README.md", "bench.py"]
+    for pat in ("danspeech_b200/**/*.py", "danspeech_b200/csrc/*", "oracle/*.py", "oracle/*.cpp", "tests/*.py", "tests/golden/*.py"):
+        ours += [os.path.relpath(p, root) for p in glob.glob(os.path.join(root, pat), recursive=True)]
+    cite = re.compile(r"([A-Za-z_][\w/\.]*\.(?:py|rst|txt|json)):(\d+)(?:-(\d+))?")
+    checked, bad = 0, []
+    for rel in ours:
+        path = os.path.join(root, rel)
+        if not os.path.isfile(path):
+            continue
+        text = open(path, encoding="utf-8", errors="ignore").read()
+        for m in cite.finditer(text):
+            name, a, b = m.group(1), int(m.group(2)), int(m.group(3) or m.group(2))
+            cands = lines.get(os.path.basename(name))
+            if not cands:
+                if not (os.path.exists(os.path.join(root, name)) or os.path.exists(os.path.join(root, "danspeech_b200", name))
+                        or os.path.exists(os.path.join(root, "tests", os.path.basename(name)))):
+                    bad.append((rel, m.group(0), "no such file"))
+                continue
+            cands = [c for c in cands if c[0].endswith(name)] or cands
+            checked += 1
+            if not any(a <= b <= n for _, n in cands):
+                bad.append((rel, m.group(0), "line range"))
+    assert not bad, bad[:10]
+    assert checked > 150
