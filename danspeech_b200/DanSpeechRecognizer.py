@@ -175,11 +175,40 @@ class DanSpeechRecognizer(object):
             results[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
         return results
 
-    def transcribe_batches(self, batches, show_all=False):
-        """Several batches back to back.  A helper thread converts batch k+1 into one of two cached pinned buffers and
-        starts its host->device copy on a side stream while the GPU works on batch k, so neither the float64->float32
-        conversion nor the PCIe copy sits between two batches.  A batch is a list of recordings or a
-        (pinned f32 tensor [B, stride], n_samples) tuple sorted by length descending.  Returns one result list per batch."""
+    # Batches that transcribe_batches runs through ONE pass of the model: the persistent recurrence keeps up to three
+    # groups of 64 sequences in flight per CTA (csrc/rnn_tc.cu), so three batches of 64 cost far less than three passes.
+    batches_in_flight = 3
+    max_merged_rows = 192
+    max_merged_samples = 192 * 30 * 16000     # bound on rows x longest recording of a merged pass (workspace size)
+
+    def _merge_plan(self, batches, merge):
+        """Consecutive batches -> passes of at most `merge` batches within the row / sample budgets."""
+        plan, cur, rows, longest = [], [], 0, 0
+        for k, b in enumerate(batches):
+            if isinstance(b, tuple):
+                n, ln = len(b[1]), max(int(v) for v in b[1])
+            else:
+                n, ln = len(b), max(len(r) for r in b)
+            fits = cur and len(cur) < merge and rows + n <= self.max_merged_rows and \
+                (rows + n) * max(longest, ln) <= self.max_merged_samples and \
+                isinstance(b, tuple) == isinstance(batches[cur[0]], tuple)
+            if not fits and cur:
+                plan.append(cur)
+                cur, rows, longest = [], 0, 0
+            cur.append(k)
+            rows += n
+            longest = max(longest, ln)
+        if cur:
+            plan.append(cur)
+        return plan
+
+    def transcribe_batches(self, batches, show_all=False, merge=None):
+        """Several batches back to back.  Up to ``merge`` (default ``batches_in_flight``) consecutive batches go through
+        the model as ONE pass (their sequences sorted by length together), and a helper thread converts the next pass
+        into one of two cached pinned buffers and starts its host->device copy on a side stream while the GPU works on
+        the current one, so neither the float64->float32 conversion nor the PCIe copy sits between two passes.  A batch
+        is a list of recordings or a (pinned f32 tensor [B, stride], n_samples) tuple sorted by length descending.
+        Returns one result list per batch, in input order."""
         import concurrent.futures
 
         dev = torch.device(self.device if isinstance(self.device, (str, torch.device)) else "cuda")
@@ -190,30 +219,52 @@ class DanSpeechRecognizer(object):
         copy_stream = self._copy_streams.get(str(dev))
         if copy_stream is None:
             copy_stream = self._copy_streams[str(dev)] = torch.cuda.Stream(device=dev)
+        plan = self._merge_plan(batches, max(1, int(merge or self.batches_in_flight)))
 
-        def stage(k):
-            recs = batches[k]
-            if isinstance(recs, tuple):
-                host, ns = recs
-                ns = [int(v) for v in ns]
-                order = list(range(len(ns)))
+        def stage(j):
+            members = plan[j]
+            sizes = [len(batches[k][1]) if isinstance(batches[k], tuple) else len(batches[k]) for k in members]
+            if isinstance(batches[members[0]], tuple):
+                # pinned tensors, each already sorted: copy them side by side, then order the rows on the device
+                ns = [int(v) for k in members for v in batches[k][1]]
+                stride = max(batches[k][0].shape[1] for k in members)
+                order = sorted(range(len(ns)), key=lambda i: -ns[i])          # stable: equal lengths keep their order
+                with torch.cuda.device(dev), torch.cuda.stream(copy_stream):
+                    if len(members) == 1:
+                        audio = batches[members[0]][0].to(dev, non_blocking=True)
+                    else:
+                        audio = torch.empty((len(ns), stride), dtype=torch.float32, device=dev)
+                        row = 0
+                        for k in members:
+                            h = batches[k][0]
+                            audio[row:row + h.shape[0], : h.shape[1]].copy_(h, non_blocking=True)
+                            row += h.shape[0]
+                    if order != list(range(len(ns))):
+                        audio = audio.index_select(0, torch.tensor(order, dtype=torch.int64).to(dev, non_blocking=True))
+                    ns = [ns[i] for i in order]
+                    n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy_stream)
+                for k in members:
+                    self.audio_parser.mark_staging_busy(batches[k][0], done)
             else:
+                recs = [r for k in members for r in batches[k]]
                 order = sorted(range(len(recs)), key=lambda i: -len(recs[i]))
-                host, ns = self.audio_parser.stage_batch([recs[i] for i in order], slot=k & 1)
-            with torch.cuda.device(dev), torch.cuda.stream(copy_stream):
-                audio = host.to(dev, non_blocking=True)
-                n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
-                done = torch.cuda.Event()
-                done.record(copy_stream)
-            self.audio_parser.mark_staging_busy(host, done)
-            return audio, n_dev, ns, order, done
+                host, ns = self.audio_parser.stage_batch([recs[i] for i in order], slot=j & 1)
+                with torch.cuda.device(dev), torch.cuda.stream(copy_stream):
+                    audio = host.to(dev, non_blocking=True)
+                    n_dev = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy_stream)
+                self.audio_parser.mark_staging_busy(host, done)
+            return audio, n_dev, ns, order, sizes, done
 
         results = []
         with concurrent.futures.ThreadPoolExecutor(max_workers=1) as ex:
-            nxt = ex.submit(stage, 0) if batches else None
-            for k in range(len(batches)):
-                audio, n_dev, ns, order, done = nxt.result()
-                nxt = ex.submit(stage, k + 1) if k + 1 < len(batches) else None
+            nxt = ex.submit(stage, 0) if plan else None
+            for j in range(len(plan)):
+                audio, n_dev, ns, order, sizes, done = nxt.result()
+                nxt = ex.submit(stage, j + 1) if j + 1 < len(plan) else None
                 torch.cuda.current_stream(dev).wait_event(done)
                 audio.record_stream(torch.cuda.current_stream(dev))
                 n_dev.record_stream(torch.cuda.current_stream(dev))
@@ -221,8 +272,11 @@ class DanSpeechRecognizer(object):
                 input_sizes = torch.IntTensor([1 + n // self.audio_parser.hop_length for n in ns])
                 out, output_sizes = self.model(spect.view(len(ns), 1, 161, spect.shape[2]), input_sizes)
                 decoded_output, _ = self.decoder.decode(out, output_sizes)
-                res = [None] * len(order)
+                flat = [None] * len(order)
                 for pos, i in enumerate(order):
-                    res[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
-                results.append(res)
+                    flat[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
+                row = 0
+                for n in sizes:
+                    results.append(flat[row:row + n])
+                    row += n
         return results

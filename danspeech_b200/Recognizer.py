@@ -33,9 +33,10 @@ class Recognizer(PhraseListener):
     def recognize_batch(self, audio_list, show_all=False):
         return self.danspeech_recognizer.transcribe_batch(audio_list, show_all=show_all)
 
-    def recognize_batches(self, batches, show_all=False):
-        """Several batches back to back with the host staging of the next batch overlapped with the GPU work."""
-        return self.danspeech_recognizer.transcribe_batches(batches, show_all=show_all)
+    def recognize_batches(self, batches, show_all=False, merge=None):
+        """Several batches back to back: up to ``merge`` consecutive batches share one pass of the model (default: the
+        engine's ``batches_in_flight``), and the host staging of the next pass overlaps the GPU work of the current."""
+        return self.danspeech_recognizer.transcribe_batches(batches, show_all=show_all, merge=merge)
 
     def update_model(self, model):
         self.danspeech_recognizer.update_model(model)

@@ -29,6 +29,8 @@ _SIGS = {
     "dsb_profile_enable": (None, [c_int]),
     "dsb_profile_reset": (None, []),
     "dsb_profile_read": (c_int, [c_int, POINTER(c_double), POINTER(c_int)]),
+    "dsb_tune_set": (c_int, [c_char_p, c_int]),
+    "dsb_tune_get": (c_int, [c_char_p]),
     "dsb_spectrogram_num_frames": (c_int, [c_int]),
     "dsb_spectrogram_partials": (c_int, [c_int]),
     "dsb_spectrogram_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p,
@@ -118,6 +120,15 @@ def profile_read():
         check(lib().dsb_profile_read(i, ms, n), "dsb_profile_read")
         out[name] = (ms.value, n.value)
     return out
+
+
+def tune(**knobs):
+    """Sets diagnostic tuning knobs (dsb_tune_set), e.g. tune(rnn_in_flight=1); returns the previous values."""
+    prev = {}
+    for k, v in knobs.items():
+        prev[k] = int(lib().dsb_tune_get(k.encode()))
+        check(lib().dsb_tune_set(k.encode(), int(v)), "dsb_tune_set(%s)" % k)
+    return prev
 
 
 def ptr(t):

@@ -1,10 +1,12 @@
 #include "common.cuh"
+#include <cstring>
 #include <mutex>
 #include <vector>
 
 namespace dsb {
 thread_local char g_err[512] = {0};
 std::atomic<uint64_t> g_launches{0};
+Tune g_tune;
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -71,6 +73,36 @@ extern "C" int dsb_profile_read(int stage, double* total_ms, int* spans) {
   *total_ms = t;
   *spans = (int)dsb::g_spans[stage].size();
   return 0;
+}
+
+namespace {
+struct Knob { const char* name; std::atomic<int>* v; int lo, hi; };
+const Knob* knobs(int* n) {
+  static const Knob k[] = {{"rnn_in_flight", &dsb::g_tune.rnn_in_flight, 1, 3},
+                           {"rnn_max_slots", &dsb::g_tune.rnn_max_slots, 0, 1 << 20},
+                           {"gx_bf16", &dsb::g_tune.gx_bf16, 0, 1}};
+  *n = (int)(sizeof(k) / sizeof(k[0]));
+  return k;
+}
+}  // namespace
+extern "C" int dsb_tune_set(const char* key, int value) {
+  int n = 0;
+  const Knob* k = knobs(&n);
+  for (int i = 0; key && i < n; ++i)
+    if (strcmp(key, k[i].name) == 0) {
+      if (value < k[i].lo || value > k[i].hi)
+        return dsb::set_error(DSB_ERR_INVALID, "dsb_tune_set: %s = %d outside [%d, %d]", key, value, k[i].lo, k[i].hi);
+      k[i].v->store(value);
+      return 0;
+    }
+  return dsb::set_error(DSB_ERR_INVALID, "dsb_tune_set: unknown key '%s'", key ? key : "(null)");
+}
+extern "C" int dsb_tune_get(const char* key) {
+  int n = 0;
+  const Knob* k = knobs(&n);
+  for (int i = 0; key && i < n; ++i)
+    if (strcmp(key, k[i].name) == 0) return k[i].v->load();
+  return -1;
 }
 
 extern "C" const char* dsb_last_error(void) { return dsb::g_err; }

@@ -50,6 +50,14 @@ struct ProfScope {
   ~ProfScope() { prof_end(stage, st); }
 };
 
+// Tuning knobs (dsb_tune_set / dsb_tune_get; defaults are the production settings).
+struct Tune {
+  std::atomic<int> rnn_in_flight{3};
+  std::atomic<int> rnn_max_slots{0};
+  std::atomic<int> gx_bf16{0};
+};
+extern Tune g_tune;
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

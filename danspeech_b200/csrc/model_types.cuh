@@ -82,7 +82,12 @@ bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* laun
 int pack_whh_tc(const RnnLayer& L, __nv_bfloat16* out, cudaStream_t st);
 int combine_dirs_tc(const float* y, int dirs, int T, int B, int H, const int32_t* d_len, __nv_bfloat16* xb, int ldx,
                     float* xf, cudaStream_t st);
-constexpr int kRnnSyncCounters = 16;   // sync words: [0,16) step counters, [16] abort flag
+// sync words of the persistent recurrence: kRnnMaxCounters step counters (one per direction x CTA set x group in
+// flight), each on its own 128-byte line (the L2 atomic unit serialises per address), then the abort flag
+constexpr int kRnnCounterStride = 32;
+constexpr int kRnnMaxCounters = 48;
+constexpr int kRnnSyncCounters = kRnnMaxCounters * kRnnCounterStride;
+int rnn_tc_max_in_flight();
 size_t rnn_tc_hbuf_elems(const RnnLayer& L, int B);
 int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
                  __nv_bfloat16* hbuf, unsigned int* sync_words, cudaStream_t st, const float* h0 = nullptr,

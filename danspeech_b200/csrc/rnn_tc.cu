@@ -17,9 +17,9 @@
 //                   tcgen05.ld the accumulators, apply the gate non-linearities with the fp32 hidden
 //                   state kept in registers, stage h_t (bf16) in shared memory, store it coalesced for the next
 //                   step's TMA, publish (one red.release per CTA per step), then store y_t (fp32).
-// Batches above 128 rows run as groups inside the same launch (W_hh stays resident); groups can run side by side
-// on independent CTA sets ("slots") when a direction's CTAs leave SMs free, and an initial / final hidden state
-// can be carried (streaming).
+// Batches above 64 rows run as groups of 64 inside the same launch (W_hh stays resident), up to three groups IN
+// FLIGHT per CTA (see rnn_tc_kernel); groups also run side by side on independent CTA sets ("slots") when a
+// direction's CTAs leave SMs free, and an initial / final hidden state can be carried (streaming).
 // The step is latency-bound (grid barrier + L2 round trips), not tensor-bound: algorithmic work is
 // 2*B*3H*H flop per step per direction and is reported against the tensor roof.
 //
@@ -36,8 +36,9 @@ constexpr int RT_N = 64;                       // W_hh rows per CTA = 2 halves x
 constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk (8 KB)
 constexpr int RT_GROUP = 4;        // K chunks handled per elected issue region (2 when only one group of 4 would fit)
 constexpr int RT_MAX_GROUPS = 4;   // barrier slots; the ring holds 2 groups of 4 chunks or up to 4 groups of 2
+constexpr int RT_MAX_NIF = 3;      // batch groups in flight per CTA (each with its own TMEM accumulator)
 // (Consecutive tcgen05.mma into the same accumulator do not stall each other -- tested with 4 independent
-// accumulators: no change -- so a single 64-column TMEM accumulator is used.)
+// accumulators: no change -- so a single 64-column TMEM accumulator per batch group is used.)
 constexpr int RT_THREADS = 64 + 256;
 constexpr long long RT_TIMEOUT_CYCLES = 4000000000LL;
 constexpr int RT_SMEM_LIMIT = 227 * 1024;
@@ -78,8 +79,8 @@ struct RnnTcParams {
   const float* b_hn;        // [dirs][H] GRU n-gate hidden bias (else nullptr)
   float* y;                 // [dirs][T][B][H]
   __nv_bfloat16* hbuf;      // [n_bgroups][2][dirs][BP][HP]
-  const int32_t* lens;      // [B] or nullptr (every sequence runs Tmax steps)
-  unsigned int* counters;   // [dirs][slots]
+  const int32_t* lens;      // [B] sorted descending, or nullptr (every sequence runs Tmax steps)
+  unsigned int* counters;   // [dirs][slots][NIF] step counters, kRnnCounterStride words apart
   int* abort_flag;
   const float* h0;          // [dirs][B][H] initial hidden state or nullptr (zeros)
   const float* c0;          // LSTM cell state, likewise
@@ -90,11 +91,12 @@ struct RnnTcParams {
   int dir0;   // first direction handled by this launch
   int cpd;    // CTAs per (direction, slot)
   int n_bgroups;   // the batch is processed in groups of BP rows ...
-  int slots;       // ... by `slots` independent CTA sets per direction (set k takes groups k, k+slots, ...)
+  int slots;       // ... by `slots` independent CTA sets per direction (set k takes groups k, k+slots, ...),
+                   // NIF groups of a set in flight at a time
   int U;      // hidden units per CTA (2 * units per half)
   int small_groups;   // ring in groups of 2 K chunks even when two groups of 4 fit (DSB_RNN_GSZ=2)
   int nkc;    // K chunks of 64 (HP / 64)
-  unsigned long long* dbg;   // optional [grid][16] cycle counters (DSB_RNN_DEBUG=1)
+  unsigned long long* dbg;   // optional [grid][128] cycle counters (DSB_RNN_DEBUG=1)
 };
 
 __device__ __forceinline__ bool wait_abortable(uint64_t* bar, uint32_t parity, int* abort_flag) {
@@ -143,16 +145,35 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f,
 // exp-based form below is accurate to ~1e-6 and still a handful of instructions.
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
+// Steps of batch group bg: the lengths are sorted descending (forward() rejects anything else, like
+// pack_padded_sequence behind model.py:117), so the group's first row is its longest sequence.
+__device__ __forceinline__ int rt_group_steps(const RnnTcParams& p, int bg) {
+  if (bg >= p.n_bgroups) return 0;
+  if (!p.lens) return p.Tmax;
+  const int l = p.lens[bg * p.BP];
+  return l < p.Tmax ? l : p.Tmax;
+}
+
+// NIF batch groups of a CTA set are in flight at a time.  One step of one group is a serial chain -- all-gather of
+// h (publish -> barrier -> TMA: ~3.4 k cycles of latency) -> 76 MMAs (~4.5 k) -> gate math and publish (~2.7 k) --
+// in which the tensor pipe is busy less than half of the time and nothing can overlap, because every chunk of h
+// becomes available at the same moment.  Independent groups can: all three roles walk the same item sequence
+// (wave, step, group-in-flight); while group A sits in its epilogue and communication chain, the MMA warp runs
+// group B against the same resident W_hh slice.  Per group in flight: its own TMEM accumulator, accumulator-full
+// barrier, step counter and exchange buffers; the TMA ring is shared (the MMA phases are serialised on the tensor
+// pipe anyway) and the eight epilogue warps take the groups in turn.
+//
 // SPLITM (GRU, batch groups of 64 rows): an M = 64 accumulator quarter only fills TMEM lanes 0-15, so lanes 16-31 of
 // every epilogue warp would idle through the MUFU-bound gate math.  Lane l+16 computes the second half of lane l's
 // hidden units on values handed over by shuffle and hands h back; loads, stores and the recurrent state stay with
 // lanes 0-15 (splitting those as well doubled the number of memory requests and was measured slower).
-template <int GATES, bool SPLITM = false>
+template <int GATES, bool SPLITM, int NIF>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
               const RnnTcParams p) {
   constexpr int UH = 32 / GATES;   // units per 32-column half
   constexpr int U = 2 * UH;
+  constexpr int TMEM_COLS = NIF == 1 ? 64 : (NIF == 2 ? 128 : 256);
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const RtPlan pl = rt_plan(p.nkc, p.BP, U, p.small_groups);
@@ -162,37 +183,33 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.bar_off);   // [RT_MAX_GROUPS] group landed (TMA tx)
   uint64_t* gempty = full + RT_MAX_GROUPS;                           // [RT_MAX_GROUPS] group consumed by the MMAs
   uint64_t* wbar = gempty + RT_MAX_GROUPS;
-  uint64_t* dfull = wbar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
+  uint64_t* dfull = wbar + 1;                                        // [RT_MAX_NIF] accumulator of group-in-flight i complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + RT_MAX_NIF);
   const int n_groups = pl.groups;
   const int gsz = pl.gsz;
-  const int gps = (p.nkc + gsz - 1) / gsz;   // group uses per step
+  const int gps = (p.nkc + gsz - 1) / gsz;   // ring-group uses per step
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int set = blockIdx.x / p.cpd;          // (direction, slot)
   const int dir = p.dir0 + set / p.slots;
   const int slot = set % p.slots;
   const int c = blockIdx.x % p.cpd;
-  // Optional clusters of CL CTAs (same direction) share the h stream by TMA multicast; every cluster (or
-  // CTA) walks the K chunks in its own rotation so that the readers do not hit the same L2 lines together.
-  const int CL = (int)cluster_nctarank();
-  const int crank = (int)cluster_ctarank();
-  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
-  const int g_rot = (int)(((long long)(c / CL) * gps) / ((p.cpd + CL - 1) / CL));   // rotation in whole groups
+  // every CTA walks the K chunks in its own rotation so that the readers do not hit the same L2 lines together
+  const int g_rot = (int)(((long long)c * gps) / p.cpd);   // rotation in whole ring groups
+  unsigned* const ctr0 = p.counters + (size_t)((dir * p.slots + slot) * NIF) * kRnnCounterStride;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_h);
     for (int i = 0; i < RT_MAX_GROUPS; ++i) mbar_init(&full[i], 1);
-    for (int i = 0; i < RT_MAX_GROUPS; ++i) mbar_init(&gempty[i], CL);   // one commit from every CTA of the cluster
+    for (int i = 0; i < RT_MAX_GROUPS; ++i) mbar_init(&gempty[i], 1);
     mbar_init(wbar, 1);
-    mbar_init(dfull, 1);
+    for (int i = 0; i < RT_MAX_NIF; ++i) mbar_init(&dfull[i], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<64>(tmem_slot);
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();    // peers' barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
@@ -206,7 +223,6 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     }
     __syncwarp();
     bool ok = true;
-    const unsigned* ctr = p.counters + dir * p.slots + slot;
     unsigned long long d_spin = 0, d_fence = 0, d_issue = 0, d_empty = 0;
     // ring positions of the next group to arm / to load (slot index + phase kept incrementally: a 64-bit
     // modulo per group costs the single issuing warp hundreds of cycles)
@@ -231,58 +247,71 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       if (++load_slot == n_groups) load_slot = 0;
       int gg = g + g_rot;
       if (gg >= gps) gg -= gps;
-      if (elect_one_sync()) {
-        if (CL == 1)
-          tma_load_3d(sA + grp * gsz * pl.stage_bytes, &tmap_h, &full[grp], 0, row0, gg * gsz);
-        else if (g % CL == crank)
-          tma_load_3d_mcast(sA + grp * gsz * pl.stage_bytes, &tmap_h, &full[grp], 0, row0, gg * gsz, cmask);
-      }
+      if (elect_one_sync()) tma_load_3d(sA + grp * gsz * pl.stage_bytes, &tmap_h, &full[grp], 0, row0, gg * gsz);
       __syncwarp();
     };
-    unsigned done = 0;   // steps of earlier batch groups (the step counter keeps counting across groups)
-    for (int bg = slot; bg < p.n_bgroups && ok; bg += p.slots, done += (unsigned)p.Tmax)
-    for (int s = 0; s < p.Tmax && ok; ++s) {
+    // one step of one group: `steps_before` = steps this group-in-flight index has completed in earlier waves
+    auto item = [&](int i, int s, int bg, unsigned steps_before) -> bool {
       long long c0 = clock64();
       const int pre = min(gps, n_groups);
-      for (int g = 0; g < pre && ok; ++g) ok = arm_group();
-      if (!ok) break;
+      for (int g = 0; g < pre; ++g)
+        if (!arm_group()) return false;
       d_empty += clock64() - c0;
       c0 = clock64();
-      if (s > 0 || done > 0) {
-        // set-wide barrier: every CTA of this set has published h_{s-1} (at s = 0 of a later batch group:
-        // has finished the previous group, so its TMEM accumulator and staging buffers are free again)
-        const unsigned target = (unsigned)p.cpd * (done + (unsigned)s);
+      if (steps_before + (unsigned)s > 0) {
+        // set-wide barrier: every CTA of this set has published h_{s-1} of this group (at s = 0 of a later wave:
+        // has finished the group that used this accumulator / counter before)
+        const unsigned target = (unsigned)p.cpd * (steps_before + (unsigned)s);
+        const unsigned* ctr = ctr0 + i * kRnnCounterStride;
         long long t0 = 0;
         unsigned n = 0;
+        bool good = true;
         while (ld_acquire_gpu(ctr) < target) {
           if ((++n & 0x3F) == 0) {
-            if (*(volatile int*)p.abort_flag) { ok = false; break; }
+            if (*(volatile int*)p.abort_flag) { good = false; break; }
             long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > RT_TIMEOUT_CYCLES) { atomicExch(p.abort_flag, 1); ok = false; break; }
+            else if (now - t0 > RT_TIMEOUT_CYCLES) { atomicExch(p.abort_flag, 1); good = false; break; }
           }
         }
-        ok = __all_sync(0xffffffffu, ok);
-        if (!ok) break;
+        if (!__all_sync(0xffffffffu, good)) return false;
         long long c1 = clock64();
         asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
         d_spin += c1 - c0;
         d_fence += clock64() - c1;
       }
       long long c2 = clock64();
-      if (p.dbg && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 15] = c2;
+      if (p.dbg && s == 100 && i == 0 && lane == 0) p.dbg[blockIdx.x * 128 + 15] = c2;
       const int row0 = ((bg * 2 + (s & 1)) * p.dirs + dir) * p.BP;
-      for (int g = 0; g < gps && ok; ++g) {
+      for (int g = 0; g < gps; ++g) {
         if (g >= pre) {
           long long w0 = clock64();
-          ok = arm_group();
+          if (!arm_group()) return false;
           d_empty += clock64() - w0;
-          if (!ok) break;
         }
         load_group(g, row0);
-        if (p.dbg && s == 100 && g < 8 && lane == 0) p.dbg[blockIdx.x * 128 + 16 + g] = clock64();
+        if (p.dbg && s == 100 && i == 0 && g < 8 && lane == 0) p.dbg[blockIdx.x * 128 + 16 + g] = clock64();
       }
       d_issue += clock64() - c2;
+      return true;
+    };
+    unsigned before[NIF];
+#pragma unroll
+    for (int i = 0; i < NIF; ++i) before[i] = 0;
+    for (int k0 = 0; ok && slot + k0 * p.slots < p.n_bgroups; k0 += NIF) {
+      int Tg[NIF], Tw = 0;
+#pragma unroll
+      for (int i = 0; i < NIF; ++i) {
+        Tg[i] = rt_group_steps(p, slot + (k0 + i) * p.slots);
+        Tw = max(Tw, Tg[i]);
+      }
+      for (int s = 0; s < Tw && ok; ++s) {
+#pragma unroll
+        for (int i = 0; i < NIF; ++i)
+          if (ok && s < Tg[i]) ok = item(i, s, slot + (k0 + i) * p.slots, before[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < NIF; ++i) before[i] += (unsigned)Tg[i];
     }
     if (p.dbg && lane == 0) {
       p.dbg[blockIdx.x * 128 + 0] = d_spin;
@@ -302,21 +331,20 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     unsigned long long d_wait0 = 0, d_rest = 0, d_waitn = 0;
     int grp = 0;
     uint32_t fphase = 0;
-    for (int bg = slot; bg < p.n_bgroups && ok; bg += p.slots)
-    for (int s = 0; s < p.Tmax && ok; ++s) {
+    auto item = [&](int i, int s) -> bool {
       long long m0 = clock64();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(i * 64);
       for (int g = 0; g < gps; ++g) {
         int gg = g + g_rot;
         if (gg >= gps) gg -= gps;
         const int i0 = gg * gsz, i1 = min(p.nkc, i0 + gsz);
         long long w0 = clock64();
-        ok = __all_sync(0xffffffffu, wait_abortable(&full[grp], fphase, p.abort_flag));
-        if (!ok) break;
+        if (!__all_sync(0xffffffffu, wait_abortable(&full[grp], fphase, p.abort_flag))) return false;
         if (g == 0) { long long m1 = clock64(); d_wait0 += m1 - m0; m0 = m1; }
         else d_waitn += clock64() - w0;
         tc_fence_after();
         if (elect_one_sync()) {
-          if (p.dbg && s == 100 && g < 8) p.dbg[blockIdx.x * 128 + 40 + g] = clock64();
+          if (p.dbg && s == 100 && i == 0 && g < 8) p.dbg[blockIdx.x * 128 + 40 + g] = clock64();
           const uint32_t a0 = a_lo + (uint32_t)(grp * gsz) * stage16;
           const uint32_t b0 = w_lo + (uint32_t)i0 * (RT_W_BYTES >> 4);
           const int nch = i1 - i0;
@@ -327,19 +355,32 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
               const uint64_t bdesc = desc0 + (uint64_t)(b0 + (uint32_t)j * (RT_W_BYTES >> 4));
 #pragma unroll
               for (int k = 0; k < RT_BK / 16; ++k)
-                umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                           (j | k) ? 1u : (uint32_t)(g != 0));
             }
           }
-          if (CL == 1) umma_commit(&gempty[grp]);
-          else umma_commit_mcast(&gempty[grp], cmask);
-          if (g == gps - 1) umma_commit(dfull);
+          umma_commit(&gempty[grp]);
+          if (g == gps - 1) umma_commit(&dfull[i]);
         }
         __syncwarp();
         if (++grp == n_groups) { grp = 0; fphase ^= 1; }
       }
-      if (p.dbg && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 64] = clock64();
+      if (p.dbg && s == 100 && i == 0 && lane == 0) p.dbg[blockIdx.x * 128 + 64] = clock64();
       d_rest += clock64() - m0;
+      return true;
+    };
+    for (int k0 = 0; ok && slot + k0 * p.slots < p.n_bgroups; k0 += NIF) {
+      int Tg[NIF], Tw = 0;
+#pragma unroll
+      for (int i = 0; i < NIF; ++i) {
+        Tg[i] = rt_group_steps(p, slot + (k0 + i) * p.slots);
+        Tw = max(Tw, Tg[i]);
+      }
+      for (int s = 0; s < Tw && ok; ++s) {
+#pragma unroll
+        for (int i = 0; i < NIF; ++i)
+          if (ok && s < Tg[i]) ok = item(i, s);
+      }
     }
     if (p.dbg && lane == 0) {
       p.dbg[blockIdx.x * 128 + 3] = d_wait0;
@@ -356,30 +397,21 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     const int lrow = q * rpq + lane;     // row inside the batch group (= TMEM lane / hbuf row)
     const int j0 = c * U + half * UH;
     const int ncol = p.dirs * GATES * p.H;
-    float hprev[UH], cst[UH], bhn[UH];
+    float hprev[NIF][UH], cst[NIF][UH], bhn[UH];
 #pragma unroll
     for (int u = 0; u < UH; ++u)
       bhn[u] = (GATES == 3 && p.b_hn && j0 + u < p.H) ? p.b_hn[(size_t)dir * p.H + j0 + u] : 0.f;
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
     // h store staging sH [BP][U] bf16 + row validity sT [BP].  Single-buffered: the next write happens after
-    // this CTA's publish of the step (behind the second named barrier), i.e. after every read of it.
+    // this CTA's publish of the item (behind the second named barrier), i.e. after every read of it.
     __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(sStg);
     __shared__ int sT[128];
     const bool vec2 = ((p.H & 1) == 0) && ((UH & 1) == 0);
     unsigned long long e_load = 0, e_wait = 0, e_math = 0, e_bar = 0, e_pub = 0;
-    unsigned done = 0;
-    bool alive = true;
-    for (int bg = slot; bg < p.n_bgroups && alive; bg += p.slots, done += (unsigned)p.Tmax) {
-    const int b = bg * p.BP + lrow;
-    const bool row_ok = lane < rpq && b < p.B;
-    const int len = row_ok ? (p.lens ? p.lens[b] : p.Tmax) : 0;
-#pragma unroll
-    for (int u = 0; u < UH; ++u) {
-      const bool in = row_ok && j0 + u < p.H;
-      hprev[u] = (p.h0 && in) ? p.h0[((size_t)dir * p.B + b) * p.H + j0 + u] : 0.f;
-      cst[u] = (p.c0 && in) ? p.c0[((size_t)dir * p.B + b) * p.H + j0 + u] : 0.f;
-    }
-    for (int s = 0; s < p.Tmax; ++s) {
+
+    // one step of one group.  hp / cs: this group's recurrent state (registers); returns false on abort.
+    auto item = [&](int i, int s, int bg, int b, bool row_ok, int len, unsigned steps_before, float (&hp)[UH],
+                    float (&cs)[UH]) -> bool {
       long long e0 = clock64();
       const bool active = row_ok && s < len;
       const int t = dir == 0 ? s : len - 1 - s;
@@ -404,12 +436,12 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       }
       if (half == 0 && lane < rpq) sT[lrow] = active ? t : -1;
       long long e1 = clock64();
-      const bool ok = wait_abortable(dfull, (uint32_t)((done + (unsigned)s) & 1u), p.abort_flag);
+      const bool ok = wait_abortable(&dfull[i], (uint32_t)((steps_before + (unsigned)s) & 1u), p.abort_flag);
       long long e2 = clock64();
-      if (p.dbg && s == 100 && et == 64) p.dbg[blockIdx.x * 128 + 65] = e2;
+      if (p.dbg && s == 100 && i == 0 && et == 64) p.dbg[blockIdx.x * 128 + 65] = e2;
       tc_fence_after();
       uint32_t r[32];
-      tmem_ld32(t_addr, r);
+      tmem_ld32(t_addr + (uint32_t)(i * 64), r);
       tmem_ld_wait();
       tc_fence_before();
       if constexpr (SPLITM && GATES == 3) {
@@ -429,13 +461,13 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             av[g] = hi ? a_hi : __uint_as_float(r[u * 3 + g]);
             gv[g] = hi ? g_hi : gxv[g][u];
           }
-          const float h_hi = __shfl_sync(0xffffffffu, hprev[UL + u], src);
-          const float hp = hi ? h_hi : hprev[u];
+          const float h_hi = __shfl_sync(0xffffffffu, hp[UL + u], src);
+          const float hpv = hi ? h_hi : hp[u];
           const float bh = hi ? bhn[UL + u] : bhn[u];
           const float rg = fast_sigmoid(gv[0] + av[0]);
           const float zg = fast_sigmoid(gv[1] + av[1]);
           const float ng = fast_tanh(gv[2] + rg * (av[2] + bh));
-          hn[u] = (1.0f - zg) * ng + zg * hp;
+          hn[u] = (1.0f - zg) * ng + zg * hpv;
         }
         __nv_bfloat16* sh = sH + (size_t)(q * rpq + src) * U + half * UH + (hi ? UL : 0);
 #pragma unroll
@@ -443,8 +475,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           const float back = __shfl_sync(0xffffffffu, hn[u], src + 16);
           if (act2) sh[u] = __float2bfloat16_rn(hn[u]);
           if (ok && active) {   // lanes 0-15: the state of all UH units
-            hprev[u] = hn[u];
-            hprev[UL + u] = back;
+            hp[u] = hn[u];
+            hp[UL + u] = back;
           }
         }
       } else
@@ -457,71 +489,105 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             const float rg = fast_sigmoid(gxv[0][u] + __uint_as_float(r[u * GATES + 0]));
             const float zg = fast_sigmoid(gxv[1 % GATES][u] + __uint_as_float(r[u * GATES + (1 % GATES)]));
             const float ng = fast_tanh(gxv[2 % GATES][u] + rg * (__uint_as_float(r[u * GATES + (2 % GATES)]) + bhn[u]));
-            hn = (1.0f - zg) * ng + zg * hprev[u];
+            hn = (1.0f - zg) * ng + zg * hp[u];
           } else if (GATES == 4) {
             const float ig = fast_sigmoid(gxv[0][u] + __uint_as_float(r[u * GATES + 0]));
             const float fg = fast_sigmoid(gxv[1 % GATES][u] + __uint_as_float(r[u * GATES + (1 % GATES)]));
             const float gg = fast_tanh(gxv[2 % GATES][u] + __uint_as_float(r[u * GATES + (2 % GATES)]));
             const float og = fast_sigmoid(gxv[3 % GATES][u] + __uint_as_float(r[u * GATES + (3 % GATES)]));
-            cst[u] = fg * cst[u] + ig * gg;
-            hn = og * fast_tanh(cst[u]);
+            cs[u] = fg * cs[u] + ig * gg;
+            hn = og * fast_tanh(cs[u]);
           } else {
             hn = fast_tanh(gxv[0][u] + __uint_as_float(r[u]));
           }
-          hprev[u] = hn;
+          hp[u] = hn;
           sh[u] = __float2bfloat16_rn(hn);
         }
       }
       long long e3 = clock64();
       const bool all_ok = bar_red_and(ok, 1, 256);     // staging complete (and uniform abort decision)
-      if (!all_ok) { alive = false; break; }
+      if (!all_ok) return false;
       // h_t -> global (bf16), coalesced: each row contributes U contiguous values
       {
         const int n_valid = min(U, p.H - c * U);       // units of this CTA inside H
         __nv_bfloat16* hrow0 = p.hbuf + ((size_t)((bg * 2 + ((s + 1) & 1)) * p.dirs + dir) * p.BP) * p.HP + c * U;
         if ((U & 3) == 0 && n_valid == U && (p.HP & 3) == 0) {
           const int per_row = U / 4;                   // 8-byte pieces
-          for (int i = et; i < p.BP * per_row; i += 256) {
-            const int row = i / per_row, part = i - row * per_row;
+          for (int k = et; k < p.BP * per_row; k += 256) {
+            const int row = k / per_row, part = k - row * per_row;
             if (sT[row] >= 0)
               *reinterpret_cast<uint2*>(hrow0 + (size_t)row * p.HP + part * 4) =
                   *reinterpret_cast<const uint2*>(sH + (size_t)row * U + part * 4);
           }
         } else {
-          for (int i = et; i < p.BP * U; i += 256) {
-            const int row = i / U, u = i - row * U;
+          for (int k = et; k < p.BP * U; k += 256) {
+            const int row = k / U, u = k - row * U;
             if (sT[row] >= 0 && u < n_valid) hrow0[(size_t)row * p.HP + u] = sH[(size_t)row * U + u];
           }
         }
       }
       named_bar_sync(2, 256);                          // all h stores issued
       long long e4 = clock64();
-      if (et == 0) red_release_gpu_add(p.counters + dir * p.slots + slot, 1u);   // publish h_t (release: cumulative over the CTA)
-      if (p.dbg && s == 99 && et == 0) p.dbg[blockIdx.x * 128 + 66] = clock64();
-      if (p.dbg && s == 100 && et == 0) p.dbg[blockIdx.x * 128 + 67] = clock64();
+      if (et == 0) red_release_gpu_add(ctr0 + i * kRnnCounterStride, 1u);   // publish h_t (release: cumulative over the CTA)
+      if (p.dbg && i == 0 && s == 99 && et == 0) p.dbg[blockIdx.x * 128 + 66] = clock64();
+      if (p.dbg && i == 0 && s == 100 && et == 0) p.dbg[blockIdx.x * 128 + 67] = clock64();
       // y_t -> global (fp32) straight from registers, after the publish: nobody waits on these stores
       if (ok && active) {
         float* yo = p.y + (((size_t)dir * p.T + t) * p.B + b) * p.H + j0;
         if ((UH & 1) == 0 && (p.H & 1) == 0 && j0 + UH <= p.H) {
 #pragma unroll
           for (int u = 0; u < UH; u += 2)
-            *reinterpret_cast<float2*>(yo + u) = make_float2(hprev[u], hprev[u + 1 < UH ? u + 1 : u]);
+            *reinterpret_cast<float2*>(yo + u) = make_float2(hp[u], hp[u + 1 < UH ? u + 1 : u]);
         } else {
 #pragma unroll
           for (int u = 0; u < UH; ++u)
-            if (j0 + u < p.H) yo[u] = hprev[u];
+            if (j0 + u < p.H) yo[u] = hp[u];
         }
       }
       e_load += e1 - e0; e_wait += e2 - e1; e_math += e3 - e2; e_bar += e4 - e3; e_pub += clock64() - e4;
-    }
-    if (alive && row_ok) {   // carry the state out (streaming): the last active step's h (and c)
+      return true;
+    };
+
+    unsigned before[NIF];
 #pragma unroll
-      for (int u = 0; u < UH; ++u)
-        if (j0 + u < p.H) {
-          if (p.hT) p.hT[((size_t)dir * p.B + b) * p.H + j0 + u] = hprev[u];
-          if (p.cT) p.cT[((size_t)dir * p.B + b) * p.H + j0 + u] = cst[u];
+    for (int i = 0; i < NIF; ++i) before[i] = 0;
+    bool alive = true;
+    for (int k0 = 0; alive && slot + k0 * p.slots < p.n_bgroups; k0 += NIF) {
+      int Tg[NIF], Tw = 0, bb[NIF], ln[NIF];
+      bool rok[NIF];
+#pragma unroll
+      for (int i = 0; i < NIF; ++i) {
+        const int bg = slot + (k0 + i) * p.slots;
+        Tg[i] = rt_group_steps(p, bg);
+        Tw = max(Tw, Tg[i]);
+        bb[i] = bg * p.BP + lrow;
+        rok[i] = bg < p.n_bgroups && lane < rpq && bb[i] < p.B;
+        ln[i] = rok[i] ? (p.lens ? p.lens[bb[i]] : p.Tmax) : 0;
+#pragma unroll
+        for (int u = 0; u < UH; ++u) {
+          const bool in = rok[i] && j0 + u < p.H;
+          hprev[i][u] = (p.h0 && in) ? p.h0[((size_t)dir * p.B + bb[i]) * p.H + j0 + u] : 0.f;
+          cst[i][u] = (GATES == 4 && p.c0 && in) ? p.c0[((size_t)dir * p.B + bb[i]) * p.H + j0 + u] : 0.f;
         }
-    }
+      }
+      for (int s = 0; s < Tw && alive; ++s) {
+#pragma unroll
+        for (int i = 0; i < NIF; ++i)
+          if (alive && s < Tg[i])
+            alive = item(i, s, slot + (k0 + i) * p.slots, bb[i], rok[i], ln[i], before[i], hprev[i], cst[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < NIF; ++i) {
+        before[i] += (unsigned)Tg[i];
+        if (alive && rok[i]) {   // carry the state out (streaming): the last active step's h (and c)
+#pragma unroll
+          for (int u = 0; u < UH; ++u)
+            if (j0 + u < p.H) {
+              if (p.hT) p.hT[((size_t)dir * p.B + bb[i]) * p.H + j0 + u] = hprev[i][u];
+              if (GATES == 4 && p.cT) p.cT[((size_t)dir * p.B + bb[i]) * p.H + j0 + u] = cst[i][u];
+            }
+        }
+      }
     }
     if (p.dbg && et == 64) {   // warp 4: quarter 0, an active row
       p.dbg[blockIdx.x * 128 + 5] = e_load;
@@ -533,10 +599,9 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();    // nobody leaves while a peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<64>(tmem_base);
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -583,13 +648,21 @@ __global__ void combine_dirs_kernel(const float* __restrict__ y, int dirs, int T
 
 }  // namespace tc
 
-// Batches larger than 128 run as groups of 128 rows inside the same launch (W_hh stays resident); when the
-// CTAs of one direction leave SMs free, several groups run side by side on independent CTA sets ("slots").
+// Batches above 64 rows run as groups of 64 rows inside the same launch (W_hh stays resident), up to RT_MAX_NIF of
+// them in flight per CTA; when the CTAs of one direction leave SMs free, groups also run side by side on
+// independent CTA sets ("slots").  dsb_tune_set("rnn_in_flight", 1) restores the round-1 scheme (groups of 128 rows,
+// one at a time).
+int rnn_tc_max_in_flight() {
+  const int v = g_tune.rnn_in_flight.load();
+  return v < 1 ? 1 : (v > tc::RT_MAX_NIF ? tc::RT_MAX_NIF : v);
+}
+static int rt_bp(int B) { return (B <= 64 || rnn_tc_max_in_flight() > 1) ? 64 : 128; }
+
 bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* launches_out) {
   const int UH = 32 / L.gates, U = 2 * UH;
   const int cpd = cdiv(L.H, U);
   const int HP = (L.H + 63) / 64 * 64;
-  const tc::RtPlan pl = tc::rt_plan(HP / 64, B <= 64 ? 64 : 128, U);
+  const tc::RtPlan pl = tc::rt_plan(HP / 64, rt_bp(B), U);
   if (B < 1 || pl.groups < 1 || pl.total > tc::RT_SMEM_LIMIT || cpd > sms) return false;
   if (cpd_out) *cpd_out = cpd;
   if (launches_out) *launches_out = (L.dirs * cpd <= sms) ? 1 : L.dirs;
@@ -597,7 +670,7 @@ bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* laun
 }
 
 size_t rnn_tc_hbuf_elems(const RnnLayer& L, int B) {
-  const int HP = (L.H + 63) / 64 * 64, BP = B <= 64 ? 64 : 128;
+  const int HP = (L.H + 63) / 64 * 64, BP = rt_bp(B);
   return (size_t)cdiv(B, BP) * 2 * L.dirs * BP * HP;
 }
 
@@ -689,13 +762,16 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (!rnn_tc_supported(L, B, sms, &cpd, &launches))
     return set_error(DSB_ERR_UNSUPPORTED, "rnn_layer_tc: shape H=%d B=%d not supported", L.H, B);
-  const int HP = (L.H + 63) / 64 * 64, BP = B <= 64 ? 64 : 128, nkc = HP / 64;
+  const int HP = (L.H + 63) / 64 * 64, BP = rt_bp(B), nkc = HP / 64;
   const int n_bgroups = cdiv(B, BP);
-  const int dirs_per_launch_ = L.dirs / launches;
-  int slots = sms / (dirs_per_launch_ * cpd);
+  const int dirs_per_launch = L.dirs / launches;
+  int slots = sms / (dirs_per_launch * cpd);
   if (slots > n_bgroups) slots = n_bgroups;
-  if (slots * L.dirs > kRnnSyncCounters) slots = kRnnSyncCounters / L.dirs;
+  if (g_tune.rnn_max_slots.load() > 0 && slots > g_tune.rnn_max_slots.load()) slots = g_tune.rnn_max_slots.load();
   if (slots < 1) slots = 1;
+  int nif = cdiv(n_bgroups, slots);          // groups per CTA set; up to RT_MAX_NIF of them in flight
+  if (nif > rnn_tc_max_in_flight()) nif = rnn_tc_max_in_flight();
+  while (slots > 1 && L.dirs * slots * nif > kRnnMaxCounters) --slots;
   DSB_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(__nv_bfloat16) * rnn_tc_hbuf_elems(L, B), st));
   DSB_CUDA(cudaMemsetAsync(sync_words, 0, sizeof(unsigned int) * kRnnSyncCounters, st));   // step counters only; abort flag is sticky
   if (h0) {
@@ -732,10 +808,16 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.small_groups = small_groups;
   const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates), small_groups).total;
   static const int split_env = getenv("DSB_RNN_SPLIT") ? atoi(getenv("DSB_RNN_SPLIT")) : 1;
-  const void* fn = L.gates == 3 ? ((BP == 64 && split_env) ? (const void*)rnn_tc_kernel<3, true> : (const void*)rnn_tc_kernel<3>)
-                   : L.gates == 4 ? (const void*)rnn_tc_kernel<4> : (const void*)rnn_tc_kernel<1>;
+  const bool split = L.gates == 3 && BP == 64 && split_env;
+  const void* fn = nullptr;
+#define RT_PICK(G, S)                                                                          \
+  fn = nif == 1 ? (const void*)rnn_tc_kernel<G, S, 1> : nif == 2 ? (const void*)rnn_tc_kernel<G, S, 2> \
+                                                                 : (const void*)rnn_tc_kernel<G, S, 3>
+  if (L.gates == 3) { if (split) RT_PICK(3, true); else RT_PICK(3, false); }
+  else if (L.gates == 4) RT_PICK(4, false);
+  else RT_PICK(1, false);
+#undef RT_PICK
   DSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int dirs_per_launch = L.dirs / launches;
   static const bool debug = getenv("DSB_RNN_DEBUG") != nullptr;
   unsigned long long* dbg = nullptr;
   const int grid = dirs_per_launch * slots * cpd;
@@ -744,10 +826,6 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     DSB_CUDA(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 128 * grid, st));
   }
   p.dbg = dbg;
-  static const int cl_env = getenv("DSB_RNN_CLUSTER") ? atoi(getenv("DSB_RNN_CLUSTER")) : 1;   // multicast clusters measured 2 % slower
-  int cl = 1;
-  for (int c2 = cl_env; c2 >= 2; c2 >>= 1)
-    if (cpd % c2 == 0) { cl = c2; break; }
   for (int l = 0; l < launches; ++l) {
     p.dir0 = l * dirs_per_launch;
     void* args[] = {(void*)&tw, (void*)&th, (void*)&p};
@@ -756,27 +834,12 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     cfg.blockDim = dim3(RT_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attrs[2];
+    cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeCooperative;          // all CTAs co-resident (they spin on each other)
     attrs[0].val.cooperative = 1;
-    attrs[1].id = cudaLaunchAttributeClusterDimension;
-    attrs[1].val.clusterDim.x = cl;
-    attrs[1].val.clusterDim.y = 1;
-    attrs[1].val.clusterDim.z = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = cl > 1 ? 2 : 1;
-    cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
-    if (le != cudaSuccess && cl > 1) {   // cluster + cooperative rejected: fall back to unicast TMA
-      (void)cudaGetLastError();
-      static bool warned = false;
-      if (!warned) {
-        fprintf(stderr, "[danspeech_b200] cluster launch of the recurrence failed (%s); using cluster size 1\n",
-                cudaGetErrorString(le));
-        warned = true;
-      }
-      cfg.numAttrs = 1;
-      le = cudaLaunchKernelExC(&cfg, fn, args);
-    }
+    cfg.numAttrs = 1;
+    const cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
     if (le != cudaSuccess)
       return set_error(DSB_ERR_CUDA, "rnn_layer_tc: launch failed: %s", cudaGetErrorString(le));
     count_launch();
@@ -789,10 +852,11 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     const char* names[12] = {"prod.spin", "prod.fence", "prod.issue", "mma.wait_first", "mma.rest", "epi.gload",
                              "epi.wait_mma", "epi.math_store", "epi.bar", "epi.publish", "mma.wait_rest",
                              "prod.wait_empty"};
-    fprintf(stderr, "[rnn_tc debug] H=%d B=%d Tmax=%d grid=%d  cycles/step (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid);
+    const int items = cdiv(n_bgroups, slots) * Tmax;   // (step, group) items per CTA (upper bound for ragged groups)
+    fprintf(stderr, "[rnn_tc debug] H=%d B=%d Tmax=%d grid=%d groups=%d slots=%d in flight=%d  cycles/item (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid, n_bgroups, slots, nif);
     for (int k = 0; k < 12; ++k) {
       double sum = 0, mx = 0;
-      for (int c = 0; c < grid; ++c) { double v = (double)h[c * 128 + k] / Tmax; sum += v; mx = v > mx ? v : mx; }
+      for (int c = 0; c < grid; ++c) { double v = (double)h[c * 128 + k] / items; sum += v; mx = v > mx ? v : mx; }
       fprintf(stderr, "   %-16s %9.0f | %9.0f\n", names[k], sum / grid, mx);
     }
     for (int c = 0; c < grid; c += grid / 2 + 1) {   // step-100 timeline of two CTAs (cycles since this CTA published step 99)

@@ -46,6 +46,18 @@ void dsb_profile_enable(int on);
 void dsb_profile_reset(void);
 int dsb_profile_read(int stage, double* total_ms, int* spans);
 
+/* Diagnostic tuning knobs (process-wide integers; defaults are the production settings, nothing needs to be set).
+ * They exist for A/B measurements and for tests that force a code path on small shapes; the reference has no
+ * equivalent (its only knobs are constructor kwargs, danspeech/DanSpeechRecognizer.py:15-17).
+ *   "rnn_in_flight"  1..3  batch groups of 64 sequences in flight per CTA in the persistent recurrence (default 3;
+ *                          1 = one group of up to 128 rows at a time)
+ *   "rnn_max_slots"  >= 0  cap on the independent CTA sets of the recurrence (0 = as many as fit, default)
+ *   "gx_bf16"        0/1   gate pre-activations of the input projection stored as bf16 (default 0 = fp32)
+ * dsb_tune_set returns DSB_ERR_INVALID for an unknown key or an out-of-range value; dsb_tune_get returns the value
+ * or -1 for an unknown key. */
+int dsb_tune_set(const char* key, int value);
+int dsb_tune_get(const char* key);
+
 /* ------------------------------------------------------------------------- *
  * Spectrogram (replaces danspeech/audio/parsers.py:50-72,
  * SpectrogramAudioParser.parse_audio: librosa.stft(n_fft=320, hop=160, symmetric

@@ -566,3 +566,108 @@ def test_recognize_more_example_wavs_matches_reference(name):
     assert rel_err(spect[[3, 80]].cpu().numpy(), g["spect_rows_" + name]) < FP32_TOL
     probs, sizes = m.cuda()(spect.view(1, 1, 161, -1), torch.IntTensor([spect.size(1)]))
     assert logit_rel_err(probs[0, [0, -1]].cpu().numpy(), g["probs_ends_" + name]) < FP32_TOL
+
+
+# ------------------------------------------------------------------ recurrence: batch groups in flight
+@pytest.fixture
+def one_cta_set():
+    """Forces the persistent recurrence onto ONE CTA set per direction, so that the groups of 64 sequences queue on
+    it and run in flight together (small test models would otherwise spread the groups over idle SMs)."""
+    from danspeech_b200 import _native as N
+    prev = N.tune(rnn_max_slots=1)
+    yield N
+    N.tune(**prev)
+
+
+@pytest.mark.parametrize("rnn_type,B", [("gru", 150), ("gru", 400), ("lstm", 150), ("rnn", 130)])
+def test_recurrence_groups_in_flight(one_cta_set, rnn_type, B):
+    """Groups of 64 sequences in flight per CTA (2, 3, and several waves of 3 with a ragged tail) against the oracle on
+    single utterances and against the one-group-at-a-time schedule of the same kernels."""
+    N = one_cta_set
+    kw = dict(rnn_hidden_size=64, rnn_layers=2, rnn_type=rnn_type)
+    if rnn_type == "lstm":
+        kw["ih_scale"] = 2.5
+    cfg = case_config("TestModel", kw)
+    sd = syn.make_state_dict(seed=12, **cfg)
+    m = _model("TestModel", kw, seed=12, precision="bf16")
+    p = osp.SpectrogramOracle()
+    kinds = [p.parse_audio(syn.synthetic_audio(n, seed=400 + i)) for i, n in enumerate((4000, 3100, 2500, 900))]
+    cuts = [B // 3, B // 2, B - 20, B]                  # ragged: four lengths, boundaries not on multiples of 64
+    which = [next(j for j, c in enumerate(cuts) if b < c) for b in range(B)]
+    x = torch.zeros(B, 1, 161, kinds[0].size(1))
+    for b, j in enumerate(which):
+        x[b, 0, :, : kinds[j].size(1)] = kinds[j]
+    xl = torch.IntTensor([kinds[j].size(1) for j in which])
+    probs, sizes = m(x.cuda(), xl)
+    torch.cuda.synchronize()
+    prev = N.tune(rnn_in_flight=1)
+    try:
+        base, _ = m(x.cuda(), xl)
+        torch.cuda.synchronize()
+    finally:
+        N.tune(**prev)
+    refs = {}
+    for b in sorted({0, 63, 64, 127, 128, cuts[0] - 1, cuts[0], cuts[1], cuts[2] - 1, cuts[2], B - 1}):
+        if b >= B:
+            continue
+        j = which[b]
+        if j not in refs:
+            one = kinds[j].view(1, 1, 161, -1)
+            refs[j] = om.forward(sd, one, torch.IntTensor([one.size(3)]), cfg["conv_layers"], cfg["rnn_layers"],
+                                 rnn_type=rnn_type)
+        ref, rs = refs[j]
+        L = int(sizes[b])
+        assert L == int(rs[0])
+        assert logit_rel_err(probs[b, :L].cpu().numpy(), ref[0, :L].numpy()) < BF16_TOL, b
+        assert logit_rel_err(probs[b, :L].cpu().numpy(), base[b, :L].cpu().numpy()) < 1e-4, b
+
+
+def test_streaming_bf16_groups_in_flight_carry_state(one_cta_set):
+    """200 lock-step streams on one CTA set = 4 groups of 64, three in flight + one more wave; the hidden state is
+    carried across chunks per stream (h0 / hT of every group)."""
+    from danspeech_b200.audio.parsers import InferenceSpectrogramAudioParser
+    m = _model("CPUStreamingRNN", dict(rnn_hidden_size=96, rnn_layers=2), seed=6, precision="bf16")
+    S, K = 200, 3
+    auds = [syn.synthetic_audio(8640 + 6240 * 3, seed=70 + i) for i in range(K)]
+    specs = []
+    for a in auds:
+        sp = InferenceSpectrogramAudioParser()
+        specs.append([sp.parse_audio(c, is_last=(i == 3)) for i, c in enumerate(_stream_chunks(a))])
+    solo = [[] for _ in range(K)]
+    for s in range(K):
+        for i in range(4):
+            o = m(specs[s][i].view(1, 1, 161, -1), i == 0, i == 3)
+            solo[s].append(None if o is None else o.clone())
+    for i in range(4):
+        x = torch.stack([specs[s % K][i] for s in range(S)]).view(S, 1, 161, -1)
+        o = m(x, i == 0, i == 3)
+        for s in (0, 1, 2, 63, 64, 127, 128, 191, 192, 199):
+            if solo[s % K][i] is None:
+                assert o is None
+            else:
+                assert logit_rel_err(o[s].cpu().numpy(), solo[s % K][i][0].cpu().numpy()) < 2e-3
+
+
+def test_recognize_batches_merged_passes_equal_single_batches():
+    """recognize_batches runs up to three batches through one pass of the model; transcripts must equal the
+    one-batch-per-pass results, for lists of recordings and for pinned (tensor, n_samples) batches."""
+    from danspeech_b200 import Recognizer
+    from danspeech_b200.pretrained_models import build_model
+    rng = np.random.default_rng(11)
+    r = Recognizer(model=build_model("TestModel", seed=0, rnn_hidden_size=160, rnn_layers=3).set_precision("bf16"))
+    batches = [[syn.synthetic_audio(int(n), seed=900 + 40 * k + i) for i, n in
+                enumerate(rng.integers(8000, 50000, size=sz))] for k, sz in enumerate((20, 33, 7, 64, 5))]
+    single = r.recognize_batches(batches, merge=1)
+    assert [len(x) for x in single] == [20, 33, 7, 64, 5]
+    assert single[1] == r.recognize_batch(batches[1])
+    for merge in (2, 3):
+        assert r.recognize_batches(batches, merge=merge) == single
+    eng = r.danspeech_recognizer
+    pinned = []
+    for b in batches[:3]:
+        order = sorted(range(len(b)), key=lambda i: -len(b[i]))
+        host, ns = eng.audio_parser.stage_batch([b[i] for i in order], slot=7 + len(pinned))
+        pinned.append(((host.clone().pin_memory(), ns), order))
+    got = r.recognize_batches([p for p, _ in pinned], merge=3)
+    for (p, order), res, ref in zip(pinned, got, single):
+        assert [res[pos] for pos in range(len(order))] == [ref[i] for i in order]
