@@ -253,7 +253,12 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     // one step of one group: `steps_before` = steps this group-in-flight index has completed in earlier waves
     auto item = [&](int i, int s, int bg, unsigned steps_before) -> bool {
       long long c0 = clock64();
-      const int pre = min(gps, n_groups);
+      // One group at a time: arm first, so that after the barrier only the proxy fence and the TMA issues remain on
+      // the critical path.  Several groups in flight: the barrier of this item is usually open already (its group
+      // published while the other groups ran), and the ring slots only free up as the MMAs of the previous item
+      // complete -- poll FIRST, so that the loads go out the moment a slot is free and the MMA warp does not sit
+      // through an L2 round trip between two items.
+      const int pre = NIF == 1 ? min(gps, n_groups) : 0;
       for (int g = 0; g < pre; ++g)
         if (!arm_group()) return false;
       d_empty += clock64() - c0;
@@ -435,6 +440,17 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         }
       }
       if (half == 0 && lane < rpq) sT[lrow] = active ? t : -1;
+      if (NIF > 1 && row_ok && s + 1 < len) {
+        // With several groups in flight the loads above are no longer hidden behind this group's MMA wait; the
+        // pre-activations of the group's NEXT step are pulled into L2 now, one round of items ahead.
+        const int tn = dir == 0 ? s + 1 : len - 2 - s;
+        const float* gn = p.gx + ((size_t)tn * p.B + b) * ncol + (size_t)dir * GATES * p.H + j0;
+#pragma unroll
+        for (int g = 0; g < GATES; ++g) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)g * p.H));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)g * p.H + (UH - 1)));
+        }
+      }
       long long e1 = clock64();
       const bool ok = wait_abortable(&dfull[i], (uint32_t)((steps_before + (unsigned)s) & 1u), p.abort_flag);
       long long e2 = clock64();
