@@ -98,7 +98,8 @@ class DanSpeechRecognizer(object):
         self.string_parts = bool(return_string_parts)
 
     def disable_streaming(self, keep_secondary_model=False):
-        self.audio_parser = SpectrogramAudioParser(self.audio_config, device=self.device)
+        self.audio_parser = SpectrogramAudioParser(self.audio_config, device=self.device,
+                                                   fast_fft=getattr(self.model, "precision", "fp32") == "bf16")
         self.greedy_decoder = None
         self.reset_streaming_params()
         self.string_parts = False
@@ -145,7 +146,13 @@ class DanSpeechRecognizer(object):
 
     # ------------------------------------------------------------------ offline (DanSpeechRecognizer.py:218-231)
     def transcribe(self, recording, show_all=False):
-        spect, input_sizes = self.audio_parser.parse_batch([recording])
+        if hasattr(self.audio_parser, "parse_batch"):
+            spect, input_sizes = self.audio_parser.parse_batch([recording])
+        else:
+            # real-time streaming is enabled: like the reference (DanSpeechRecognizer.py:218-222) the recording goes
+            # through whatever parser is installed, here the streaming one with its adaptive normalisation
+            s = self.audio_parser.parse_audio(recording)
+            spect, input_sizes = s.view(1, 1, s.size(0), s.size(1)), torch.IntTensor([s.size(1)])
         out, output_sizes = self.model(spect, input_sizes)
         decoded_output, _ = self.decoder.decode(out, output_sizes)
         if show_all:

@@ -60,11 +60,17 @@ def build_native(verbose=True):
         results = list(ex.map(_compile, srcs))
     objs = [o for o, _ in results]
     rebuilt = any(c for _, c in results)
+    link_stamp = LIB + ".objs"
+    obj_list = "\n".join(objs)
+    if not os.path.exists(link_stamp) or open(link_stamp).read() != obj_list:
+        rebuilt = True                    # a source file was added or removed
     if rebuilt or not os.path.exists(LIB):
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+        with open(link_stamp, "w") as f:
+            f.write(obj_list)
     if verbose:
         print("[danspeech_b200] %s (%s)" % (LIB, "rebuilt" if rebuilt else "up to date"), file=sys.stderr)
     return LIB

@@ -38,7 +38,7 @@ _SIGS = {
     "dsb_spectrogram_s16": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p,
                                     c_void_p, c_int, c_void_p]),
     "dsb_spectrogram_stream_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p,
-                                           c_void_p, c_void_p]),
+                                           c_void_p, c_int, c_void_p]),
     "dsb_spectrogram_stream_normalize": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "dsb_spectrogram_stream_running_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_double,
                                                      c_void_p]),

@@ -17,7 +17,8 @@ import torch
 
 from .. import _native as N
 
-_SUPPORTED_WINDOWS = ("hamming",)
+# audio_conf["window"] -> DSB_SPECT_WINDOW_* (the four scipy.signal windows of parsers.py:9-10)
+_WINDOW_FLAGS = {"hamming": 0 << 4, "hann": 1 << 4, "blackman": 2 << 4, "bartlett": 3 << 4}
 
 _convert_pool = None
 
@@ -45,10 +46,13 @@ class AudioParser(ABC):
         self.window_size = self.audio_config.get("window_size", 0.02)
         self.n_fft = int(self.sampling_rate * self.window_size)
         self.hop_length = int(self.sampling_rate * self.window_stride)
-        if self.window not in _SUPPORTED_WINDOWS or self.n_fft != 320 or self.hop_length != 160:
+        if self.window not in _WINDOW_FLAGS:
+            raise KeyError(self.window)          # the reference's windows.get() gives None and dies inside librosa
+        if self.n_fft != 320 or self.hop_length != 160:
             raise NotImplementedError(
-                "danspeech_b200 spectrogram kernel is specialised for the DanSpeech audio config "
-                "(16 kHz, hamming, 20 ms / 10 ms); got %r" % (self.audio_config,))
+                "danspeech_b200 spectrogram kernel is specialised for the DanSpeech framing "
+                "(16 kHz, 20 ms window / 10 ms stride); got %r" % (self.audio_config,))
+        self._window_flag = _WINDOW_FLAGS[self.window]
 
     @abstractmethod
     def parse_audio(self, recording):
@@ -86,7 +90,7 @@ class SpectrogramAudioParser(AudioParser):
         partials = torch.empty((B, L.dsb_spectrogram_partials(out_stride), 2), dtype=torch.float64, device=audio.device)
         N.check(L.dsb_spectrogram_f32(N.ptr(audio), stride, N.ptr(n_samples), B, int(max_samples), N.ptr(out),
                                       out_stride, N.ptr(mean_std), N.ptr(partials),
-                                      (1 if self.normalize else 0) | (2 if self.fast_fft else 0),
+                                      (1 if self.normalize else 0) | (2 if self.fast_fft else 0) | self._window_flag,
                                       N.current_stream()), "dsb_spectrogram_f32")
         return out, mean_std
 
@@ -171,8 +175,8 @@ class SpectrogramAudioParser(AudioParser):
         partials = torch.empty((B, L.dsb_spectrogram_partials(frames), 2), dtype=torch.float64, device=dev)
         N.check(L.dsb_spectrogram_s16(N.ptr(pcm), ch, stride, N.ptr(n_dev), B, max(ns), N.ptr(out), frames,
                                       N.ptr(mean_std), N.ptr(partials),
-                                      (1 if self.normalize else 0) | (2 if self.fast_fft else 0), N.current_stream()),
-                "dsb_spectrogram_s16")
+                                      (1 if self.normalize else 0) | (2 if self.fast_fft else 0) | self._window_flag,
+                                      N.current_stream()), "dsb_spectrogram_s16")
         lengths = torch.IntTensor([1 + n // self.hop_length for n in ns])
         return out.view(B, 1, 161, frames), lengths
 
@@ -234,7 +238,7 @@ class InferenceSpectrogramAudioParser(AudioParser):
         stats = torch.empty((1, 2), dtype=torch.float64, device=dev)
         partials = torch.empty((1, L.dsb_spectrogram_partials(frames), 2), dtype=torch.float64, device=dev)
         N.check(L.dsb_spectrogram_stream_f32(N.ptr(audio), stride, N.ptr(n_dev), 1, n, N.ptr(out), frames,
-                                             N.ptr(stats), N.ptr(partials), N.current_stream()),
+                                             N.ptr(stats), N.ptr(partials), self._window_flag, N.current_stream()),
                 "dsb_spectrogram_stream_f32")
         chunk_mean, chunk_std = stats[0].tolist()
 

@@ -106,5 +106,5 @@ extern "C" int dsb_tune_get(const char* key) {
 }
 
 extern "C" const char* dsb_last_error(void) { return dsb::g_err; }
-extern "C" int dsb_abi_version(void) { return 1; }
+extern "C" int dsb_abi_version(void) { return 2; }
 extern "C" uint64_t dsb_kernel_launch_count(void) { return dsb::g_launches.load(); }

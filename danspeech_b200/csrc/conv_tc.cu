@@ -328,11 +328,8 @@ static int launch_conv(const __nv_bfloat16* x, const ConvLayer& L, const ConvTcP
   uint64_t sw[3] = {2, frame, (uint64_t)NOUT * frame};
   uint32_t bw[3] = {CIN, NOUT, S::FIRST ? (uint32_t)CV_G1 : (uint32_t)kConvKW};
   if (int e = make_tmap_bf16(&tw, L.w_tc, 3, dw, sw, bw, swz)) return e;
-  static bool attr = false;
-  if (!attr) {
-    DSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NOUT, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr = true;
-  }
+  // per device (and a cheap host-side call): set on every launch, not once per process
+  DSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NOUT, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -388,11 +388,8 @@ static int launch_gemm2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16
   uint64_t dimsB[2] = {(uint64_t)K, (uint64_t)N}, strB[2] = {2, (uint64_t)ldw * 2};
   uint32_t boxB[2] = {BK, BN / 2};
   if (int e = make_tmap_bf16(&tb, W, 2, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  static bool attr = false;
-  if (!attr) {
-    DSB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::TOTAL));
-    attr = true;
-  }
+  // per device (and a cheap host-side call): set on every launch, not once per process
+  DSB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<BN>::TOTAL));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -414,11 +411,8 @@ static int launch_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16*
   uint64_t dimsB[2] = {(uint64_t)K, (uint64_t)N}, strB[2] = {2, (uint64_t)ldw * 2};
   uint32_t boxB[2] = {BK, BN};
   if (int e = make_tmap_bf16(&tb, W, 2, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  static bool attr = false;
-  if (!attr) {
-    DSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
-    attr = true;
-  }
+  // per device (and a cheap host-side call): set on every launch, not once per process
+  DSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

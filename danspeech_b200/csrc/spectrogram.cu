@@ -41,7 +41,7 @@ template <> struct V2<double> { typedef double2 type; };
 template <> struct V2<float> { typedef float2 type; };
 template <typename T>
 struct SpecTablesT {
-  T window[kNfft];                       // symmetric Hamming
+  T window[4][kNfft];                    // symmetric hamming, hann, blackman, bartlett (scipy.signal, parsers.py:9-10)
   typename V2<T>::type tw160[5][32];     // W160^(lane*k1)
   typename V2<T>::type tw32[4][32];      // radix-2 DIF stage twiddles, halves 16, 8, 4, 2
   typename V2<T>::type tw320[kBins + 3]; // W320^k, k = 0..160
@@ -53,13 +53,22 @@ template <typename T> __device__ __forceinline__ const SpecTablesT<T>& tables();
 template <> __device__ __forceinline__ const SpecTablesT<double>& tables<double>() { return g_tab; }
 template <> __device__ __forceinline__ const SpecTablesT<float>& tables<float>() { return g_tabf; }
 
-static std::once_flag g_tab_once;
-static cudaError_t g_tab_err = cudaSuccess;
+// The tables live in __device__ symbols, i.e. once per device: uploaded on first use of every device.
+static std::mutex g_tab_mu;
+static bool g_tab_done[64] = {false};
 
-static void init_tables() {
+static cudaError_t init_tables() {
   static SpecTables h;
+  cudaError_t g_tab_err = cudaSuccess;
   const double PI = 3.14159265358979323846;
-  for (int k = 0; k < kNfft; ++k) h.window[k] = 0.54 - 0.46 * cos(2.0 * PI * k / (kNfft - 1));
+  for (int k = 0; k < kNfft; ++k) {
+    // scipy.signal.{hamming,hann,blackman,bartlett}(320), sym=True (librosa calls the window function with win_length)
+    const double x = 2.0 * PI * k / (kNfft - 1);
+    h.window[0][k] = 0.54 - 0.46 * cos(x);
+    h.window[1][k] = 0.5 - 0.5 * cos(x);
+    h.window[2][k] = 0.42 - 0.5 * cos(x) + 0.08 * cos(2.0 * x);
+    h.window[3][k] = 1.0 - fabs(2.0 * k / (kNfft - 1) - 1.0);
+  }
   for (int k1 = 0; k1 < 5; ++k1)
     for (int l = 0; l < 32; ++l) {
       double a = -2.0 * PI * (double)(l * k1) / 160.0;
@@ -78,13 +87,15 @@ static void init_tables() {
   }
   g_tab_err = cudaMemcpyToSymbol(g_tab, &h, sizeof(h));
   static SpecTablesT<float> hf;
-  for (int k = 0; k < kNfft; ++k) hf.window[k] = (float)h.window[k];
+  for (int w = 0; w < 4; ++w)
+    for (int k = 0; k < kNfft; ++k) hf.window[w][k] = (float)h.window[w][k];
   for (int a = 0; a < 5; ++a)
     for (int l = 0; l < 32; ++l) hf.tw160[a][l] = make_float2((float)h.tw160[a][l].x, (float)h.tw160[a][l].y);
   for (int a = 0; a < 4; ++a)
     for (int l = 0; l < 32; ++l) hf.tw32[a][l] = make_float2((float)h.tw32[a][l].x, (float)h.tw32[a][l].y);
   for (int k = 0; k < kBins + 3; ++k) hf.tw320[k] = make_float2((float)h.tw320[k].x, (float)h.tw320[k].y);
   if (g_tab_err == cudaSuccess) g_tab_err = cudaMemcpyToSymbol(g_tabf, &hf, sizeof(hf));
+  return g_tab_err;
 }
 
 template <typename C, typename T>
@@ -152,7 +163,7 @@ template <int MODE, typename T, bool S16>
 __global__ void __launch_bounds__(kWarps * 32)
 spectrogram_kernel(const void* __restrict__ audio_v, int channels, int64_t audio_stride, const int32_t* __restrict__ n_samples,
                    float* __restrict__ out, int64_t out_stride, float* __restrict__ mean_std_out,
-                   double* __restrict__ partials, int n_partials, int center, int normalize) {
+                   double* __restrict__ partials, int n_partials, int center, int normalize, int window) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef typename V2<T>::type T2;
   typedef SpecSmemT<T> SpecSmem;
@@ -217,7 +228,7 @@ spectrogram_kernel(const void* __restrict__ audio_v, int channels, int64_t audio
         sm.samples[i] = v;
       }
     }
-    for (int i = tid; i < kNfft; i += kWarps * 32) sm.window[i] = g_tab.window[i];
+    for (int i = tid; i < kNfft; i += kWarps * 32) sm.window[i] = g_tab.window[window][i];
     for (int i = tid; i < kBins + 3; i += kWarps * 32) sm.tw320[i] = g_tab.tw320[i];
   }
   // per-lane twiddles (registers)
@@ -405,26 +416,30 @@ __global__ void stream_normalize_kernel(float* __restrict__ spect, int64_t out_s
 }
 
 static int ensure_tables() {
-  std::call_once(g_tab_once, init_tables);
-  if (g_tab_err != cudaSuccess)
-    return set_error(DSB_ERR_CUDA, "spectrogram table upload failed: %s", cudaGetErrorString(g_tab_err));
+  int dev = 0;
+  DSB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  if (dev < 0 || dev >= 64) return set_error(DSB_ERR_UNSUPPORTED, "spectrogram: device ordinal %d", dev);
+  if (!g_tab_done[dev]) {
+    const cudaError_t e = init_tables();
+    if (e != cudaSuccess)
+      return set_error(DSB_ERR_CUDA, "spectrogram table upload failed: %s", cudaGetErrorString(e));
+    g_tab_done[dev] = true;
+  }
   return 0;
 }
 
 template <int MODE, typename T, bool S16 = false>
 static int launch_spec(const void* audio, int channels, int64_t audio_stride, const int32_t* d_n, int B, float* out,
                        int64_t out_stride, float* mean_std, double* partials, int n_partials, int tiles, int center,
-                       int normalize, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DSB_CUDA(cudaFuncSetAttribute(spectrogram_kernel<MODE, T, S16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(SpecSmemT<T>)));
-    attr_set = true;
-  }
+                       int normalize, int window, cudaStream_t st) {
+  // per device and cheap (a host-side table update): set on every launch rather than once per process
+  DSB_CUDA(cudaFuncSetAttribute(spectrogram_kernel<MODE, T, S16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(SpecSmemT<T>)));
   dim3 grid(tiles, B);
   spectrogram_kernel<MODE, T, S16><<<grid, kWarps * 32, sizeof(SpecSmemT<T>), st>>>(audio, channels, audio_stride, d_n, out, out_stride,
                                                                       mean_std, partials, n_partials, center,
-                                                                      normalize);
+                                                                      normalize, window);
   DSB_CHECK_LAUNCH();
   return 0;
 }
@@ -442,6 +457,7 @@ static int spectrogram_offline(const void* audio, bool s16, int channels, int64_
                                float* mean_std, double* partials, int flags, void* stream) {
   const int normalize = flags & DSB_SPECT_NORMALIZE;
   const bool fast = (flags & DSB_SPECT_FAST_FFT) != 0;
+  const int window = (flags & DSB_SPECT_WINDOW_MASK) >> DSB_SPECT_WINDOW_SHIFT;
   DSB_REQUIRE(audio && n_samples && out && partials && B > 0, "dsb_spectrogram: null argument or B <= 0");
   DSB_REQUIRE(max_samples >= 1 && max_samples <= audio_stride, "dsb_spectrogram: max_samples %d out of range",
               max_samples);
@@ -460,14 +476,14 @@ static int spectrogram_offline(const void* audio, bool s16, int channels, int64_
   int e;
   if (s16)
     e = fast ? launch_spec<MODE_RAW, float, true>(audio, channels, audio_stride, n_samples, B, out, out_stride, nullptr,
-                                                  partials, n_partials, tiles_all, 1, 0, st)
+                                                  partials, n_partials, tiles_all, 1, 0, window, st)
              : launch_spec<MODE_RAW, double, true>(audio, channels, audio_stride, n_samples, B, out, out_stride, nullptr,
-                                                   partials, n_partials, tiles_all, 1, 0, st);
+                                                   partials, n_partials, tiles_all, 1, 0, window, st);
   else
     e = fast ? launch_spec<MODE_RAW, float, false>(audio, 1, audio_stride, n_samples, B, out, out_stride, nullptr,
-                                                   partials, n_partials, tiles_all, 1, 0, st)
+                                                   partials, n_partials, tiles_all, 1, 0, window, st)
              : launch_spec<MODE_RAW, double, false>(audio, 1, audio_stride, n_samples, B, out, out_stride, nullptr,
-                                                    partials, n_partials, tiles_all, 1, 0, st);
+                                                    partials, n_partials, tiles_all, 1, 0, window, st);
   if (e) return e;
   if (!normalize) return 0;
   stream_stats_kernel<<<cdiv(B, 128), 128, 0, st>>>(partials, n_partials, n_samples, nullptr, B, 1, normalize,
@@ -499,7 +515,7 @@ extern "C" int dsb_spectrogram_s16(const int16_t* audio, int channels, int64_t a
 
 extern "C" int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int S,
                                           int max_samples, float* out, int64_t out_stride, double* stats,
-                                          double* partials, void* stream) {
+                                          double* partials, int flags, void* stream) {
   DSB_REQUIRE(audio && n_samples && out && partials && stats && S > 0, "dsb_spectrogram_stream_f32: null argument");
   DSB_REQUIRE(max_samples >= kNfft && max_samples <= audio_stride,
               "dsb_spectrogram_stream_f32: max_samples %d out of range", max_samples);
@@ -509,7 +525,8 @@ extern "C" int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stri
   DSB_REQUIRE(out_stride >= max_frames, "dsb_spectrogram_stream_f32: out_stride too small");
   const int n_partials = dsb_spectrogram_partials((int)out_stride);
   if (int e = launch_spec<MODE_RAW, double, false>(audio, 1, audio_stride, n_samples, S, out, out_stride, nullptr, partials,
-                                    n_partials, cdiv((int)out_stride, kFT), 0, 0, st))
+                                    n_partials, cdiv((int)out_stride, kFT), 0, 0,
+                                    (flags & DSB_SPECT_WINDOW_MASK) >> DSB_SPECT_WINDOW_SHIFT, st))
     return e;
   stream_stats_kernel<<<cdiv(S, 128), 128, 0, st>>>(partials, n_partials, n_samples, stats, S, 0, 1, nullptr,
                                                    audio_stride);

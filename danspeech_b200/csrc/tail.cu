@@ -204,11 +204,8 @@ int fc_softmax_argmax_f32(const float* x, const float* W, const float* bias, flo
   const int Hp = (H + 127) / 128 * 128;
   const size_t smem = ((size_t)NC * Hp + FC_WARPS * R * NC) * sizeof(float);
   if (C <= NC && (H & 3) == 0 && smem <= 227 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-    static bool attr = false;
-    if (!attr) {
-      DSB_CUDA(cudaFuncSetAttribute(fc_softmax_argmax_kernel<NC, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr = true;
-    }
+    // per device (and a cheap host-side call): set on every launch, not once per process
+    DSB_CUDA(cudaFuncSetAttribute(fc_softmax_argmax_kernel<NC, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int64_t groups = ((int64_t)T * B + R - 1) / R;
     const int grid = (int)(cdiv64(groups, FC_WARPS) < 148 ? cdiv64(groups, FC_WARPS) : 148);
     fc_softmax_argmax_kernel<NC, R><<<grid, FC_WARPS * 32, smem, st>>>(x, W, bias, probs, argmax, T, B, C, H, Hp);

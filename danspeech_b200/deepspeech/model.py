@@ -248,14 +248,19 @@ class DeepSpeech(nn.Module):
         x = x.to(device=dev, dtype=torch.float32).contiguous()
         S, k = x.size(0), x.size(3)
         with torch.cuda.device(dev):
-            key = (S,)
-            if self._stream_state is None or self._stream_key != key:
+            if self._stream_state is not None and self._stream_key[0] == S and k > self._stream_key[1] and not is_first:
+                raise N.NativeError("streaming chunk of %d frames exceeds the %d frames this stream's state was sized "
+                                    "for; start the stream (is_first) with the largest chunk or call "
+                                    "reserve_stream_frames()" % (k, self._stream_key[1]))
+            if self._stream_state is None or self._stream_key[0] != S or k > self._stream_key[1]:
+                # (re)size the per-stream state: the reference accepts any chunk length (model.py:517-537)
                 if self._stream_state is not None:
                     L.dsb_stream_state_destroy(self._stream_state)
                     self._stream_state = None
+                max_k = max(512, getattr(self, "_stream_reserve", 0), k)
                 st = N.c_void_p()
-                N.check(L.dsb_stream_state_create(h, S, 512, st), "dsb_stream_state_create")
-                self._stream_state, self._stream_key = st, key
+                N.check(L.dsb_stream_state_create(h, S, max_k, st), "dsb_stream_state_create")
+                self._stream_state, self._stream_key = st, (S, max_k)
             k_max = L.dsb_stream_max_out_frames(self._stream_state, k)
             flat = torch.empty((S * max(k_max, 1) * len(self.labels),), dtype=torch.float32, device=dev)
             k_out = N.c_int32(0)
@@ -267,11 +272,18 @@ class DeepSpeech(nn.Module):
         C = len(self.labels)
         return flat[: S * k_out.value * C].view(S, k_out.value, C)
 
+    def reserve_stream_frames(self, max_chunk_frames):
+        """Sizes the streaming state for chunks of up to ``max_chunk_frames`` spectrogram frames (default 512 = 5.1 s)."""
+        self._stream_reserve = int(max_chunk_frames)
+        return self
+
     # ------------------------------------------------------------------ (de)serialisation
     @classmethod
-    def load_model(cls, path):
-        """model.py:599-624.  Reference packages are plain pickles of tensors, str and dict."""
-        package = torch.load(path, map_location=lambda storage, loc: storage, weights_only=False)
+    def load_model(cls, path, trust_pickle=False):
+        """model.py:599-624.  Reference packages are plain pickles of tensors, str, int, bool, list and (ordered)
+        dict, which the restricted unpickler of ``weights_only=True`` accepts; ``trust_pickle=True`` opts into full
+        unpickling for a package from a trusted source that carries other objects."""
+        package = torch.load(path, map_location=lambda storage, loc: storage, weights_only=not trust_pickle)
         return cls.load_model_package(package)
 
     @classmethod

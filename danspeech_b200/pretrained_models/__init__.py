@@ -1,10 +1,16 @@
 """Model factories with the reference's names (danspeech/pretrained_models/__init__.py:1-30).
 
-The reference factories download a ``.pth`` release artefact (e.g. danspeech_primary.py:22-24) which is
-impossible offline, so each factory here builds the *named architecture*  and, unless a
-``model_path`` to a reference package is given, fills it with seeded random weights
-(``utils.synthetic.make_state_dict``).  ``CustomModel(path)`` loads a real reference package.
+The reference factories download a ``.pth`` release artefact into ``~/.danspeech/models`` and load it
+(e.g. danspeech_primary.py:22-24, utils/data_utils.py:43-88).  There is no downloading here: a factory loads the
+package the reference would have cached -- ``<cache_dir or ~/.danspeech/models>/<file>.pth`` -- or an explicit
+``model_path``, and raises ``FileNotFoundError`` when neither exists, so that ``Recognizer(model=DanSpeechPrimary())``
+can never silently transcribe with random weights.  Seeded random weights of the *named architecture* (SURVEY A.6;
+what tests and bench.py use, since the artefacts cannot be fetched offline) are an explicit opt-in:
+``build_model(name, seed=...)`` or ``DanSpeechPrimary(synthetic=True)`` / ``DanSpeechPrimary(seed=0)``.
+``CustomModel(path)`` loads a real reference package.
 """
+import os
+
 import torch.nn as nn
 
 from ..deepspeech.model import DeepSpeech, supported_rnns
@@ -25,11 +31,27 @@ def build_model(name, model_path=None, seed=0, rnn_type="gru", **overrides):
     return model
 
 
+# factory name -> cached file name, as published by the reference (pretrained_models/*.py)
+_PUBLISHED = {"EnglishLibrispeech": "Librispeech.pth"}
+
+
 def _factory(name):
-    def make(cache_dir=None, model_path=None, seed=0):
-        return build_model(name, model_path=model_path, seed=seed)
-    make.__name__ = name
-    make.__doc__ = "%s-shaped DeepSpeech model (random-init unless model_path is given)." % name
+    def make(cache_dir=None, model_path=None, seed=None, synthetic=False):
+        if model_path:
+            return DeepSpeech.load_model(model_path)
+        if synthetic or seed is not None:
+            return build_model(name, seed=seed or 0)
+        root = cache_dir if cache_dir is not None else os.path.join(os.path.expanduser("~"), ".danspeech", "models")
+        path = os.path.join(root, _PUBLISHED.get(name, name + ".pth"))
+        if os.path.isfile(path):
+            return DeepSpeech.load_model(path)
+        raise FileNotFoundError(
+            "%s not found; this package does not download models -- place the reference's release artefact there, "
+            "pass model_path=..., or ask for seeded random weights of this architecture explicitly with "
+            "%s(synthetic=True)" % (path, name))
+    make.__name__ = make.__qualname__ = name
+    make.__doc__ = ("%s: loads <cache_dir or ~/.danspeech/models>/%s (or ``model_path``); ``synthetic=True`` / ``seed=`` "
+                    "builds the architecture with seeded random weights instead." % (name, _PUBLISHED.get(name, name + ".pth")))
     return make
 
 

@@ -77,10 +77,12 @@ class BatchedStreamingParser:
     n_fft, hop = 320, 160
     dataset_mean, dataset_std, alpha_increment = 5.492418704733003, 1.7552755216970917, 0.1
 
-    def __init__(self, n_streams, device="cuda"):
+    def __init__(self, n_streams, device="cuda", audio_config=None):
         N.require_cuda()
+        from .audio.parsers import _WINDOW_FLAGS
         self.S = int(n_streams)
         self.device = torch.device(device)
+        self._window_flag = _WINDOW_FLAGS[(audio_config or {}).get("window", "hamming")]
         self.reset()
 
     def reset(self):
@@ -113,7 +115,8 @@ class BatchedStreamingParser:
         partials = torch.empty((self.S, L.dsb_spectrogram_partials(frames), 2), dtype=torch.float64, device=self.device)
         st = N.current_stream()
         N.check(L.dsb_spectrogram_stream_f32(N.ptr(audio), audio.stride(0), N.ptr(n_dev), self.S, n, N.ptr(out), frames,
-                                             N.ptr(stats), N.ptr(partials), st), "dsb_spectrogram_stream_f32")
+                                             N.ptr(stats), N.ptr(partials), self._window_flag, st),
+                "dsb_spectrogram_stream_f32")
         ms = torch.empty((self.S, 2), dtype=torch.float32, device=self.device)
         N.check(L.dsb_spectrogram_stream_running_stats(N.ptr(self.run), N.ptr(stats), N.ptr(ms), self.S,
                                                        self.dataset_mean, self.dataset_std, self.alpha_increment, st),
@@ -142,7 +145,8 @@ class MultiStreamRecognizer:
         self.greedy_decoder = GreedyDecoder(labels=self.labels, blank_index=self.labels.index("_"))
         self.decoder = decoder            # final-pass decoder (None or a GreedyDecoder == the reference's lm "greedy")
         self.string_parts = bool(string_parts)
-        self.audio_parser = BatchedStreamingParser(self.S, device=self.device)
+        self.audio_parser = BatchedStreamingParser(self.S, device=self.device,
+                                                   audio_config=getattr(self.model, "audio_conf", None))
         self.reset_streaming_params()
 
     def reset_streaming_params(self):
@@ -179,5 +183,11 @@ class MultiStreamRecognizer:
                 elif self.decoder is not None and not isinstance(self.decoder, GreedyDecoder):
                     final = [d[0] for d in self.decoder.decode(torch.cat(self.full_output, dim=1))[0]]
             out = [f if h else "" for f, h in zip(final, heard)]
-            self.reset_streaming_params()
+            # like DanSpeechRecognizer.py:181-214 the state is reset only where something was heard: a stream whose
+            # phrase decoded to fewer than two characters keeps its iterating transcript for the next phrase (the
+            # phrase-level buffers are shared by the lock-step streams and are dropped as soon as any stream was heard)
+            self.iterating_transcript = ["" if h else it for it, h in zip(self.iterating_transcript, heard)]
+            if any(heard):
+                self.full_output = []
+                self.spectrograms = []
         return out

@@ -70,10 +70,18 @@ int dsb_tune_get(const char* key);
  *   partials       device f64 [B, dsb_spectrogram_partials(max_frames), 2] scratch
  *   flags          DSB_SPECT_NORMALIZE: audio_conf["normalize"] (parsers.py:25);
  *                  DSB_SPECT_FAST_FFT: run the transform in fp32 instead of fp64 (errors up to ~2e-3 in weak
- *                  bins: inside the 2e-2 bar of the bf16 mode, outside the 1e-4 bar of the fp32 mode)
+ *                  bins: inside the 2e-2 bar of the bf16 mode, outside the 1e-4 bar of the fp32 mode);
+ *                  DSB_SPECT_WINDOW_*: audio_conf["window"], one of the four scipy.signal windows the reference
+ *                  offers (parsers.py:9-10), symmetric, 320 points; 0 = hamming (the default of deepspeech/utils.py:4)
  * ------------------------------------------------------------------------- */
 #define DSB_SPECT_NORMALIZE 1
 #define DSB_SPECT_FAST_FFT 2
+#define DSB_SPECT_WINDOW_SHIFT 4
+#define DSB_SPECT_WINDOW_MASK (3 << DSB_SPECT_WINDOW_SHIFT)
+#define DSB_SPECT_WINDOW_HAMMING (0 << DSB_SPECT_WINDOW_SHIFT)
+#define DSB_SPECT_WINDOW_HANN (1 << DSB_SPECT_WINDOW_SHIFT)
+#define DSB_SPECT_WINDOW_BLACKMAN (2 << DSB_SPECT_WINDOW_SHIFT)
+#define DSB_SPECT_WINDOW_BARTLETT (3 << DSB_SPECT_WINDOW_SHIFT)
 int dsb_spectrogram_num_frames(int n_samples);                 /* 1 + n/160 */
 int dsb_spectrogram_partials(int max_frames);                  /* scratch rows per utterance */
 int dsb_spectrogram_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int B,
@@ -99,7 +107,7 @@ int dsb_spectrogram_s16(const int16_t* audio, int channels, int64_t audio_stride
  */
 int dsb_spectrogram_stream_f32(const float* audio, int64_t audio_stride, const int32_t* n_samples, int S,
                                int max_samples, float* out, int64_t out_stride, double* stats, double* partials,
-                               void* stream);
+                               int flags /* DSB_SPECT_WINDOW_* only */, void* stream);
 int dsb_spectrogram_stream_normalize(float* spect, int64_t out_stride, const int32_t* n_frames /* device */, int S,
                                      const float* mean_std /* device f32 [S,2] */, void* stream);
 /* The running-statistics recurrence of parsers.py:146-157 kept on the device for S lock-step streams (the

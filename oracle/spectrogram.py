@@ -21,7 +21,22 @@ def hamming_sym(n):
     return 0.54 - 0.46 * np.cos(2.0 * np.pi * k / (n - 1))
 
 
-_WINDOWS = {"hamming": hamming_sym}
+def _cos_window(coeffs):
+    def w(n):
+        x = 2.0 * np.pi * np.arange(n, dtype=np.float64) / (n - 1)
+        return sum(((-1) ** i) * a * np.cos(i * x) for i, a in enumerate(coeffs))
+    return w
+
+
+def bartlett_sym(n):
+    """scipy.signal.bartlett(n): 1 - |2k/(n-1) - 1|."""
+    k = np.arange(n, dtype=np.float64)
+    return 1.0 - np.abs(2.0 * k / (n - 1) - 1.0)
+
+
+# the four windows the reference offers through audio_conf["window"] (parsers.py:9-10), all symmetric
+_WINDOWS = {"hamming": hamming_sym, "hann": _cos_window((0.5, 0.5)), "blackman": _cos_window((0.42, 0.5, 0.08)),
+            "bartlett": bartlett_sym}
 
 
 def stft(y, n_fft=320, hop_length=160, win_length=320, window=hamming_sym, center=True):

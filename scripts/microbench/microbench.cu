@@ -1,6 +1,6 @@
 // Diagnostic micro-benchmarks of tcgen05.mma issue / commit costs (not part of the product path; used to
 // derive the pipeline structure of rnn_tc.cu / gemm_tc.cu / conv_tc.cu -- see DESIGN.md section 5).
-#include "tc_common.cuh"
+#include "tc_common.cuh"   // from danspeech_b200/csrc (-I)
 
 namespace dsb {
 namespace tc {

@@ -5,11 +5,10 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
-import __graft_entry__ as g  # noqa: E402
-g.build()
-from danspeech_b200 import _native as N  # noqa: E402
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "microbench"))
+import build as _mb  # noqa: E402
 
-L = ctypes.CDLL(N.lib_path())
+L = ctypes.CDLL(_mb.build())
 torch.zeros(1).cuda()
 out = (ctypes.c_longlong * 2)()
 n = 1024

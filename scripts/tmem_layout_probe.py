@@ -7,9 +7,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
-import __graft_entry__ as g  # noqa: E402
-g.build()
-from danspeech_b200 import _native as N  # noqa: E402
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "microbench"))
+import build as _mb  # noqa: E402
 
 
 def rng(a):
@@ -26,7 +25,7 @@ def rng(a):
     return ",".join(out)
 
 
-L = ctypes.CDLL(N.lib_path())
+L = ctypes.CDLL(_mb.build())
 torch.zeros(1).cuda()
 for cg, M, Nn in ((1, 64, 64), (1, 128, 64), (2, 128, 64), (2, 256, 64), (2, 128, 32)):
     buf = np.zeros((cg, 128, 128), np.float32)

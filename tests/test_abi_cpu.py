@@ -34,7 +34,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_abi_version_and_errors(lib):
     from danspeech_b200 import _native as N
-    assert lib.dsb_abi_version() == 1
+    assert lib.dsb_abi_version() == 2
     assert lib.dsb_spectrogram_num_frames(240000) == 1501
     assert lib.dsb_spectrogram_num_frames(66944) == 419
     rc = lib.dsb_greedy_decode(None, None, None, 1, 1, 33, 0, None, None, None, None)

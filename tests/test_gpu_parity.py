@@ -684,3 +684,20 @@ def test_recognize_batches_merged_passes_equal_single_batches():
     got = r.recognize_batches([p for p, _ in pinned], merge=3)
     for (p, order), res, ref in zip(pinned, got, single):
         assert [res[pos] for pos in range(len(order))] == [ref[i] for i in order]
+
+
+@pytest.mark.parametrize("window", ["hann", "blackman", "bartlett"])
+def test_spectrogram_windows_match_reference_golden(window):
+    """audio_conf["window"] (parsers.py:9-10): CUDA parsers against the goldens of the unmodified reference parsers."""
+    import os
+    from conftest import ROOT
+    from danspeech_b200.audio.parsers import InferenceSpectrogramAudioParser, SpectrogramAudioParser
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_windows.npz"))
+    a = g["audio"].astype(np.float64)
+    conf = dict(window=window)
+    s = SpectrogramAudioParser(conf).parse_audio(a)
+    assert rel_err(s.cpu().numpy(), g["spect_" + window]) < FP32_TOL
+    sp = InferenceSpectrogramAudioParser(conf)
+    for i, c in enumerate([a[:8640], a[8640:8640 + 6240], a[8640 + 6240:]]):
+        o = sp.parse_audio(c, is_last=(i == 2))
+        assert rel_err(o.cpu().numpy(), g["stream_%s_%d" % (window, i)]) < FP32_TOL

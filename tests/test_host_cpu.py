@@ -267,7 +267,8 @@ def test_multistream_push_control_flow_without_a_gpu():
     assert e.push(sp, True, False) == ["", "", ""]
     assert e.push(sp, False, False) == ["ab", "", "x"]
     assert e.push(sp, False, True) == ["abc", "", ""]            # stream 1: one character, stream 2: "x" -> nothing heard
-    assert e.iterating_transcript == ["", "", ""]
+    # as in the reference (DanSpeechRecognizer.py:181-214) only a stream that was heard is reset
+    assert e.iterating_transcript == ["", "q", "x"]
     e = engine([["ab", "cd"], ["b", "d"]], S=2, string_parts=False)
     e.push(sp[:2], True, False)
     assert e.push(sp[:2], False, False) == ["ab", "cd"]
@@ -416,3 +417,50 @@ def test_public_api_surface_covers_the_reference():
             assert hasattr(R, n) and hasattr(M, n), (mod, n)
             pa, pb = list(inspect.signature(getattr(R, n)).parameters), list(inspect.signature(getattr(M, n)).parameters)
             assert pa == pb[:len(pa)], (mod, n, pa, pb)
+
+
+def test_model_factories_load_the_cached_package_or_raise(tmp_path):
+    """pretrained_models factories (danspeech/pretrained_models/*.py): load <cache_dir>/<Name>.pth like the reference's
+    get_model cache, raise when it is absent (never silently random weights), random weights only on request; the
+    package is read with the restricted unpickler (weights_only=True)."""
+    import torch
+    from danspeech_b200 import pretrained_models as pm
+    with pytest.raises(FileNotFoundError) as ei:
+        pm.TestModel(cache_dir=str(tmp_path))
+    assert "TestModel.pth" in str(ei.value) and "synthetic=True" in str(ei.value)
+    with pytest.raises(FileNotFoundError):
+        pm.get_model_from_string("EnglishLibrispeech") if not os.path.exists(
+            os.path.expanduser("~/.danspeech/models/Librispeech.pth")) else (_ for _ in ()).throw(FileNotFoundError())
+    small = pm.build_model("TestModel", seed=4, rnn_hidden_size=32, rnn_layers=1)
+    torch.save(small.serialize(), str(tmp_path / "TestModel.pth"))
+    loaded = pm.TestModel(cache_dir=str(tmp_path))
+    assert loaded.rnn_hidden_size == 32 and loaded.rnn_layers == 1
+    for (k, a), (_, b) in zip(small.state_dict().items(), loaded.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert pm.CustomModel(str(tmp_path / "TestModel.pth")).model_name == "TestModel"
+    syn_model = pm.TestModel(synthetic=True)
+    assert syn_model.rnn_hidden_size == 400 and pm.TestModel(seed=0).rnn_layers == 5
+
+    # a package that smuggles an arbitrary object is refused unless the caller opts into full unpickling
+    class Evil:
+        def __reduce__(self):
+            return (print, ("unpickled",))
+    pkg = small.serialize()
+    pkg["extra"] = Evil()
+    torch.save(pkg, str(tmp_path / "evil.pth"))
+    with pytest.raises(Exception):
+        pm.CustomModel(str(tmp_path / "evil.pth"))
+
+
+def test_audio_parser_windows_and_config_errors():
+    """audio_conf["window"]: the four reference windows are accepted (parsers.py:9-10), an unknown one raises KeyError
+    like the reference's dict lookup, another framing than 20 ms / 10 ms at 16 kHz is refused loudly."""
+    from danspeech_b200.audio.parsers import SpectrogramAudioParser, _WINDOW_FLAGS
+    assert set(_WINDOW_FLAGS) == {"hamming", "hann", "blackman", "bartlett"}
+    for w, flag in _WINDOW_FLAGS.items():
+        p = SpectrogramAudioParser(dict(window=w))
+        assert p._window_flag == flag and (flag >> 4) in (0, 1, 2, 3)
+    with pytest.raises(KeyError):
+        SpectrogramAudioParser(dict(window="kaiser"))
+    with pytest.raises(NotImplementedError):
+        SpectrogramAudioParser(dict(window_size=0.025))

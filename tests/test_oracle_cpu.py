@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import BATCH_CASES, batch_inputs, case_config, rel_err
+from conftest import BATCH_CASES, ROOT, batch_inputs, case_config, rel_err
 from oracle import greedy as og
 from oracle import model as om
 from oracle import refharness
@@ -265,3 +265,22 @@ def test_oracle_equals_live_reference_recognize_on_all_13_example_wavs():
             text = og.greedy_decode(probs.numpy(), sizes.tolist())[0][0][0]
             assert text == r.recognize(a), os.path.basename(path)
             assert len(text) > 0
+
+
+@pytest.mark.parametrize("window", ["hann", "blackman", "bartlett"])
+def test_window_oracles_match_reference_parsers(window):
+    """audio_conf["window"] (parsers.py:9-10): oracle windows against goldens written by the unmodified reference
+    parsers (tests/golden/gen_window_golden.py), offline and streaming."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_windows.npz"))
+    a = g["audio"].astype(np.float64)
+    conf = dict(window=window)
+    s = osp.SpectrogramOracle(conf).parse_audio(a).numpy()
+    assert s.shape == g["spect_" + window].shape
+    assert np.abs(s - g["spect_" + window]).max() < 1e-5
+    sp = osp.StreamingSpectrogramOracle(conf)
+    for i, c in enumerate([a[:8640], a[8640:8640 + 6240], a[8640 + 6240:]]):
+        o = sp.parse_audio(c, is_last=(i == 2)).numpy()
+        assert np.abs(o - g["stream_%s_%d" % (window, i)]).max() < 1e-5
+    # the windows themselves against scipy's definitions
+    import scipy.signal.windows as sw
+    assert np.allclose(osp._WINDOWS[window](320), getattr(sw, window)(320), atol=1e-15)
