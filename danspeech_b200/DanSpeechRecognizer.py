@@ -42,6 +42,7 @@ class DanSpeechRecognizer(object):
         self.beam_width = beam_width
         self.secondary_model = None
         self._copy_streams = {}     # device -> side stream of transcribe_batches
+        self._decode_streams = {}   # device -> decode stream of transcribe_batches
         if model_name:
             self.update_model(model_name)
         if lm_name:
@@ -266,24 +267,51 @@ class DanSpeechRecognizer(object):
                 self.audio_parser.mark_staging_busy(host, done)
             return audio, n_dev, ns, order, sizes, done
 
+        # Decode runs on its own stream: the beam search (or the greedy kernel) of pass j and the host's string building
+        # overlap the forward pass j+1 -- dsb_forward does not synchronise, so the model of the next pass is enqueued
+        # before the results of this one are read back.
+        decode_stream = self._decode_streams.get(str(dev))
+        if decode_stream is None:
+            decode_stream = self._decode_streams[str(dev)] = torch.cuda.Stream(device=dev)
         results = []
+
+        def finish(pending):
+            dev_out, probs, order, sizes = pending
+            with torch.cuda.device(dev), torch.cuda.stream(decode_stream):
+                decoded_output, _ = self.decoder.decode_finish(dev_out, probs)
+            flat = [None] * len(order)
+            for pos, i in enumerate(order):
+                flat[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
+            row = 0
+            for n in sizes:
+                results.append(flat[row:row + n])
+                row += n
+
         with concurrent.futures.ThreadPoolExecutor(max_workers=1) as ex:
             nxt = ex.submit(stage, 0) if plan else None
+            pending = None
             for j in range(len(plan)):
                 audio, n_dev, ns, order, sizes, done = nxt.result()
                 nxt = ex.submit(stage, j + 1) if j + 1 < len(plan) else None
-                torch.cuda.current_stream(dev).wait_event(done)
-                audio.record_stream(torch.cuda.current_stream(dev))
-                n_dev.record_stream(torch.cuda.current_stream(dev))
+                main = torch.cuda.current_stream(dev)
+                main.wait_event(done)
+                audio.record_stream(main)
+                n_dev.record_stream(main)
                 spect, _ = self.audio_parser.parse_device(audio, n_dev, max(ns))
                 input_sizes = torch.IntTensor([1 + n // self.audio_parser.hop_length for n in ns])
                 out, output_sizes = self.model(spect.view(len(ns), 1, 161, spect.shape[2]), input_sizes)
-                decoded_output, _ = self.decoder.decode(out, output_sizes)
-                flat = [None] * len(order)
-                for pos, i in enumerate(order):
-                    flat[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
-                row = 0
-                for n in sizes:
-                    results.append(flat[row:row + n])
-                    row += n
+                fwd_done = torch.cuda.Event()
+                fwd_done.record(main)
+                with torch.cuda.device(dev), torch.cuda.stream(decode_stream):
+                    decode_stream.wait_event(fwd_done)
+                    out.record_stream(decode_stream)
+                    argmax = getattr(out, "_dsb_argmax", None)
+                    if argmax is not None:
+                        argmax.record_stream(decode_stream)
+                    dev_out = self.decoder.decode_device(out, output_sizes)
+                if pending is not None:
+                    finish(pending)            # pass j-1: read back and build strings while pass j runs
+                pending = (dev_out, out, order, sizes)
+            if pending is not None:
+                finish(pending)
         return results

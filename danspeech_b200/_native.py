@@ -51,6 +51,7 @@ _SIGS = {
     "dsb_forward_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "dsb_forward": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int, c_int, c_void_p, POINTER(c_int32), c_void_p,
                             c_void_p, c_size_t, c_void_p]),
+    "dsb_forward_status": (c_int, [c_void_p]),
     "dsb_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                               c_void_p]),
     "dsb_stream_state_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),

@@ -191,7 +191,7 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
   const int H = d.rnn_hidden_size, C = d.num_classes;
   const int64_t M = (int64_t)Tp * B;
   DSB_CUDA(cudaMemcpyAsync(ws.d_len, h_out_len, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
-  DSB_CUDA(cudaMemsetAsync(ws.sync_words, 0, sizeof(unsigned int) * (kRnnSyncCounters + 1), st));   // step counters + abort flag
+  DSB_CUDA(cudaMemsetAsync(ws.sync_words, 0, sizeof(unsigned int) * kRnnSyncCounters, st));   // step counters
 
   prof_begin(ST_CONV, st);
   if (int e = im2col_time_tc(spect, ws.cb[0], B, T, Tp, st)) return e;
@@ -228,7 +228,7 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
     const int next_ld = (H + 7) / 8 * 8;
     if (tc_rnn) {
       used_tc_rnn = true;
-      if (int e = rnn_layer_tc(R, ws.gates, ws.d_len, B, Tp, Tmax, ws.ydir, ws.hbuf, ws.sync_words, st)) return e;
+      if (int e = rnn_layer_tc(R, ws.gates, ws.d_len, B, Tp, Tmax, ws.ydir, ws.hbuf, ws.sync_words, m->d_abort, st)) return e;
       if (int e = combine_dirs_tc(ws.ydir, R.dirs, Tp, B, H, ws.d_len, last ? nullptr : ws.xb, next_ld,
                                   last ? ws.xf : nullptr, st))
         return e;
@@ -252,11 +252,10 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
   prof_end(ST_TAIL, st);
 
   if (used_tc_rnn) {
-    // the persistent recurrence never spins forever: a stuck step barrier raises this flag instead
-    int abort_flag = 0;
-    DSB_CUDA(cudaMemcpyAsync(&abort_flag, ws.sync_words + kRnnSyncCounters, sizeof(int), cudaMemcpyDeviceToHost, st));
-    DSB_CUDA(cudaStreamSynchronize(st));
-    if (abort_flag) return set_error(DSB_ERR_CUDA, "dsb_forward: persistent recurrence step barrier timed out");
+    // The persistent recurrence never spins forever: a stuck step barrier raises the (sticky) abort flag.  Its value
+    // travels to pinned host memory behind the kernels of this call; nobody waits for it here -- dsb_forward_status()
+    // and the next dsb_forward() read the mirror (the caller synchronises anyway before it touches the results).
+    DSB_CUDA(cudaMemcpyAsync(m->h_abort, m->d_abort, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   return 0;
 }

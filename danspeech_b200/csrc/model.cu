@@ -141,7 +141,17 @@ extern "C" int dsb_model_create(const dsb_model_desc* d, dsb_model** out) {
 extern "C" void dsb_model_destroy(dsb_model* m) {
   if (!m) return;
   for (void* p : m->owned) cudaFree(p);
+  if (m->d_abort) cudaFree(m->d_abort);
+  if (m->h_abort) cudaFreeHost(m->h_abort);
   delete m;
+}
+
+extern "C" int dsb_forward_status(const dsb_model* m) {
+  DSB_REQUIRE(m, "dsb_forward_status: null model");
+  if (m->h_abort && *(volatile int*)m->h_abort)
+    return set_error(DSB_ERR_CUDA, "dsb_forward: the persistent recurrence's step barrier timed out (results of that "
+                                   "call are invalid; re-create the model)");
+  return 0;
 }
 
 extern "C" int dsb_model_set_tensor(dsb_model* m, const char* name, const float* data, int64_t numel) {
@@ -164,6 +174,12 @@ extern "C" int dsb_model_finalize(dsb_model* m, int precision, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   for (void* p : m->owned) cudaFree(p);
   m->owned.clear();
+  if (!m->d_abort) {
+    DSB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->d_abort), sizeof(int)));
+    DSB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&m->h_abort), sizeof(int), cudaHostAllocDefault));
+  }
+  DSB_CUDA(cudaMemsetAsync(m->d_abort, 0, sizeof(int), st));
+  *m->h_abort = 0;
   Lookup lk{m};
   const dsb_model_desc& d = m->desc;
   char nm[128];
@@ -337,6 +353,7 @@ extern "C" int dsb_forward(dsb_model* m, const float* spect, const int32_t* leng
     return set_error(DSB_ERR_WORKSPACE, "dsb_forward: workspace %zu < required %zu", workspace_bytes,
                      dsb_forward_workspace_bytes(m, B, T));
   cudaStream_t st = (cudaStream_t)stream;
+  if (int e = dsb_forward_status(m)) return e;   // an earlier call's recurrence aborted: the flag is read lazily
   if (m->precision == DSB_PREC_BF16)
     return forward_tc(m, spect, out_lengths, B, T, probs, argmax, workspace, st);
 

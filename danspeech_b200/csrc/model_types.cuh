@@ -54,6 +54,11 @@ struct dsb_model {
   float* fc_w = nullptr;             // BN-folded [C][H]
   float* fc_b = nullptr;             // BN-folded [C]
   std::vector<void*> owned;          // device allocations to free
+  // Abort flag of the persistent recurrence (a stuck step barrier raises it instead of hanging the GPU): a device
+  // word that is sticky for the life of the model, mirrored into pinned host memory by an async copy at the end of
+  // every forward -- no host/device synchronisation per batch (dsb_forward_status reads the mirror).
+  int* d_abort = nullptr;
+  int* h_abort = nullptr;
 };
 
 namespace dsb {
@@ -90,8 +95,8 @@ constexpr int kRnnSyncCounters = kRnnMaxCounters * kRnnCounterStride;
 int rnn_tc_max_in_flight();
 size_t rnn_tc_hbuf_elems(const RnnLayer& L, int B);
 int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
-                 __nv_bfloat16* hbuf, unsigned int* sync_words, cudaStream_t st, const float* h0 = nullptr,
-                 const float* c0 = nullptr, float* hT = nullptr, float* cT = nullptr);
+                 __nv_bfloat16* hbuf, unsigned int* sync_words, int* abort_flag, cudaStream_t st,
+                 const float* h0 = nullptr, const float* c0 = nullptr, float* hT = nullptr, float* cT = nullptr);
 int f32_to_bf16_ld(const float* x, __nv_bfloat16* y, int64_t rows, int cols, int ld, cudaStream_t st);
 int finalize_tc(dsb_model* m, cudaStream_t st);
 size_t forward_tc_workspace_bytes(const dsb_model* m, int B, int T);

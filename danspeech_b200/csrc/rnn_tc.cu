@@ -766,12 +766,12 @@ __global__ void init_hbuf_kernel(const float* __restrict__ h0, __nv_bfloat16* __
 }  // namespace tc
 
 // One BatchRNN layer.  gx [T*B][dirs*G*H] fp32, y [dirs][T][B][H] fp32 (rows t >= len_b are NOT written),
-// hbuf rnn_tc_hbuf_elems() bf16, sync = {counters[<= kRnnSyncCounters] u32, abort i32} (device).
+// hbuf rnn_tc_hbuf_elems() bf16, sync_words = kRnnSyncCounters u32 step counters, abort_flag = one sticky i32 (device).
 // d_len == nullptr: every sequence runs Tmax steps.  h0/c0 (nullptr = zeros) and hT/cT (nullptr = dropped)
 // are [dirs][B][H] fp32 and may alias (streaming state carried across chunks, model.py:219-237).
 int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
-                 __nv_bfloat16* hbuf, unsigned int* sync_words, cudaStream_t st, const float* h0, const float* c0,
-                 float* hT, float* cT) {
+                 __nv_bfloat16* hbuf, unsigned int* sync_words, int* abort_flag, cudaStream_t st, const float* h0,
+                 const float* c0, float* hT, float* cT) {
   using namespace tc;
   int dev = 0, sms = 148, cpd = 0, launches = 1;
   cudaGetDevice(&dev);
@@ -816,7 +816,7 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.hbuf = hbuf;
   p.lens = d_len;
   p.counters = sync_words;
-  p.abort_flag = reinterpret_cast<int*>(sync_words + kRnnSyncCounters);
+  p.abort_flag = abort_flag;
   p.h0 = h0; p.c0 = c0; p.hT = hT; p.cT = cT;
   p.n_bgroups = n_bgroups; p.slots = slots;
   p.B = B; p.H = L.H; p.HP = HP; p.BP = BP; p.T = T; p.Tmax = Tmax;

@@ -303,7 +303,8 @@ extern "C" int dsb_streaming_forward(dsb_model* m, dsb_stream_state* s, const fl
       prof_begin(ST_RNN, st);
       if (tc_rnn) {
         used_tc_rnn = true;
-        if (int e = rnn_layer_tc(R, s->gates, nullptr, S, T2, T2, s->ya, s->hbuf, s->sync_words, st,
+        if (int e = rnn_layer_tc(R, s->gates, nullptr, S, T2, T2, s->ya, s->hbuf, s->sync_words,
+                                 reinterpret_cast<int*>(s->sync_words + kRnnSyncCounters), st,
                                  s->h_init ? h_io : nullptr, (s->h_init && c_io) ? c_io : nullptr, h_io, c_io))
           return e;
         if (int e = combine_dirs_tc(s->ya, 1, T2, S, H, s->lens, last ? nullptr : s->xb, next_ld, last ? s->yb : nullptr, st))

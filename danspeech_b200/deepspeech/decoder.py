@@ -42,6 +42,14 @@ class Decoder(object):
         raise NotImplementedError
 
 
+def _after_sync(probs):
+    """Called once the host has synchronised for a decode result: the forward that produced `probs` has completed, so
+    its device-side status can be read without waiting (DeepSpeech.check_status)."""
+    chk = getattr(probs, "_dsb_status", None)
+    if chk is not None:
+        chk()
+
+
 def _sizes_to_device(sizes, B, dev):
     if sizes is None:
         return None
@@ -109,6 +117,7 @@ class GreedyDecoder(Decoder):
         costs more host time than the kernel."""
         tokens, _, out_len = self.decode_device(probs, sizes)
         packed = torch.cat([out_len.view(-1, 1), tokens], dim=1).cpu().numpy()
+        _after_sync(probs)
         if not hasattr(self, "_char_arr"):
             self._char_arr = np.array([self.int_to_char[i] for i in range(len(self.int_to_char))])
         chars = self._char_arr[np.clip(packed[:, 1:], 0, len(self._char_arr) - 1)]   # entries past out_len are unwritten
@@ -116,8 +125,13 @@ class GreedyDecoder(Decoder):
 
     def decode(self, probs, sizes=None):
         """Returns (strings: List[B][1] str, offsets: List[B][1] IntTensor) -- decoder.py:183-198."""
-        tokens, offsets, out_len = self.decode_device(probs, sizes)
+        return self.decode_finish(self.decode_device(probs, sizes), probs)
+
+    def decode_finish(self, dev_out, probs=None):
+        """Host half of ``decode``: one D2H copy of what ``decode_device`` produced, then the strings."""
+        tokens, offsets, out_len = dev_out
         packed = torch.cat([out_len.view(-1, 1), tokens, offsets], dim=1).cpu().numpy()   # one D2H copy
+        _after_sync(probs)
         B, T = tokens.shape
         chars = self.int_to_char
         lens = packed[:, 0].tolist()
@@ -208,7 +222,12 @@ class BeamCTCDecoder(Decoder):
 
     def decode(self, probs, sizes=None):
         """Returns (strings: List[B][beam] str, offsets: List[B][beam] IntTensor) -- decoder.py:129-144."""
-        out, scores, ts, out_len = self.decode_device(probs, sizes)
+        return self.decode_finish(self.decode_device(probs, sizes), probs)
+
+    def decode_finish(self, dev_out, probs=None):
+        """Host half of ``decode``: D2H copies of what ``decode_device`` produced, then strings and offsets."""
+        out, scores, ts, out_len = dev_out
         out, scores, ts, out_len = out.cpu(), scores.cpu(), ts.cpu(), out_len.cpu()
+        _after_sync(probs)
         self.last_scores = scores
         return self.convert_to_strings(out, out_len), self.convert_tensor(ts, out_len)

@@ -238,7 +238,13 @@ class DeepSpeech(nn.Module):
         t_max = int(output_lengths.max())
         probs = probs[:, :t_max]
         probs._dsb_argmax = argmax[:, :t_max]   # fused torch.max(probs, 2) for GreedyDecoder
+        probs._dsb_status = self.check_status    # the decoders call it once they have synchronised for the results
         return probs, output_lengths
+
+    def check_status(self):
+        """dsb_forward does not synchronise; raises if a completed forward of this model aborted on the device."""
+        if self._handle is not None:
+            N.check(N.lib().dsb_forward_status(self._handle), "dsb_forward")
 
     def streaming_forward(self, x, is_first, is_last):
         """Chunked streaming forward (model.py:517-537); returns probs [S,k,C] or None while buffering."""

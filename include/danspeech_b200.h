@@ -166,6 +166,13 @@ size_t dsb_forward_workspace_bytes(const dsb_model* m, int B, int T);
 int dsb_forward(dsb_model* m, const float* spect, const int32_t* lengths, int B, int T,
                 float* probs, int32_t* out_lengths, int32_t* argmax,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* dsb_forward only enqueues work: it does not synchronise with the device.  The one failure that can happen on the
+ * device -- a step barrier of the persistent recurrence timing out (it raises a flag instead of hanging the GPU) -- is
+ * mirrored into pinned host memory behind the kernels of the call.  dsb_forward_status returns DSB_ERR_CUDA if any
+ * forward of this model that has COMPLETED so far aborted (call it after synchronising with the stream, e.g. after
+ * reading the transcripts back); the next dsb_forward checks the same flag.  The reference has no equivalent: its
+ * forward is synchronous Python (danspeech/deepspeech/model.py:496-515). */
+int dsb_forward_status(const dsb_model* m);
 
 /* Tensor-core GEMM building block of the model path (also exported for diagnostics and tests):
  * C[M,N] (f32, row stride ldc) = A[M,K] (bf16, row stride lda) * W[N,K]^T (bf16, row stride ldw) + bias[N].
