@@ -177,7 +177,8 @@ class DanSpeechRecognizer(object):
     def _transcribe_staged(self, host_audio, n_samples, order, show_all=False):
         spect, input_sizes = self.audio_parser.parse_packed(host_audio, n_samples)
         out, output_sizes = self.model(spect, input_sizes)
-        decoded_output, _ = self.decoder.decode(out, output_sizes)
+        decoded_output, _ = self.decoder.decode_finish(self.decoder.decode_device(out, output_sizes), out,
+                                                       top_only=not show_all)
         results = [None] * len(order)
         for pos, i in enumerate(order):
             results[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
@@ -278,7 +279,7 @@ class DanSpeechRecognizer(object):
         def finish(pending):
             dev_out, probs, order, sizes = pending
             with torch.cuda.device(dev), torch.cuda.stream(decode_stream):
-                decoded_output, _ = self.decoder.decode_finish(dev_out, probs)
+                decoded_output, _ = self.decoder.decode_finish(dev_out, probs, top_only=not show_all)
             flat = [None] * len(order)
             for pos, i in enumerate(order):
                 flat[i] = decoded_output[pos] if show_all else decoded_output[pos][0]

@@ -67,6 +67,7 @@ _SIGS = {
     "dsb_beam_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "dsb_beam_decode": (c_int, [c_void_p, c_void_p, POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dsb_lm_inspect": (c_int, [c_char_p, POINTER(c_int), POINTER(c_int64), POINTER(c_int64), POINTER(c_uint64)]),
     "dsb_beam_lm_order": (c_int, [c_void_p]),
     "dsb_beam_lm_is_char_based": (c_int, [c_void_p]),
     "dsb_beam_lm_num_ngrams": (c_int64, [c_void_p]),

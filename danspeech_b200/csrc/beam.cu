@@ -18,6 +18,7 @@
 //   (few candidates) or bitonic sort -> materialise the surviving prefixes in a per-utterance node arena.
 // The work is latency / random-access bound, reported as utterances/s and steps/s.
 #include "model_types.cuh"
+#include "lm_host.h"
 #include <float.h>
 #include <math.h>
 #include <cstdlib>
@@ -60,14 +61,9 @@ __host__ __device__ inline uint64_t mix64(uint64_t x) {
   x ^= x >> 31;
   return x;
 }
-__host__ __device__ inline void pack_key(const int* ids, int n, uint64_t& k0, uint64_t& k1) {
-  k0 = (uint64_t)n;
-  k1 = 0;
-  for (int i = 0; i < n; ++i) {
-    if (i < 3) k0 |= (uint64_t)(ids[i] & 0xFFFFF) << (3 + 20 * i);
-    else k1 |= (uint64_t)(ids[i] & 0xFFFFF) << (20 * (i - 3));
-  }
-}
+// Table key of an n-gram: (k0, k1) = (KenLM chain hash over the word ids -- the id itself for a unigram --, order).
+// A KenLM probing binary stores exactly these hashes and nothing else about an n-gram (lm_host.h), so ARPA text and
+// .klm files load into the same table.
 __host__ __device__ inline uint32_t key_hash(uint64_t k0, uint64_t k1) { return (uint32_t)mix64(k0 ^ mix64(k1 + 0x9e3779b97f4a7c15ULL)); }
 
 // continue a lookup whose first slot `e` (at index h) has already been loaded
@@ -101,15 +97,22 @@ __device__ __noinline__ float lm_log_cond_prob_impl(const LmEntry* __restrict__ 
   uint64_t fk0[MAXQ], fk1[MAXQ], ck0[MAXQ], ck1[MAXQ];
   uint32_t fh[MAXQ], ch[MAXQ];
   LmEntry fe[MAXQ], ce[MAXQ];
+  // query q: the n-gram words[first+q .. n-1] (f) and its context words[first+q .. n-2] (c).  The chain hash runs from
+  // the last word backwards, so the hash of a longer history is one combine step on top of the shorter one.
+  uint64_t hf = 0, hc = 0;
 #pragma unroll
-  for (int q = 0; q < MAXQ; ++q) {
+  for (int q = MAXQ - 1; q >= 0; --q) {
     if (q < nq) {
       const int start = first + q;
-      pack_key(words + start, n - start, fk0[q], fk1[q]);
+      hf = (start == n - 1) ? (uint64_t)(uint32_t)words[start] : lm_combine_word_hash(hf, (uint32_t)words[start]);
+      fk0[q] = hf;
+      fk1[q] = (uint64_t)(n - start);
       fh[q] = key_hash(fk0[q], fk1[q]) & mask;
       fe[q] = lm[fh[q]];
       if (start < n - 1) {
-        pack_key(words + start, n - 1 - start, ck0[q], ck1[q]);
+        hc = (start == n - 2) ? (uint64_t)(uint32_t)words[start] : lm_combine_word_hash(hc, (uint32_t)words[start]);
+        ck0[q] = hc;
+        ck1[q] = (uint64_t)(n - 1 - start);
         ch[q] = key_hash(ck0[q], ck1[q]) & mask;
         ce[q] = lm[ch[q]];
       }
@@ -671,102 +674,6 @@ beam_kernel(const BeamParams p) {
 }
 
 // ------------------------------------------------------------------------------------------ host
-struct HostLm {
-  int order = 0;
-  std::unordered_map<std::string, int> vocab;
-  std::vector<std::string> words;
-  struct Gram { std::vector<int> ids; float prob, backoff; };
-  std::vector<Gram> grams;
-  float unk_prob = -100.f;
-  int index(const std::string& w) const {
-    auto it = vocab.find(w);
-    return it == vocab.end() ? 0 : it->second;
-  }
-};
-
-// KenLM binary files (lm/binary_format.cc: 88-byte sanity header starting with the magic string, then
-// FixedWidthParameters {order, probing_multiplier, model_type, has_vocabulary, search_version} and one uint64
-// count per order) are recognised and refused with what they contain: the device LM table is built from ARPA
-// text, and a .klm only stores 64-bit hashes of its n-grams (second half: not built).
-static int refuse_kenlm_binary(const char* path) {
-  FILE* fp = fopen(path, "rb");
-  if (!fp) return 0;
-  unsigned char hdr[88 + 20 + 8 * 8];
-  const size_t n = fread(hdr, 1, sizeof(hdr), fp);
-  fclose(fp);
-  static const char magic[] = "mmap lm http://kheafield.com/code format version";
-  if (n < sizeof(magic) - 1 || memcmp(hdr, magic, sizeof(magic) - 1) != 0) return 0;
-  int order = 0, type = -1;
-  unsigned long long counts[8] = {0};
-  if (n >= 88 + 20) {
-    order = hdr[88];
-    memcpy(&type, hdr + 96, 4);
-    for (int i = 0; i < order && i < 8 && 108 + 8 * (size_t)(i + 1) <= n; ++i) memcpy(&counts[i], hdr + 108 + 8 * i, 8);
-  }
-  static const char* names[] = {"probing", "rest-probing", "trie", "quantised trie", "array trie", "quantised array trie"};
-  return set_error(DSB_ERR_UNSUPPORTED,
-                   "dsb_beam_create: '%s' is a KenLM binary (format version %c, %s, order %d, %llu unigrams); this build "
-                   "reads ARPA text only -- pass the .arpa the binary was built from",
-                   path, n > sizeof(magic) ? (char)hdr[sizeof(magic)] : '?', (type >= 0 && type < 6) ? names[type] : "unknown type",
-                   order, counts[0]);
-}
-
-static int load_arpa(const char* path, HostLm& lm) {
-  if (int e = refuse_kenlm_binary(path)) return e;
-  std::ifstream f(path);
-  if (!f) return set_error(DSB_ERR_IO, "dsb_beam_create: cannot open language model '%s'", path);
-  lm.vocab["<unk>"] = 0;
-  lm.words.push_back("<unk>");
-  std::string line;
-  int cur = 0;
-  while (std::getline(f, line)) {
-    if (!line.empty() && line.back() == '\r') line.pop_back();
-    if (line.empty()) continue;
-    if (line[0] == '\\') {
-      if (line.find("-grams:") != std::string::npos) {
-        cur = atoi(line.c_str() + 1);
-        if (cur > lm.order) lm.order = cur;
-      } else if (line == "\\end\\") {
-        break;
-      }
-      continue;
-    }
-    if (cur == 0) continue;
-    std::vector<std::string> tok;
-    std::stringstream ss(line);
-    std::string t;
-    while (ss >> t) tok.push_back(t);
-    if ((int)tok.size() < cur + 1) continue;
-    HostLm::Gram g;
-    g.prob = (float)atof(tok[0].c_str());
-    g.backoff = (int)tok.size() > cur + 1 ? (float)atof(tok[cur + 1].c_str()) : 0.f;
-    for (int i = 0; i < cur; ++i) {
-      const std::string& w = tok[1 + i];
-      int id;
-      if (cur == 1 && w != "<unk>") {
-        auto it = lm.vocab.find(w);
-        if (it == lm.vocab.end()) {
-          id = (int)lm.words.size();
-          lm.vocab[w] = id;
-          lm.words.push_back(w);
-        } else {
-          id = it->second;
-        }
-      } else {
-        id = lm.index(w);
-      }
-      g.ids.push_back(id);
-    }
-    if (cur == 1 && g.ids[0] == 0) lm.unk_prob = g.prob;
-    lm.grams.push_back(g);
-  }
-  if (lm.order == 0) return set_error(DSB_ERR_IO, "dsb_beam_create: '%s' is not an ARPA language model", path);
-  if (lm.order > BM_HIST + 1)
-    return set_error(DSB_ERR_UNSUPPORTED, "dsb_beam_create: LM order %d > %d", lm.order, BM_HIST + 1);
-  if (lm.words.size() >= (1u << 20)) return set_error(DSB_ERR_UNSUPPORTED, "dsb_beam_create: vocabulary too large");
-  return 0;
-}
-
 static std::vector<std::string> utf8_split(const std::string& s) {
   std::vector<std::string> out;
   for (size_t i = 0; i < s.size();) {
@@ -834,7 +741,10 @@ extern "C" int dsb_beam_create(const char* labels_utf8, int n_labels, const char
   };
   if (lm_path && lm_path[0]) {
     HostLm lm;
-    if (int e = load_arpa(lm_path, lm)) return fail(e);
+    const int klm = is_kenlm_binary(lm_path);
+    if (klm < 0) return fail(klm);
+    if (int e = klm ? load_klm(lm_path, lm) : load_arpa(lm_path, lm)) return fail(e);
+    if (lm.order > BM_HIST + 1) return fail(set_error(DSB_ERR_UNSUPPORTED, "dsb_beam_create: LM order %d > %d", lm.order, BM_HIST + 1));
     T.has_lm = 1;
     T.order = lm.order;
     T.unk_prob = lm.unk_prob;
@@ -849,8 +759,7 @@ extern "C" int dsb_beam_create(const char* labels_utf8, int n_labels, const char
     std::vector<LmEntry> table(cap);
     memset(table.data(), 0, sizeof(LmEntry) * cap);
     for (const HostLm::Gram& g : lm.grams) {
-      uint64_t k0, k1;
-      pack_key(g.ids.data(), (int)g.ids.size(), k0, k1);
+      const uint64_t k0 = g.key, k1 = (uint64_t)g.n;
       uint32_t h = key_hash(k0, k1) & (uint32_t)(cap - 1);
       while (table[h].used && !(table[h].k0 == k0 && table[h].k1 == k1)) h = (h + 1) & (uint32_t)(cap - 1);
       table[h].k0 = k0; table[h].k1 = k1; table[h].prob = g.prob; table[h].backoff = g.backoff; table[h].used = 1;

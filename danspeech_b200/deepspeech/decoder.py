@@ -127,7 +127,7 @@ class GreedyDecoder(Decoder):
         """Returns (strings: List[B][1] str, offsets: List[B][1] IntTensor) -- decoder.py:183-198."""
         return self.decode_finish(self.decode_device(probs, sizes), probs)
 
-    def decode_finish(self, dev_out, probs=None):
+    def decode_finish(self, dev_out, probs=None, top_only=False):
         """Host half of ``decode``: one D2H copy of what ``decode_device`` produced, then the strings."""
         tokens, offsets, out_len = dev_out
         packed = torch.cat([out_len.view(-1, 1), tokens, offsets], dim=1).cpu().numpy()   # one D2H copy
@@ -224,9 +224,14 @@ class BeamCTCDecoder(Decoder):
         """Returns (strings: List[B][beam] str, offsets: List[B][beam] IntTensor) -- decoder.py:129-144."""
         return self.decode_finish(self.decode_device(probs, sizes), probs)
 
-    def decode_finish(self, dev_out, probs=None):
-        """Host half of ``decode``: D2H copies of what ``decode_device`` produced, then strings and offsets."""
+    def decode_finish(self, dev_out, probs=None, top_only=False):
+        """Host half of ``decode``: D2H copies of what ``decode_device`` produced, then strings and offsets.
+        ``top_only`` reads back and converts the best beam only (what ``transcribe`` without ``show_all`` keeps,
+        DanSpeechRecognizer.py:225-231): the full [B, beam, T] token and timestep tensors are 2 x 12 MB per batch of
+        64 x 751 frames and 4096 Python string conversions."""
         out, scores, ts, out_len = dev_out
+        if top_only:
+            out, ts, out_len = out[:, :1].contiguous(), ts[:, :1].contiguous(), out_len[:, :1].contiguous()
         out, scores, ts, out_len = out.cpu(), scores.cpu(), ts.cpu(), out_len.cpu()
         _after_sync(probs)
         self.last_scores = scores

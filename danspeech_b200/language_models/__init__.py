@@ -2,9 +2,9 @@
 
 In the reference these factories download a KenLM binary into ``~/.danspeech/lms/`` and return its path
 (danspeech/language_models/*.py, utils/data_utils.py:43-80).  There is no downloading here: a factory returns the
-path of an already present file -- the ARPA text form ``<name>.arpa`` when it is there (what this package's decoder
-reads), else the ``.klm`` the reference would have cached (which ``BeamCTCDecoder`` refuses with a message naming the
-ARPA route) -- and otherwise says where it looked.  ``CustomLanguageModel`` is the identity, as in the reference.
+path of an already present file -- the ``.klm`` the reference would have cached (KenLM probing binaries are read
+directly, csrc/lm_load.cu), else the ARPA text form ``<name>.arpa`` -- and otherwise says where it looked.
+``CustomLanguageModel`` is the identity, as in the reference.
 """
 import os
 
@@ -16,11 +16,11 @@ def CustomLanguageModel(path):
 
 def _cached(stem, cache_dir):
     root = cache_dir if cache_dir is not None else os.path.join(os.path.expanduser("~"), ".danspeech", "lms")
-    for ext in (".arpa", ".klm"):
+    for ext in (".klm", ".arpa"):
         path = os.path.join(root, stem + ext)
         if os.path.isfile(path):
             return path
-    raise FileNotFoundError("language model %s.arpa (or .klm) not found in %s; this package does not download models -- "
+    raise FileNotFoundError("language model %s.klm (or .arpa) not found in %s; this package does not download models -- "
                             "place the file there or pass a path to Recognizer(lm=...)" % (stem, root))
 
 

@@ -222,6 +222,10 @@ int dsb_beam_decode(dsb_beam* d, const float* probs, const int32_t* seq_lens, in
                     int32_t* out_tokens, int32_t* out_timesteps, float* out_scores, int32_t* out_lens,
                     void* workspace, size_t workspace_bytes, void* stream);
 /* LM introspection used by the host wrapper and tests. */
+/* Host-only inspection of a language-model file through the same loaders dsb_beam_create uses (no CUDA call): the
+ * LM order, the number of n-grams and vocabulary words, and an order-independent 64-bit digest of the loaded model.
+ * An ARPA file and the KenLM probing binary built from it load into the same model and have the same digest. */
+int dsb_lm_inspect(const char* path, int* order, int64_t* n_ngrams, int64_t* n_words, uint64_t* digest);
 int dsb_beam_lm_order(const dsb_beam* d);
 int dsb_beam_lm_is_char_based(const dsb_beam* d);
 int64_t dsb_beam_lm_num_ngrams(const dsb_beam* d);

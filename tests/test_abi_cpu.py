@@ -64,11 +64,12 @@ def test_product_fails_loudly_without_gpu():
 
 
 def test_kenlm_binary_is_recognised_and_refused(lib, tmp_path):
-    """A .klm (KenLM binary, lm/binary_format.cc header) must fail with what it is, not with an ARPA parse error."""
+    """A .klm variant the reader does not handle (here: a trie model) must fail with what it is, not with an ARPA parse
+    error (the probing model is read: tests/test_lm_cpu.py)."""
     import struct
     from danspeech_b200.utils import synthetic as syn
     magic = b"mmap lm http://kheafield.com/code format version 5\n\0"
-    sanity = magic.ljust(56, b"\0") + struct.pack("<fffIIQ", 0.0, 1.0, -0.5, 1, 0xFFFFFFFF, 1) + b"\0" * 4
+    sanity = magic.ljust(56, b"\0") + struct.pack("<fffII4xQ", 0.0, 1.0, -0.5, 1, 0xFFFFFFFF, 1)
     assert len(sanity) == 88
     params = struct.pack("<B3xfiB3xI", 3, 1.5, 2, 1, 1)          # order 3, trie, with vocabulary
     p = tmp_path / "dsl_3gram.klm"

@@ -116,3 +116,46 @@ def test_recognizer_with_lm_end_to_end(tmp_path, golden):
     ref = CTCBeamDecoderOracle(syn.LABELS, arpa, 1.3, 0.2, 40, 1.0, 64, 6, 0)
     r_strings, _ = ref.decode_strings(golden["cfg1_probs"], golden["cfg1_sizes"])
     assert r.recognize(audio) == r_strings[0][0]
+
+
+@pytest.mark.parametrize("char_based", [False, True])
+def test_beam_klm_equals_arpa(tmp_path, char_based):
+    """the reference hands the decoder a KenLM binary (language_models/dsl_3gram.py:16-20).  The same
+    model as ARPA text and as a probing .klm (written by oracle/klm_writer.py) must decode identically: every beam,
+    every score, bit for bit -- both files load into the same device table."""
+    from danspeech_b200.deepspeech.decoder import BeamCTCDecoder
+    from oracle import klm_writer as kw
+    arpa = syn.write_synthetic_arpa(str(tmp_path / "m.arpa"), n_words=2000, seed=0, char_based=char_based)
+    klm = str(tmp_path / "m.klm")
+    kw.write_klm(arpa, klm)
+    rng = np.random.default_rng(31)
+    probs, lens = _spelled_probs(rng, syn.synthetic_vocab(2000, 0), B=16, T=140)
+    p, ln = torch.from_numpy(probs).cuda(), torch.IntTensor(lens)
+    a = BeamCTCDecoder(syn.LABELS, arpa, 1.3, 0.2, 40, 1.0, 64, 6, 0)
+    k = BeamCTCDecoder(syn.LABELS, klm, 1.3, 0.2, 40, 1.0, 64, 6, 0)
+    L = a._handle and __import__("danspeech_b200")._native.lib()
+    assert L.dsb_beam_lm_order(k._handle) == L.dsb_beam_lm_order(a._handle) == 3
+    assert L.dsb_beam_lm_num_ngrams(k._handle) == L.dsb_beam_lm_num_ngrams(a._handle)
+    assert L.dsb_beam_lm_is_char_based(k._handle) == L.dsb_beam_lm_is_char_based(a._handle) == int(char_based)
+    for x, y in zip(a.decode_device(p, ln), k.decode_device(p, ln)):
+        assert torch.equal(x, y)
+    # and the ARPA path still agrees with the CPU oracle (which keys its LM by word tuples, not by hashes)
+    ref = CTCBeamDecoderOracle(syn.LABELS, arpa, 1.3, 0.2, 40, 1.0, 64, 6, 0)
+    _compare(k, ref, probs, lens)
+
+
+def test_recognizer_accepts_a_klm_language_model(tmp_path, golden):
+    """Recognizer(model, lm="x.klm") -- the reference's own call shape (Recognizer.py:39-80 with a language_models path)."""
+    from danspeech_b200 import Recognizer
+    from danspeech_b200.pretrained_models import build_model
+    from oracle import klm_writer as kw
+    arpa = syn.write_synthetic_arpa(str(tmp_path / "dsl_3gram.arpa"), n_words=2000, seed=0)
+    kw.write_klm(arpa, str(tmp_path / "dsl_3gram.klm"))
+    from danspeech_b200.language_models import DSL3gram
+    lm = DSL3gram(cache_dir=str(tmp_path))
+    assert lm.endswith(".klm")
+    model = build_model("TestModel", seed=0).set_precision("fp32")
+    audio = golden["wav_u0013002"].astype(np.float64)
+    got = Recognizer(model=model, lm=lm, alpha=1.3, beta=0.2, beam_width=64).recognize(audio, show_all=True)
+    want = Recognizer(model=model, lm=arpa, alpha=1.3, beta=0.2, beam_width=64).recognize(audio, show_all=True)
+    assert got == want and len(got) == 64

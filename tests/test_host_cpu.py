@@ -360,10 +360,10 @@ def test_language_model_factories_return_cached_paths_and_never_download(tmp_pat
     assert lm.CustomLanguageModel("/x/y.arpa") == "/x/y.arpa"
     with pytest.raises(FileNotFoundError, match="does not download"):
         lm.DSL3gram(cache_dir=str(tmp_path))
-    (tmp_path / "dsl_3gram.klm").write_bytes(b"x")
-    assert lm.DSL3gram(cache_dir=str(tmp_path)) == str(tmp_path / "dsl_3gram.klm")
     (tmp_path / "dsl_3gram.arpa").write_text("\\data\\\n")
-    assert lm.DSL3gram(cache_dir=str(tmp_path)) == str(tmp_path / "dsl_3gram.arpa")     # the readable form wins
+    assert lm.DSL3gram(cache_dir=str(tmp_path)) == str(tmp_path / "dsl_3gram.arpa")
+    (tmp_path / "dsl_3gram.klm").write_bytes(b"x")
+    assert lm.DSL3gram(cache_dir=str(tmp_path)) == str(tmp_path / "dsl_3gram.klm")      # the reference's artefact wins
     assert set(lm.__all__) >= {"DSL5gram", "DSLWiki3gram", "DSLWiki5gram", "DSLWikiLeipzig3gram", "Wiki3gram", "Wiki5gram",
                                "Folketinget3gram", "DSL3gramWithNames"}
     assert lm.Wiki5gram.__name__ == "Wiki5gram"
