@@ -101,6 +101,12 @@ int finalize_tc(dsb_model* m, cudaStream_t st) {
       if (int e = dev_alloc_tc(m, &R.w_hh_pack, (int64_t)R.dirs * cpd * 64 * HP)) return e;
       if (int e = pack_whh_tc(R, R.w_hh_pack, st)) return e;
     }
+    // the K-split CTA-pair kernel shares the exchange buffers and counters of the one-CTA kernel (groups of 64 rows)
+    R.ks_recurrence = R.tc_recurrence && rnn_ks_supported(R, sms, nullptr, nullptr);
+    if (R.ks_recurrence) {
+      if (int e = dev_alloc_tc(m, &R.w_hh_pack_ks, (int64_t)rnn_ks_pack_elems(R))) return e;
+      if (int e = pack_whh_ks(R, R.w_hh_pack_ks, st)) return e;
+    }
   }
   return 0;
 }

@@ -33,6 +33,8 @@ struct RnnLayer {
   float* b_hn = nullptr;              // [dirs][H] GRU n-gate hidden bias
   __nv_bfloat16* w_hh_pack = nullptr; // per-CTA W_hh slices for the persistent recurrence (rnn_tc.cu)
   bool tc_recurrence = false;
+  __nv_bfloat16* w_hh_pack_ks = nullptr;   // per-CTA-pair W_hh slices for the K-split recurrence (rnn_ks.cu)
+  bool ks_recurrence = false;
 };
 
 struct HostTensor {
@@ -95,6 +97,15 @@ constexpr int kRnnSyncCounters = kRnnMaxCounters * kRnnCounterStride;
 int rnn_tc_max_in_flight();
 size_t rnn_tc_hbuf_elems(const RnnLayer& L, int B);
 int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
+                 __nv_bfloat16* hbuf, unsigned int* sync_words, int* abort_flag, cudaStream_t st,
+                 const float* h0 = nullptr, const float* c0 = nullptr, float* hT = nullptr, float* cT = nullptr);
+int rnn_tc_init_hbuf(const float* h0, __nv_bfloat16* hbuf, int dirs, int B, int H, int HP, int BP, int n_bgroups,
+                     cudaStream_t st);
+// K-split CTA-pair recurrence (rnn_ks.cu): same contract as rnn_layer_tc, batch groups of 64 rows
+bool rnn_ks_supported(const RnnLayer& L, int sms, int* pairs_out, int* launches_out);
+size_t rnn_ks_pack_elems(const RnnLayer& L);
+int pack_whh_ks(const RnnLayer& L, __nv_bfloat16* out, cudaStream_t st);
+int rnn_layer_ks(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
                  __nv_bfloat16* hbuf, unsigned int* sync_words, int* abort_flag, cudaStream_t st,
                  const float* h0 = nullptr, const float* c0 = nullptr, float* hT = nullptr, float* cT = nullptr);
 int f32_to_bf16_ld(const float* x, __nv_bfloat16* y, int64_t rows, int cols, int ld, cudaStream_t st);

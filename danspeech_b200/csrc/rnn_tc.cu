@@ -765,6 +765,15 @@ __global__ void init_hbuf_kernel(const float* __restrict__ h0, __nv_bfloat16* __
 }
 }  // namespace tc
 
+int rnn_tc_init_hbuf(const float* h0, __nv_bfloat16* hbuf, int dirs, int B, int H, int HP, int BP, int n_bgroups,
+                     cudaStream_t st) {
+  const int64_t total = (int64_t)n_bgroups * dirs * BP * H;
+  tc::init_hbuf_kernel<<<(int)(cdiv64(total, 256) < 1184 ? cdiv64(total, 256) : 1184), 256, 0, st>>>(h0, hbuf, dirs, B, H, HP, BP,
+                                                                                                     n_bgroups);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
 // One BatchRNN layer.  gx [T*B][dirs*G*H] fp32, y [dirs][T][B][H] fp32 (rows t >= len_b are NOT written),
 // hbuf rnn_tc_hbuf_elems() bf16, sync_words = kRnnSyncCounters u32 step counters, abort_flag = one sticky i32 (device).
 // d_len == nullptr: every sequence runs Tmax steps.  h0/c0 (nullptr = zeros) and hT/cT (nullptr = dropped)
@@ -773,6 +782,8 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
                  __nv_bfloat16* hbuf, unsigned int* sync_words, int* abort_flag, cudaStream_t st, const float* h0,
                  const float* c0, float* hT, float* cT) {
   using namespace tc;
+  if (L.ks_recurrence && g_tune.rnn_ksplit.load() && rnn_tc_max_in_flight() > 1)
+    return rnn_layer_ks(L, gx, d_len, B, T, Tmax, y, hbuf, sync_words, abort_flag, st, h0, c0, hT, cT);
   int dev = 0, sms = 148, cpd = 0, launches = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -790,12 +801,8 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   while (slots > 1 && L.dirs * slots * nif > kRnnMaxCounters) --slots;
   DSB_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(__nv_bfloat16) * rnn_tc_hbuf_elems(L, B), st));
   DSB_CUDA(cudaMemsetAsync(sync_words, 0, sizeof(unsigned int) * kRnnSyncCounters, st));   // step counters only; abort flag is sticky
-  if (h0) {
-    const int64_t total = (int64_t)n_bgroups * L.dirs * BP * L.H;
-    init_hbuf_kernel<<<(int)(cdiv64(total, 256) < 1184 ? cdiv64(total, 256) : 1184), 256, 0, st>>>(h0, hbuf, L.dirs, B, L.H, HP,
-                                                                                                 BP, n_bgroups);
-    DSB_CHECK_LAUNCH();
-  }
+  if (h0)
+    if (int e = rnn_tc_init_hbuf(h0, hbuf, L.dirs, B, L.H, HP, BP, n_bgroups, st)) return e;
 
   CUtensorMap tw, th;
   uint64_t dw[2] = {(uint64_t)HP, (uint64_t)L.dirs * cpd * RT_N}, sw[2] = {2, (uint64_t)HP * 2};

@@ -15,18 +15,22 @@ LAYERS = int(os.environ.get("LAYERS", "9"))
 BS = [int(b) for b in os.environ.get("BATCHES", "64,128,192").split(",")]
 NIFS = [int(b) for b in os.environ.get("NIFS", "1,2,3").split(",")]
 REPS = int(os.environ.get("REPS", "3"))
+KSPLITS = [int(b) for b in os.environ.get("KSPLITS", "0,1").split(",")]
 T = 1 + int(SECONDS * 16000) // 160
-model = build_model("DanSpeechPrimary", seed=0, rnn_layers=LAYERS).cuda().eval().set_precision("bf16")
+BIDIR = os.environ.get("BIDIR", "1") == "1"
+H = int(os.environ.get("HIDDEN", "1200"))
+model = build_model("DanSpeechPrimary", seed=0, rnn_layers=LAYERS, bidirectional=BIDIR,
+                    rnn_hidden_size=H).cuda().eval().set_precision("bf16")
 L = N.lib()
 gen = torch.Generator(device="cuda").manual_seed(0)
 for B in BS:
     x = torch.randn((B, 1, 161, T), generator=gen, device="cuda")
     lens = torch.IntTensor([T] * B)
     ref = None
-    for nif in NIFS:
-        if nif > 1 and B <= 64:
+    for nif, ks in [(n, k) for n in NIFS for k in KSPLITS]:
+        if (nif > 1 and B <= 64) or (nif == 1 and ks == 1 and B > 64):
             continue
-        N.tune(rnn_in_flight=nif)
+        N.tune(rnn_in_flight=max(nif, 2) if ks else nif, rnn_ksplit=ks)
         probs, _ = model(x, lens)
         torch.cuda.synchronize()
         L.dsb_profile_reset()
@@ -43,9 +47,9 @@ for B in BS:
         if ref is None:
             ref = probs.clone()
         diff = float((probs - ref).abs().max())
-        print(json.dumps({"B": B, "in_flight": nif, "ms_per_forward": round(ms, 3), "ms_per_64": round(ms * 64 / B, 3),
+        print(json.dumps({"B": B, "in_flight": nif, "ksplit": ks, "ms_per_forward": round(ms, 3), "ms_per_64": round(ms * 64 / B, 3),
                           "rnn_ms_per_64": round(prof["rnn_recurrence"][0] / REPS * 64 / B, 3),
                           "proj_ms_per_64": round(prof["rnn_input_proj"][0] / REPS * 64 / B, 3),
                           "conv_ms_per_64": round(prof["conv"][0] / REPS * 64 / B, 3),
                           "max_prob_diff_vs_first": diff}), flush=True)
-N.tune(rnn_in_flight=3)
+N.tune(rnn_in_flight=3, rnn_ksplit=1)

@@ -579,8 +579,17 @@ def one_cta_set():
     N.tune(**prev)
 
 
+@pytest.fixture(params=[1, 0], ids=["ksplit", "one_cta"])
+def ksplit(request):
+    """Both persistent recurrence kernels: CTA pairs that split K (rnn_ks.cu, the default) and one CTA per W_hh slice."""
+    from danspeech_b200 import _native as N
+    prev = N.tune(rnn_ksplit=request.param)
+    yield request.param
+    N.tune(**prev)
+
+
 @pytest.mark.parametrize("rnn_type,B", [("gru", 150), ("gru", 400), ("lstm", 150), ("rnn", 130)])
-def test_recurrence_groups_in_flight(one_cta_set, rnn_type, B):
+def test_recurrence_groups_in_flight(one_cta_set, ksplit, rnn_type, B):
     """Groups of 64 sequences in flight per CTA (2, 3, and several waves of 3 with a ragged tail) against the oracle on
     single utterances and against the one-group-at-a-time schedule of the same kernels."""
     N = one_cta_set
