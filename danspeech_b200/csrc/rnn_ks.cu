@@ -33,28 +33,34 @@ constexpr int KS_STAGE = KS_N * KS_BK * 2;       // one h chunk (8 KB)
 constexpr int KS_X_BYTES = KS_N * 64 * 4;        // partial-sum exchange [64 batch][64 rows] fp32
 constexpr int KS_MAX_SLOTS = 4;
 constexpr int KS_MAX_NIF = 3;
-constexpr int KS_THREADS = 64 + 256;
+constexpr int KS_THREADS = 64 + 256 + 32;   // producer, MMA issuer, 8 epilogue warps, publisher
 constexpr long long KS_TIMEOUT_CYCLES = 4000000000LL;
 constexpr int KS_SMEM_LIMIT = 227 * 1024;
 
+constexpr int KS_LEN_BYTES = KS_MAX_NIF * KS_N * 4;   // sequence lengths of the groups in flight
 struct KsPlan {
-  int slots, gsz, ring_off, x_off, bar_off, total;
+  int slots, gsz, ring_off, x_off, len_off, bar_off, total;
 };
-// half = K chunks of 64 per CTA
-__host__ __device__ inline KsPlan ks_plan(int half) {
+// half = K chunks of 64 per CTA; want_gsz = chunks per ring slot (0 = default).  A ring slot is one TMA box and one
+// elected MMA region; the ring is as deep as shared memory allows: with few large slots the MMAs of slot g wait for
+// (MMA completion of slot g-2 + TMA latency), with more small ones they run back to back.
+__host__ __device__ inline KsPlan ks_plan(int half, int want_gsz = 0) {
   KsPlan pl;
   const int w_bytes = half * KS_W_BYTES;
-  const int room = KS_SMEM_LIMIT - 1024 - 256 - w_bytes - KS_X_BYTES;   // 1 KB alignment slack, 256 B of barriers
+  const int room = KS_SMEM_LIMIT - 1024 - 256 - KS_LEN_BYTES - w_bytes - KS_X_BYTES;   // 1 KB alignment slack, barriers
   const int stages = room > 0 ? room / KS_STAGE : 0;
-  int gsz = stages >= 8 ? 4 : stages >= 6 ? 3 : stages >= 4 ? 2 : stages >= 2 ? 1 : 0;
+  int gsz = want_gsz > 0 ? want_gsz : 2;
+  if (gsz > 4) gsz = 4;
+  while (gsz > 1 && stages / gsz < 2) --gsz;
   if (gsz > half) gsz = half;
-  int slots = gsz ? stages / gsz : 0;
+  int slots = gsz > 0 ? stages / gsz : 0;
   if (slots > KS_MAX_SLOTS) slots = KS_MAX_SLOTS;
   pl.slots = slots;
   pl.gsz = gsz;
   pl.ring_off = w_bytes;
   pl.x_off = w_bytes + slots * gsz * KS_STAGE;
-  pl.bar_off = pl.x_off + KS_X_BYTES;
+  pl.len_off = pl.x_off + KS_X_BYTES;
+  pl.bar_off = pl.len_off + KS_LEN_BYTES;
   pl.total = pl.bar_off + 256 + 1024;
   return pl;
 }
@@ -76,6 +82,7 @@ struct KsParams {
   int pairs;       // CTA pairs per (direction, slot)
   int n_bgroups, slots;
   int nkc, half;   // K chunks of 64 in total / per CTA
+  int ring_gsz;    // chunks per ring slot (ks_plan)
   unsigned long long* dbg;
 };
 
@@ -172,17 +179,19 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   constexpr int TMEM_COLS = NIF == 1 ? 64 : (NIF == 2 ? 128 : 256);
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  const KsPlan pl = ks_plan(p.half);
+  const KsPlan pl = ks_plan(p.half, p.ring_gsz);
   unsigned char* sW = smem;
   unsigned char* sA = smem + pl.ring_off;
   float* sX = reinterpret_cast<float*>(smem + pl.x_off);
+  int* sLen = reinterpret_cast<int*>(smem + pl.len_off);             // [KS_MAX_NIF][64] lengths of the groups in flight
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + pl.bar_off);   // [KS_MAX_SLOTS] ring slot landed
   uint64_t* gempty = full + KS_MAX_SLOTS;                            // [KS_MAX_SLOTS] ring slot consumed
   uint64_t* wbar = gempty + KS_MAX_SLOTS;
   uint64_t* dfull = wbar + 1;                                        // [KS_MAX_NIF] accumulator complete
   uint64_t* xfull = dfull + KS_MAX_NIF;     // the peer's partial sums for my rows have arrived in sX (128 arrivals)
   uint64_t* xfree = xfull + 1;              // the peer is done with ITS sX: I may overwrite it (1 arrival)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfree + 1);
+  uint64_t* hdone = xfree + 1;              // [4] all 256 epilogue threads have issued the h stores of item ic (slot ic & 3)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hdone + 4);
   const int n_slots = pl.slots, gsz = pl.gsz;
   const int gps = (p.half + gsz - 1) / gsz;   // ring-slot uses per item
 
@@ -205,6 +214,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     for (int i = 0; i < KS_MAX_NIF; ++i) mbar_init(&dfull[i], 1);
     mbar_init(xfull, 128);
     mbar_init(xfree, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&hdone[i], 256);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -353,6 +363,37 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       p.dbg[blockIdx.x * 16 + 3] = d_wait0;
       p.dbg[blockIdx.x * 16 + 4] = d_rest;
     }
+  } else if (warp == 10) {
+    // ---- publisher: once all epilogue threads have issued the h stores of an item, publish the step (release at GPU
+    // scope: waits for the acknowledgements of those stores, ~2 k cycles) and hand the exchange buffer back to the
+    // peer.  On its own warp this round trip is off the epilogue warps' path: they go straight on to the next item.
+    bool ok = true;
+    unsigned ic = 0;
+    unsigned long long d_pub = 0;
+    const uint32_t peer_xfree = mapa_u32(smem_u32(xfree), (uint32_t)(rank ^ 1));
+    for (int k0 = 0; ok && slot + k0 * p.slots < p.n_bgroups; k0 += NIF) {
+      int Tg[NIF], Tw = 0;
+#pragma unroll
+      for (int i = 0; i < NIF; ++i) {
+        Tg[i] = ks_group_steps(p, slot + (k0 + i) * p.slots);
+        Tw = max(Tw, Tg[i]);
+      }
+      for (int s = 0; s < Tw && ok; ++s) {
+#pragma unroll
+        for (int i = 0; i < NIF; ++i)
+          if (ok && s < Tg[i]) {
+            ok = __all_sync(0xffffffffu, ks_wait(&hdone[ic & 3], (ic >> 2) & 1u, p.abort_flag));
+            if (ok && lane == 0) {
+              long long c0 = clock64();
+              ks_red_release(ctr0 + i * kRnnCounterStride, 1u);   // publish h_t (release: cumulative over the arrivals)
+              mbar_arrive_cluster(peer_xfree);                    // the peer may overwrite my sX with its next item
+              d_pub += clock64() - c0;
+            }
+            ++ic;
+          }
+      }
+    }
+    if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + 10] = d_pub;
   } else {
     // ---- epilogue: 8 warps.  Accumulator row m = 32*q + lane (q = warp % 4) is W row m of the pair; rows
     //      [64*rho, 64*rho + 64) hold the gates of CTA rho's units; the two warps of a quarter split the 64 batch columns.
@@ -378,7 +419,6 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
     const uint32_t peer_x = mapa_u32(smem_u32(sX), (uint32_t)(rank ^ 1));
     const uint32_t peer_xfull = mapa_u32(smem_u32(xfull), (uint32_t)(rank ^ 1));
-    const uint32_t peer_xfree = mapa_u32(smem_u32(xfree), (uint32_t)(rank ^ 1));
     unsigned ic = 0;   // items processed (both CTAs of the pair walk the same item sequence)
     unsigned long long e_load = 0, e_wait = 0, e_xchg = 0, e_math = 0, e_pub = 0;
 
@@ -387,27 +427,24 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       // 1. input-projection pre-activations of this step for my pairs (consecutive threads: consecutive units)
       float gxv[PP][GATES];
       bool act[PP];
-      int tt[PP], bb[PP];
+      int tt[PP];
 #pragma unroll
       for (int k = 0; k < PP; ++k) {
         const int b = bg * KS_N + pb[k];
         const int unit = unit0 + pu[k];
-        const bool in = b < p.B && unit < p.H;
-        const int len = in ? (p.lens ? __ldg(p.lens + b) : p.Tmax) : 0;
-        act[k] = in && s < len;
+        const int len = unit < p.H ? sLen[i * KS_N + pb[k]] : 0;     // 0 for rows beyond the batch
+        act[k] = s < len;
         tt[k] = dir == 0 ? s : len - 1 - s;
-        bb[k] = b;
         if (act[k]) {
           const float* gp = p.gx + ((size_t)tt[k] * p.B + b) * ncol + (size_t)dir * GATES * p.H + unit;
 #pragma unroll
           for (int g = 0; g < GATES; ++g) gxv[k][g] = __ldg(gp + (size_t)g * p.H);
-          if (s + 1 < len) {   // the group's next step: pulled into L2 one round of items ahead
+          if (s + 1 < len && ((pu[k] & 7) == 0 || pu[k] == UR - 1)) {
+            // the group's next step: pulled into L2 one round of items ahead
             const int tn = dir == 0 ? s + 1 : len - 2 - s;
             const float* gn = p.gx + ((size_t)tn * p.B + b) * ncol + (size_t)dir * GATES * p.H + unit;
-            if ((pu[k] & 7) == 0 || pu[k] == UR - 1) {
 #pragma unroll
-              for (int g = 0; g < GATES; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)g * p.H));
-            }
+            for (int g = 0; g < GATES; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)g * p.H));
           }
         }
       }
@@ -467,15 +504,12 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         }
       }
       long long e4 = clock64();
-      ks_named_bar(2, 256);                              // all reads of sX done, all h stores issued
-      if (et == 0) {
-        ks_red_release(ctr0 + i * kRnnCounterStride, 1u);   // publish h_t (release: cumulative over the CTA)
-        mbar_arrive_cluster(peer_xfree);                    // the peer may overwrite my sX with the next item
-      }
-      // y_t -> global (fp32), after the publish: nobody waits on these stores
+      // all reads of sX done and all h stores issued: the publisher warp takes it from here (release = this arrive)
+      mbar_arrive(&hdone[ic & 3]);
+      // y_t -> global (fp32): nobody waits on these stores
 #pragma unroll
       for (int k = 0; k < PP; ++k)
-        if (act[k]) p.y[(((size_t)dir * p.T + tt[k]) * p.B + bb[k]) * p.H + unit0 + pu[k]] = hp[k];
+        if (act[k]) p.y[(((size_t)dir * p.T + tt[k]) * p.B + bg * KS_N + pb[k]) * p.H + unit0 + pu[k]] = hp[k];
       ++ic;
       e_load += e1 - e0; e_wait += e2 - e1; e_xchg += e3 - e2; e_math += e4 - e3; e_pub += clock64() - e4;
       return true;
@@ -487,11 +521,16 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     bool alive = true;
     for (int k0 = 0; alive && slot + k0 * p.slots < p.n_bgroups; k0 += NIF) {
       int Tg[NIF], Tw = 0;
+      ks_named_bar(2, 256);      // every thread is done with the previous wave's lengths
 #pragma unroll
       for (int i = 0; i < NIF; ++i) {
         const int bg = slot + (k0 + i) * p.slots;
         Tg[i] = ks_group_steps(p, bg);
         Tw = max(Tw, Tg[i]);
+        if (et < KS_N) {
+          const int b = bg * KS_N + et;
+          sLen[i * KS_N + et] = (bg < p.n_bgroups && b < p.B) ? (p.lens ? p.lens[b] : p.Tmax) : 0;
+        }
 #pragma unroll
         for (int k = 0; k < PP; ++k) {
           const int b = bg * KS_N + pb[k], unit = unit0 + pu[k];
@@ -500,6 +539,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           cst[i][k] = (GATES == 4 && p.c0 && in) ? p.c0[((size_t)dir * p.B + b) * p.H + unit] : 0.f;
         }
       }
+      ks_named_bar(2, 256);
       for (int s = 0; s < Tw && alive; ++s) {
 #pragma unroll
         for (int i = 0; i < NIF; ++i)
@@ -521,7 +561,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         }
       }
     }
-    if (p.dbg && et == 0) {
+    if (p.dbg && et == 64) {
       p.dbg[blockIdx.x * 16 + 5] = e_load;
       p.dbg[blockIdx.x * 16 + 6] = e_wait;
       p.dbg[blockIdx.x * 16 + 7] = e_xchg;
@@ -569,7 +609,7 @@ static int ks_half(int H) { return cdiv(cdiv(H, 64), 2); }
 bool rnn_ks_supported(const RnnLayer& L, int sms, int* pairs_out, int* launches_out) {
   const int UR = tc::ks_units(L.gates);
   const int pairs = cdiv(L.H, 2 * UR);
-  const tc::KsPlan pl = tc::ks_plan(ks_half(L.H));
+  const tc::KsPlan pl = tc::ks_plan(ks_half(L.H), g_tune.rnn_ring_gsz.load());
   if (pl.slots < 2 || pl.gsz < 1 || pl.total > tc::KS_SMEM_LIMIT || 2 * pairs > sms) return false;
   if (pairs_out) *pairs_out = pairs;
   if (launches_out) *launches_out = (L.dirs * 2 * pairs <= sms) ? 1 : L.dirs;
@@ -615,7 +655,8 @@ int rnn_layer_ks(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   if (h0)
     if (int e = rnn_tc_init_hbuf(h0, hbuf, L.dirs, B, L.H, HP, KS_N, n_bgroups, st)) return e;
 
-  const KsPlan pl = ks_plan(half);
+  const int ring_gsz = g_tune.rnn_ring_gsz.load();
+  const KsPlan pl = ks_plan(half, ring_gsz);
   CUtensorMap tw, th;
   uint64_t dw[2] = {(uint64_t)half * KS_BK, (uint64_t)L.dirs * pairs * 2 * KS_M}, sw[2] = {2, (uint64_t)half * KS_BK * 2};
   uint32_t bw[2] = {KS_BK, KS_M};
@@ -630,7 +671,7 @@ int rnn_layer_ks(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.counters = sync_words; p.abort_flag = abort_flag;
   p.h0 = h0; p.c0 = c0; p.hT = hT; p.cT = cT;
   p.B = B; p.H = L.H; p.HP = HP; p.T = T; p.Tmax = Tmax;
-  p.dirs = L.dirs; p.pairs = pairs; p.n_bgroups = n_bgroups; p.slots = slots; p.nkc = nkc; p.half = half;
+  p.dirs = L.dirs; p.pairs = pairs; p.n_bgroups = n_bgroups; p.slots = slots; p.nkc = nkc; p.half = half; p.ring_gsz = ring_gsz;
   const void* fn = nullptr;
 #define KS_PICK(G) \
   fn = nif == 1 ? (const void*)rnn_ks_kernel<G, 1> : nif == 2 ? (const void*)rnn_ks_kernel<G, 2> : (const void*)rnn_ks_kernel<G, 3>
@@ -674,12 +715,12 @@ int rnn_layer_ks(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     DSB_CUDA(cudaStreamSynchronize(st));
     DSB_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * 16 * grid, cudaMemcpyDeviceToHost));
     cudaFree(dbg);
-    const char* names[10] = {"prod.spin", "prod.issue", "prod.wait_empty", "mma.wait_first", "mma.rest", "epi.gload",
-                             "epi.wait_mma", "epi.exchange", "epi.math_store", "epi.publish"};
+    const char* names[11] = {"prod.spin", "prod.issue", "prod.wait_empty", "mma.wait_first", "mma.rest", "epi.gload",
+                             "epi.wait_mma", "epi.exchange", "epi.math_store", "epi.y_store", "publisher.release"};
     const int items = cdiv(n_bgroups, slots) * Tmax;
     fprintf(stderr, "[rnn_ks debug] H=%d B=%d Tmax=%d grid=%d groups=%d slots=%d in flight=%d ring=%dx%d  cycles/item "
                     "(avg over CTAs | max CTA)\n", L.H, B, Tmax, grid, n_bgroups, slots, nif, pl.slots, pl.gsz);
-    for (int k = 0; k < 10; ++k) {
+    for (int k = 0; k < 11; ++k) {
       double sum = 0, mx = 0;
       for (int c = 0; c < grid; ++c) { double v = (double)h[c * 16 + k] / items; sum += v; mx = v > mx ? v : mx; }
       fprintf(stderr, "   %-16s %9.0f | %9.0f\n", names[k], sum / grid, mx);

@@ -54,6 +54,7 @@ int dsb_profile_read(int stage, double* total_ms, int* spans);
  *   "rnn_max_slots"  >= 0  cap on the independent CTA sets of the recurrence (0 = as many as fit, default)
  *   "gx_bf16"        0/1   gate pre-activations of the input projection stored as bf16 (default 0 = fp32)
  *   "rnn_ksplit"     0/1   recurrence on CTA pairs that split K (default 1); 0 = one CTA per W_hh slice
+ *   "rnn_ring_gsz"   0..4  K chunks of 64 per slot of the CTA-pair kernel's h ring (0 = default, 2)
  * dsb_tune_set returns DSB_ERR_INVALID for an unknown key or an out-of-range value; dsb_tune_get returns the value
  * or -1 for an unknown key. */
 int dsb_tune_set(const char* key, int value);
