@@ -133,6 +133,22 @@ __device__ __forceinline__ bool ks_wait_cluster(uint64_t* bar, uint32_t parity, 
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// explicit shared-space accesses through 32-bit addresses: no 64-bit generic pointers to keep alive (the epilogue runs
+// at the register cap, and a spilled pointer costs an L2 round trip per reload -- every cluster-scope acquire /
+// release of the exchange invalidates L1, local memory included)
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ bool ks_bar_red_and(bool pred, int id, int nthreads) {
   uint32_t r;
   asm volatile(
@@ -385,8 +401,8 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             ok = __all_sync(0xffffffffu, ks_wait(&hdone[ic & 3], (ic >> 2) & 1u, p.abort_flag));
             if (ok && lane == 0) {
               long long c0 = clock64();
-              ks_red_release(ctr0 + i * kRnnCounterStride, 1u);   // publish h_t (release: cumulative over the arrivals)
               mbar_arrive_cluster(peer_xfree);                    // the peer may overwrite my sX with its next item
+              ks_red_release(ctr0 + i * kRnnCounterStride, 1u);   // publish h_t (release: cumulative over the arrivals)
               d_pub += clock64() - c0;
             }
             ++ic;
@@ -417,7 +433,9 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     }
     float hprev[NIF][PP], cst[NIF][PP];
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
-    const uint32_t peer_x = mapa_u32(smem_u32(sX), (uint32_t)(rank ^ 1));
+    const uint32_t sx = smem_u32(sX), slen = smem_u32(sLen);
+    const uint32_t my_x = sx + (uint32_t)((cb * 64 + j) * 4);                       // (batch cb, row j) of my sX
+    const uint32_t peer_x = mapa_u32(sx, (uint32_t)(rank ^ 1)) + (uint32_t)((cb * 64 + j) * 4);
     const uint32_t peer_xfull = mapa_u32(smem_u32(xfull), (uint32_t)(rank ^ 1));
     unsigned ic = 0;   // items processed (both CTAs of the pair walk the same item sequence)
     unsigned long long e_load = 0, e_wait = 0, e_xchg = 0, e_math = 0, e_pub = 0;
@@ -426,23 +444,19 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       long long e0 = clock64();
       // 1. input-projection pre-activations of this step for my pairs (consecutive threads: consecutive units)
       float gxv[PP][GATES];
-      bool act[PP];
-      int tt[PP];
+      int tt[PP];          // time index of the pair, -1 = not active at this step
 #pragma unroll
       for (int k = 0; k < PP; ++k) {
-        const int b = bg * KS_N + pb[k];
         const int unit = unit0 + pu[k];
-        const int len = unit < p.H ? sLen[i * KS_N + pb[k]] : 0;     // 0 for rows beyond the batch
-        act[k] = s < len;
-        tt[k] = dir == 0 ? s : len - 1 - s;
-        if (act[k]) {
-          const float* gp = p.gx + ((size_t)tt[k] * p.B + b) * ncol + (size_t)dir * GATES * p.H + unit;
+        const int len = unit < p.H ? lds_s32(slen + (uint32_t)((i * KS_N + pb[k]) * 4)) : 0;   // 0 for rows beyond the batch
+        tt[k] = s < len ? (dir == 0 ? s : len - 1 - s) : -1;
+        if (tt[k] >= 0) {
+          const float* gp = p.gx + ((size_t)tt[k] * p.B + (bg * KS_N + pb[k])) * ncol + (size_t)dir * GATES * p.H + unit;
 #pragma unroll
           for (int g = 0; g < GATES; ++g) gxv[k][g] = __ldg(gp + (size_t)g * p.H);
           if (s + 1 < len && ((pu[k] & 7) == 0 || pu[k] == UR - 1)) {
             // the group's next step: pulled into L2 one round of items ahead
-            const int tn = dir == 0 ? s + 1 : len - 2 - s;
-            const float* gn = p.gx + ((size_t)tn * p.B + b) * ncol + (size_t)dir * GATES * p.H + unit;
+            const float* gn = gp + (dir == 0 ? (ptrdiff_t)p.B * ncol : -(ptrdiff_t)p.B * ncol);
 #pragma unroll
             for (int g = 0; g < GATES; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)g * p.H));
           }
@@ -453,54 +467,59 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       bool ok = ks_wait(&dfull[i], (uint32_t)((steps_before + (unsigned)s) & 1u), p.abort_flag);
       long long e2 = clock64();
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(t_addr + (uint32_t)(i * 64), r);
-      tmem_ld_wait();
-      tc_fence_before();
       // 3. partial-sum exchange: my K half of the peer's rows goes to the peer, the peer's half of my rows is added
       if (!is_own) {
         if (ic > 0) ok = ks_wait_cluster(xfree, (ic - 1) & 1u, p.abort_flag) && ok;   // the peer has consumed item ic-1
-        if (ok) {
-          const uint32_t dst = peer_x + (uint32_t)((cb * 64 + j) * 4);
-#pragma unroll
-          for (int c = 0; c < 32; ++c) st_cluster_f32(dst + (uint32_t)(c * 256), __uint_as_float(r[c]));
-        }
-        mbar_arrive_cluster(peer_xfull);    // release.cluster: my stores above are visible to the peer's waiters
       } else {
         ok = ks_wait_cluster(xfull, ic & 1u, p.abort_flag) && ok;
-        if (ok) {
-          float* x = sX + cb * 64 + j;
+      }
 #pragma unroll
-          for (int c = 0; c < 32; ++c) x[c * 64] += __uint_as_float(r[c]);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[16];
+        tmem_ld16(t_addr + (uint32_t)(i * 64 + hh * 16), r);
+        tmem_ld_wait();
+        if (ok) {
+          if (!is_own) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) st_cluster_f32(peer_x + (uint32_t)((hh * 16 + c) * 256), __uint_as_float(r[c]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const uint32_t a = my_x + (uint32_t)((hh * 16 + c) * 256);
+              sts_f32(a, lds_f32(a) + __uint_as_float(r[c]));
+            }
+          }
         }
       }
+      tc_fence_before();
+      if (!is_own) mbar_arrive_cluster(peer_xfull);    // release.cluster: my stores above are visible to the peer's waiters
       long long e3 = clock64();
       if (!ks_bar_red_and(ok, 1, 256)) return false;     // sX complete (and uniform abort decision)
       // 4. gates
-      const int nxt = (bg * 2 + ((s + 1) & 1)) * p.dirs + dir;
+      const size_t nxt = (size_t)((bg * 2 + ((s + 1) & 1)) * p.dirs + dir) * KS_N;
 #pragma unroll
       for (int k = 0; k < PP; ++k) {
-        if (act[k]) {
-          const float* a = sX + pb[k] * 64 + pu[k] * GATES;
+        if (tt[k] >= 0) {
+          const uint32_t a = sx + (uint32_t)((pb[k] * 64 + pu[k] * GATES) * 4);
           float hn;
           if (GATES == 3) {
-            const float rg = ks_sigmoid(gxv[k][0] + a[0]);
-            const float zg = ks_sigmoid(gxv[k][1 % GATES] + a[1 % GATES]);
-            const float ng = ks_tanh(gxv[k][2 % GATES] + rg * (a[2 % GATES] + bhn[k]));
+            const float rg = ks_sigmoid(gxv[k][0] + lds_f32(a));
+            const float zg = ks_sigmoid(gxv[k][1 % GATES] + lds_f32(a + 4 * (1 % GATES)));
+            const float ng = ks_tanh(gxv[k][2 % GATES] + rg * (lds_f32(a + 4 * (2 % GATES)) + bhn[k]));
             hn = (1.0f - zg) * ng + zg * hp[k];
           } else if (GATES == 4) {
-            const float ig = ks_sigmoid(gxv[k][0] + a[0]);
-            const float fg = ks_sigmoid(gxv[k][1 % GATES] + a[1 % GATES]);
-            const float gg = ks_tanh(gxv[k][2 % GATES] + a[2 % GATES]);
-            const float og = ks_sigmoid(gxv[k][3 % GATES] + a[3 % GATES]);
+            const float ig = ks_sigmoid(gxv[k][0] + lds_f32(a));
+            const float fg = ks_sigmoid(gxv[k][1 % GATES] + lds_f32(a + 4 * (1 % GATES)));
+            const float gg = ks_tanh(gxv[k][2 % GATES] + lds_f32(a + 4 * (2 % GATES)));
+            const float og = ks_sigmoid(gxv[k][3 % GATES] + lds_f32(a + 4 * (3 % GATES)));
             cs[k] = fg * cs[k] + ig * gg;
             hn = og * ks_tanh(cs[k]);
           } else {
-            hn = ks_tanh(gxv[k][0] + a[0]);
+            hn = ks_tanh(gxv[k][0] + lds_f32(a));
           }
           hp[k] = hn;
           // h_t -> exchange buffer of the next step (bf16): consecutive threads write consecutive units of a row
-          p.hbuf[((size_t)nxt * KS_N + pb[k]) * p.HP + unit0 + pu[k]] = __float2bfloat16_rn(hn);
+          p.hbuf[(nxt + pb[k]) * p.HP + unit0 + pu[k]] = __float2bfloat16_rn(hn);
         }
       }
       long long e4 = clock64();
@@ -509,7 +528,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       // y_t -> global (fp32): nobody waits on these stores
 #pragma unroll
       for (int k = 0; k < PP; ++k)
-        if (act[k]) p.y[(((size_t)dir * p.T + tt[k]) * p.B + bg * KS_N + pb[k]) * p.H + unit0 + pu[k]] = hp[k];
+        if (tt[k] >= 0) p.y[(((size_t)dir * p.T + tt[k]) * p.B + bg * KS_N + pb[k]) * p.H + unit0 + pu[k]] = hp[k];
       ++ic;
       e_load += e1 - e0; e_wait += e2 - e1; e_xchg += e3 - e2; e_math += e4 - e3; e_pub += clock64() - e4;
       return true;
@@ -529,7 +548,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         Tw = max(Tw, Tg[i]);
         if (et < KS_N) {
           const int b = bg * KS_N + et;
-          sLen[i * KS_N + et] = (bg < p.n_bgroups && b < p.B) ? (p.lens ? p.lens[b] : p.Tmax) : 0;
+          sLen[i * KS_N + et] = (bg < p.n_bgroups && b < p.B) ? (p.lens ? p.lens[b] : p.Tmax) : 0;   // read back with lds_s32
         }
 #pragma unroll
         for (int k = 0; k < PP; ++k) {
