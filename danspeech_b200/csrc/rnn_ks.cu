@@ -30,7 +30,8 @@ constexpr int KS_M = 128;                        // W_hh rows per CTA pair
 constexpr int KS_N = 64;                         // sequences per batch group
 constexpr int KS_W_BYTES = KS_M * KS_BK * 2;     // one resident W chunk (16 KB)
 constexpr int KS_STAGE = KS_N * KS_BK * 2;       // one h chunk (8 KB)
-constexpr int KS_X_BYTES = KS_N * 64 * 4;        // partial-sum exchange [64 batch][64 rows] fp32
+constexpr int KS_XS = 68;                        // floats per row of the exchange buffer: 64 batch + 4 (bank spread)
+constexpr int KS_X_BYTES = 64 * KS_XS * 4;       // partial-sum exchange [64 rows][64 batch (+4)] fp32
 constexpr int KS_MAX_SLOTS = 4;
 constexpr int KS_MAX_NIF = 3;
 constexpr int KS_THREADS = 64 + 256 + 32;   // producer, MMA issuer, 8 epilogue warps, publisher
@@ -102,12 +103,13 @@ __device__ __forceinline__ bool ks_wait(uint64_t* bar, uint32_t parity, int* abo
   }
   return true;
 }
-// same, acquiring at cluster scope: the data guarded by the barrier was written by the peer CTA
+// same at cluster scope, relaxed: the barrier is arrived on by the peer CTA and only orders the REUSE of a buffer whose
+// reads completed before the arrive (no data travels with it)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -130,8 +132,24 @@ __device__ __forceinline__ bool ks_wait_cluster(uint64_t* bar, uint32_t parity, 
   }
   return true;
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+// Asynchronous store into the peer CTA's shared memory that counts its bytes on the PEER's mbarrier when it lands
+// (SASS: STAS): producer/consumer hand-over through distributed shared memory without any fence -- a cluster-scope
+// release / acquire pair costs a MEMBAR + CCTL.IVALL (L1 invalidate) in every participating thread per item.
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t mbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 // explicit shared-space accesses through 32-bit addresses: no 64-bit generic pointers to keep alive (the epilogue runs
 // at the register cap, and a spilled pointer costs an L2 round trip per reload -- every cluster-scope acquire /
@@ -204,7 +222,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   uint64_t* gempty = full + KS_MAX_SLOTS;                            // [KS_MAX_SLOTS] ring slot consumed
   uint64_t* wbar = gempty + KS_MAX_SLOTS;
   uint64_t* dfull = wbar + 1;                                        // [KS_MAX_NIF] accumulator complete
-  uint64_t* xfull = dfull + KS_MAX_NIF;     // the peer's partial sums for my rows have arrived in sX (128 arrivals)
+  uint64_t* xfull = dfull + KS_MAX_NIF;     // the peer's partial sums for my rows have landed in sX (16 KB of st.async)
   uint64_t* xfree = xfull + 1;              // the peer is done with ITS sX: I may overwrite it (1 arrival)
   uint64_t* hdone = xfree + 1;              // [4] all 256 epilogue threads have issued the h stores of item ic (slot ic & 3)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hdone + 4);
@@ -228,7 +246,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     for (int i = 0; i < KS_MAX_SLOTS; ++i) mbar_init(&gempty[i], 1);
     mbar_init(wbar, 1);
     for (int i = 0; i < KS_MAX_NIF; ++i) mbar_init(&dfull[i], 1);
-    mbar_init(xfull, 128);
+    mbar_init(xfull, 1);       // one local arrive.expect_tx per item + the bytes of the peer's st.async
     mbar_init(xfree, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&hdone[i], 256);
     fence_mbar_init();
@@ -401,7 +419,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             ok = __all_sync(0xffffffffu, ks_wait(&hdone[ic & 3], (ic >> 2) & 1u, p.abort_flag));
             if (ok && lane == 0) {
               long long c0 = clock64();
-              mbar_arrive_cluster(peer_xfree);                    // the peer may overwrite my sX with its next item
+              mbar_arrive_cluster_relaxed(peer_xfree);            // the peer may overwrite my sX with its next item
               ks_red_release(ctr0 + i * kRnnCounterStride, 1u);   // publish h_t (release: cumulative over the arrivals)
               d_pub += clock64() - c0;
             }
@@ -418,6 +436,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     const int ch = (warp - 2) >> 2;
     const int j = ((q & 1) << 5) + lane;           // row inside its owner's 64
     const bool is_own = (q >> 1) == rank;
+    const bool x_leader = is_own && ch == 0 && (q & 1) == 0 && lane == 0;
     const int cb = ch * 32;                        // first batch column of this thread
     const int ncol = p.dirs * GATES * p.H;
     const int unit0 = (pair * 2 + rank) * UR;
@@ -434,21 +453,26 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     float hprev[NIF][PP], cst[NIF][PP];
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
     const uint32_t sx = smem_u32(sX), slen = smem_u32(sLen);
-    const uint32_t my_x = sx + (uint32_t)((cb * 64 + j) * 4);                       // (batch cb, row j) of my sX
-    const uint32_t peer_x = mapa_u32(sx, (uint32_t)(rank ^ 1)) + (uint32_t)((cb * 64 + j) * 4);
+    const uint32_t my_x = sx + (uint32_t)((j * KS_XS + cb) * 4);                    // (row j, batch cb) of my sX
+    const uint32_t peer_x = mapa_u32(sx, (uint32_t)(rank ^ 1)) + (uint32_t)((j * KS_XS + cb) * 4);
     const uint32_t peer_xfull = mapa_u32(smem_u32(xfull), (uint32_t)(rank ^ 1));
     unsigned ic = 0;   // items processed (both CTAs of the pair walk the same item sequence)
-    unsigned long long e_load = 0, e_wait = 0, e_xchg = 0, e_math = 0, e_pub = 0;
+    unsigned long long e_load = 0, e_wait = 0, e_xchg = 0, e_math = 0, e_pub = 0, e_len = 0;
 
     auto item = [&](int i, int s, int bg, unsigned steps_before, float (&hp)[PP], float (&cs)[PP]) -> bool {
       long long e0 = clock64();
       // 1. input-projection pre-activations of this step for my pairs (consecutive threads: consecutive units)
       float gxv[PP][GATES];
       int tt[PP];          // time index of the pair, -1 = not active at this step
+      int lens_k[PP];
+#pragma unroll
+      for (int k = 0; k < PP; ++k)
+        lens_k[k] = unit0 + pu[k] < p.H ? lds_s32(slen + (uint32_t)((i * KS_N + pb[k]) * 4)) : 0;   // 0 beyond the batch
+      long long e0b = clock64();
 #pragma unroll
       for (int k = 0; k < PP; ++k) {
         const int unit = unit0 + pu[k];
-        const int len = unit < p.H ? lds_s32(slen + (uint32_t)((i * KS_N + pb[k]) * 4)) : 0;   // 0 for rows beyond the batch
+        const int len = lens_k[k];
         tt[k] = s < len ? (dir == 0 ? s : len - 1 - s) : -1;
         if (tt[k] >= 0) {
           const float* gp = p.gx + ((size_t)tt[k] * p.B + (bg * KS_N + pb[k])) * ncol + (size_t)dir * GATES * p.H + unit;
@@ -471,7 +495,8 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       if (!is_own) {
         if (ic > 0) ok = ks_wait_cluster(xfree, (ic - 1) & 1u, p.abort_flag) && ok;   // the peer has consumed item ic-1
       } else {
-        ok = ks_wait_cluster(xfull, ic & 1u, p.abort_flag) && ok;
+        if (x_leader) mbar_arrive_expect_tx(xfull, 64u * 64u * 4u);                    // this item's 16 KB from the peer
+        ok = ks_wait(xfull, ic & 1u, p.abort_flag) && ok;
       }
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -479,20 +504,24 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         tmem_ld16(t_addr + (uint32_t)(i * 64 + hh * 16), r);
         tmem_ld_wait();
         if (ok) {
+          // 16-byte accesses: a quarter warp touches 8 rows 272 bytes apart = all 32 banks once
           if (!is_own) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) st_cluster_f32(peer_x + (uint32_t)((hh * 16 + c) * 256), __uint_as_float(r[c]));
+            for (int c = 0; c < 16; c += 4)
+              st_async_v4(peer_x + (uint32_t)((hh * 16 + c) * 4), peer_xfull, r[c], r[c + 1], r[c + 2], r[c + 3]);
           } else {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const uint32_t a = my_x + (uint32_t)((hh * 16 + c) * 256);
-              sts_f32(a, lds_f32(a) + __uint_as_float(r[c]));
+            for (int c = 0; c < 16; c += 4) {
+              const uint32_t a = my_x + (uint32_t)((hh * 16 + c) * 4);
+              float4 v = lds_v4(a);
+              v.x += __uint_as_float(r[c]); v.y += __uint_as_float(r[c + 1]);
+              v.z += __uint_as_float(r[c + 2]); v.w += __uint_as_float(r[c + 3]);
+              sts_v4(a, v);
             }
           }
         }
       }
       tc_fence_before();
-      if (!is_own) mbar_arrive_cluster(peer_xfull);    // release.cluster: my stores above are visible to the peer's waiters
       long long e3 = clock64();
       if (!ks_bar_red_and(ok, 1, 256)) return false;     // sX complete (and uniform abort decision)
       // 4. gates
@@ -500,18 +529,18 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 #pragma unroll
       for (int k = 0; k < PP; ++k) {
         if (tt[k] >= 0) {
-          const uint32_t a = sx + (uint32_t)((pb[k] * 64 + pu[k] * GATES) * 4);
+          const uint32_t a = sx + (uint32_t)((pu[k] * GATES * KS_XS + pb[k]) * 4);   // gate g: + g rows
           float hn;
           if (GATES == 3) {
             const float rg = ks_sigmoid(gxv[k][0] + lds_f32(a));
-            const float zg = ks_sigmoid(gxv[k][1 % GATES] + lds_f32(a + 4 * (1 % GATES)));
-            const float ng = ks_tanh(gxv[k][2 % GATES] + rg * (lds_f32(a + 4 * (2 % GATES)) + bhn[k]));
+            const float zg = ks_sigmoid(gxv[k][1 % GATES] + lds_f32(a + 4 * KS_XS * (1 % GATES)));
+            const float ng = ks_tanh(gxv[k][2 % GATES] + rg * (lds_f32(a + 4 * KS_XS * (2 % GATES)) + bhn[k]));
             hn = (1.0f - zg) * ng + zg * hp[k];
           } else if (GATES == 4) {
             const float ig = ks_sigmoid(gxv[k][0] + lds_f32(a));
-            const float fg = ks_sigmoid(gxv[k][1 % GATES] + lds_f32(a + 4 * (1 % GATES)));
-            const float gg = ks_tanh(gxv[k][2 % GATES] + lds_f32(a + 4 * (2 % GATES)));
-            const float og = ks_sigmoid(gxv[k][3 % GATES] + lds_f32(a + 4 * (3 % GATES)));
+            const float fg = ks_sigmoid(gxv[k][1 % GATES] + lds_f32(a + 4 * KS_XS * (1 % GATES)));
+            const float gg = ks_tanh(gxv[k][2 % GATES] + lds_f32(a + 4 * KS_XS * (2 % GATES)));
+            const float og = ks_sigmoid(gxv[k][3 % GATES] + lds_f32(a + 4 * KS_XS * (3 % GATES)));
             cs[k] = fg * cs[k] + ig * gg;
             hn = og * ks_tanh(cs[k]);
           } else {
@@ -530,6 +559,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       for (int k = 0; k < PP; ++k)
         if (tt[k] >= 0) p.y[(((size_t)dir * p.T + tt[k]) * p.B + bg * KS_N + pb[k]) * p.H + unit0 + pu[k]] = hp[k];
       ++ic;
+      e_len += e0b - e0;
       e_load += e1 - e0; e_wait += e2 - e1; e_xchg += e3 - e2; e_math += e4 - e3; e_pub += clock64() - e4;
       return true;
     };
@@ -586,6 +616,7 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       p.dbg[blockIdx.x * 16 + 7] = e_xchg;
       p.dbg[blockIdx.x * 16 + 8] = e_math;
       p.dbg[blockIdx.x * 16 + 9] = e_pub;
+      p.dbg[blockIdx.x * 16 + 11] = e_len;
     }
   }
   tc_fence_before();
@@ -734,12 +765,12 @@ int rnn_layer_ks(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     DSB_CUDA(cudaStreamSynchronize(st));
     DSB_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * 16 * grid, cudaMemcpyDeviceToHost));
     cudaFree(dbg);
-    const char* names[11] = {"prod.spin", "prod.issue", "prod.wait_empty", "mma.wait_first", "mma.rest", "epi.gload",
-                             "epi.wait_mma", "epi.exchange", "epi.math_store", "epi.y_store", "publisher.release"};
+    const char* names[12] = {"prod.spin", "prod.issue", "prod.wait_empty", "mma.wait_first", "mma.rest", "epi.gload",
+                             "epi.wait_mma", "epi.exchange", "epi.math_store", "epi.y_store", "publisher.release", "epi.gload.lens"};
     const int items = cdiv(n_bgroups, slots) * Tmax;
     fprintf(stderr, "[rnn_ks debug] H=%d B=%d Tmax=%d grid=%d groups=%d slots=%d in flight=%d ring=%dx%d  cycles/item "
                     "(avg over CTAs | max CTA)\n", L.H, B, Tmax, grid, n_bgroups, slots, nif, pl.slots, pl.gsz);
-    for (int k = 0; k < 11; ++k) {
+    for (int k = 0; k < 12; ++k) {
       double sum = 0, mx = 0;
       for (int c = 0; c < grid; ++c) { double v = (double)h[c * 16 + k] / items; sum += v; mx = v > mx ? v : mx; }
       fprintf(stderr, "   %-16s %9.0f | %9.0f\n", names[k], sum / grid, mx);
