@@ -208,8 +208,7 @@ __global__ void __launch_bounds__(KS_THREADS, 1)
 rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
               const KsParams p) {
   constexpr int UR = ks_units(GATES);            // units per CTA
-  constexpr int PP = UR * KS_N / 256;            // (unit, batch) pairs per epilogue thread
-  static_assert(UR * KS_N % 256 == 0, "pairs must divide evenly");
+  static_assert(UR % 4 == 0, "four epilogue threads share a batch row");
   constexpr int TMEM_COLS = NIF == 1 ? 64 : (NIF == 2 ? 128 : 256);
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -440,50 +439,46 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     const int cb = ch * 32;                        // first batch column of this thread
     const int ncol = p.dirs * GATES * p.H;
     const int unit0 = (pair * 2 + rank) * UR;
-    // (unit, batch) pairs of this thread: pair index et + 256*k, unit fastest
-    int pb[PP], pu[PP];
-    float bhn[PP];
+    // gate math: thread (bq = et / 4, uq = et % 4) owns UPT consecutive units of batch row bq -- one length, one time
+    // index and one set of row base pointers per thread and item (the instruction count of the epilogue is what the
+    // eight warps compete for: every instruction here is issued 8 x per item)
+    constexpr int UPT = UR / 4;
+    const int bq = et >> 2, uq = et & 3;
+    const int ubase = unit0 + uq * UPT;
+    const int nvalid = min(UPT, max(0, p.H - ubase));          // units of this thread inside H
+    float bhn[UPT];
 #pragma unroll
-    for (int k = 0; k < PP; ++k) {
-      const int qi = et + 256 * k;
-      pb[k] = qi / UR;
-      pu[k] = qi - pb[k] * UR;
-      bhn[k] = (GATES == 3 && p.b_hn && unit0 + pu[k] < p.H) ? p.b_hn[(size_t)dir * p.H + unit0 + pu[k]] : 0.f;
-    }
-    float hprev[NIF][PP], cst[NIF][PP];
+    for (int u = 0; u < UPT; ++u)
+      bhn[u] = (GATES == 3 && p.b_hn && u < nvalid) ? p.b_hn[(size_t)dir * p.H + ubase + u] : 0.f;
+    float hprev[NIF][UPT], cst[NIF][UPT];
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
     const uint32_t sx = smem_u32(sX), slen = smem_u32(sLen);
     const uint32_t my_x = sx + (uint32_t)((j * KS_XS + cb) * 4);                    // (row j, batch cb) of my sX
     const uint32_t peer_x = mapa_u32(sx, (uint32_t)(rank ^ 1)) + (uint32_t)((j * KS_XS + cb) * 4);
     const uint32_t peer_xfull = mapa_u32(smem_u32(xfull), (uint32_t)(rank ^ 1));
+    const uint32_t gate_x = sx + (uint32_t)((uq * UPT * GATES * KS_XS + bq) * 4);   // (unit uq*UPT, gate 0, batch bq)
     unsigned ic = 0;   // items processed (both CTAs of the pair walk the same item sequence)
     unsigned long long e_load = 0, e_wait = 0, e_xchg = 0, e_math = 0, e_pub = 0, e_len = 0;
 
-    auto item = [&](int i, int s, int bg, unsigned steps_before, float (&hp)[PP], float (&cs)[PP]) -> bool {
+    auto item = [&](int i, int s, int bg, unsigned steps_before, float (&hp)[UPT], float (&cs)[UPT]) -> bool {
       long long e0 = clock64();
-      // 1. input-projection pre-activations of this step for my pairs (consecutive threads: consecutive units)
-      float gxv[PP][GATES];
-      int tt[PP];          // time index of the pair, -1 = not active at this step
-      int lens_k[PP];
-#pragma unroll
-      for (int k = 0; k < PP; ++k)
-        lens_k[k] = unit0 + pu[k] < p.H ? lds_s32(slen + (uint32_t)((i * KS_N + pb[k]) * 4)) : 0;   // 0 beyond the batch
+      // 1. input-projection pre-activations of this step
+      float gxv[UPT][GATES];
+      const int len = nvalid > 0 ? lds_s32(slen + (uint32_t)((i * KS_N + bq) * 4)) : 0;   // 0 for rows beyond the batch
+      const bool act = s < len;
+      const int t = dir == 0 ? s : len - 1 - s;
+      const size_t brow = (size_t)(bg * KS_N + bq);
       long long e0b = clock64();
+      if (act) {
+        const float* gp = p.gx + ((size_t)t * p.B + brow) * ncol + (size_t)dir * GATES * p.H + ubase;
 #pragma unroll
-      for (int k = 0; k < PP; ++k) {
-        const int unit = unit0 + pu[k];
-        const int len = lens_k[k];
-        tt[k] = s < len ? (dir == 0 ? s : len - 1 - s) : -1;
-        if (tt[k] >= 0) {
-          const float* gp = p.gx + ((size_t)tt[k] * p.B + (bg * KS_N + pb[k])) * ncol + (size_t)dir * GATES * p.H + unit;
+        for (int g = 0; g < GATES; ++g)
 #pragma unroll
-          for (int g = 0; g < GATES; ++g) gxv[k][g] = __ldg(gp + (size_t)g * p.H);
-          if (s + 1 < len && ((pu[k] & 7) == 0 || pu[k] == UR - 1)) {
-            // the group's next step: pulled into L2 one round of items ahead
-            const float* gn = gp + (dir == 0 ? (ptrdiff_t)p.B * ncol : -(ptrdiff_t)p.B * ncol);
+          for (int u = 0; u < UPT; ++u) gxv[u][g] = u < nvalid ? __ldg(gp + (size_t)g * p.H + u) : 0.f;
+        if (s + 1 < len) {   // the group's next step: pulled into L2 one round of items ahead
+          const float* gn = gp + (dir == 0 ? (ptrdiff_t)p.B * ncol : -(ptrdiff_t)p.B * ncol);
 #pragma unroll
-            for (int g = 0; g < GATES; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)g * p.H));
-          }
+          for (int g = 0; g < GATES; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + (size_t)g * p.H));
         }
       }
       long long e1 = clock64();
@@ -525,39 +520,43 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       long long e3 = clock64();
       if (!ks_bar_red_and(ok, 1, 256)) return false;     // sX complete (and uniform abort decision)
       // 4. gates
-      const size_t nxt = (size_t)((bg * 2 + ((s + 1) & 1)) * p.dirs + dir) * KS_N;
+      if (act) {
+        __nv_bfloat16* hb = p.hbuf + ((size_t)((bg * 2 + ((s + 1) & 1)) * p.dirs + dir) * KS_N + bq) * p.HP + ubase;
 #pragma unroll
-      for (int k = 0; k < PP; ++k) {
-        if (tt[k] >= 0) {
-          const uint32_t a = sx + (uint32_t)((pu[k] * GATES * KS_XS + pb[k]) * 4);   // gate g: + g rows
-          float hn;
-          if (GATES == 3) {
-            const float rg = ks_sigmoid(gxv[k][0] + lds_f32(a));
-            const float zg = ks_sigmoid(gxv[k][1 % GATES] + lds_f32(a + 4 * KS_XS * (1 % GATES)));
-            const float ng = ks_tanh(gxv[k][2 % GATES] + rg * (lds_f32(a + 4 * KS_XS * (2 % GATES)) + bhn[k]));
-            hn = (1.0f - zg) * ng + zg * hp[k];
-          } else if (GATES == 4) {
-            const float ig = ks_sigmoid(gxv[k][0] + lds_f32(a));
-            const float fg = ks_sigmoid(gxv[k][1 % GATES] + lds_f32(a + 4 * KS_XS * (1 % GATES)));
-            const float gg = ks_tanh(gxv[k][2 % GATES] + lds_f32(a + 4 * KS_XS * (2 % GATES)));
-            const float og = ks_sigmoid(gxv[k][3 % GATES] + lds_f32(a + 4 * KS_XS * (3 % GATES)));
-            cs[k] = fg * cs[k] + ig * gg;
-            hn = og * ks_tanh(cs[k]);
-          } else {
-            hn = ks_tanh(gxv[k][0] + lds_f32(a));
+        for (int u = 0; u < UPT; ++u) {
+          if (u < nvalid) {
+            const uint32_t a = gate_x + (uint32_t)(u * GATES * KS_XS * 4);
+            float hn;
+            if (GATES == 3) {
+              const float rg = ks_sigmoid(gxv[u][0] + lds_f32(a));
+              const float zg = ks_sigmoid(gxv[u][1 % GATES] + lds_f32(a + 4 * KS_XS * (1 % GATES)));
+              const float ng = ks_tanh(gxv[u][2 % GATES] + rg * (lds_f32(a + 4 * KS_XS * (2 % GATES)) + bhn[u]));
+              hn = (1.0f - zg) * ng + zg * hp[u];
+            } else if (GATES == 4) {
+              const float ig = ks_sigmoid(gxv[u][0] + lds_f32(a));
+              const float fg = ks_sigmoid(gxv[u][1 % GATES] + lds_f32(a + 4 * KS_XS * (1 % GATES)));
+              const float gg = ks_tanh(gxv[u][2 % GATES] + lds_f32(a + 4 * KS_XS * (2 % GATES)));
+              const float og = ks_sigmoid(gxv[u][3 % GATES] + lds_f32(a + 4 * KS_XS * (3 % GATES)));
+              cs[u] = fg * cs[u] + ig * gg;
+              hn = og * ks_tanh(cs[u]);
+            } else {
+              hn = ks_tanh(gxv[u][0] + lds_f32(a));
+            }
+            hp[u] = hn;
+            hb[u] = __float2bfloat16_rn(hn);     // h_t -> exchange buffer of the next step
           }
-          hp[k] = hn;
-          // h_t -> exchange buffer of the next step (bf16): consecutive threads write consecutive units of a row
-          p.hbuf[(nxt + pb[k]) * p.HP + unit0 + pu[k]] = __float2bfloat16_rn(hn);
         }
       }
       long long e4 = clock64();
       // all reads of sX done and all h stores issued: the publisher warp takes it from here (release = this arrive)
       mbar_arrive(&hdone[ic & 3]);
       // y_t -> global (fp32): nobody waits on these stores
+      if (act) {
+        float* yo = p.y + (((size_t)dir * p.T + t) * p.B + brow) * p.H + ubase;
 #pragma unroll
-      for (int k = 0; k < PP; ++k)
-        if (tt[k] >= 0) p.y[(((size_t)dir * p.T + tt[k]) * p.B + bg * KS_N + pb[k]) * p.H + unit0 + pu[k]] = hp[k];
+        for (int u = 0; u < UPT; ++u)
+          if (u < nvalid) yo[u] = hp[u];
+      }
       ++ic;
       e_len += e0b - e0;
       e_load += e1 - e0; e_wait += e2 - e1; e_xchg += e3 - e2; e_math += e4 - e3; e_pub += clock64() - e4;
@@ -581,11 +580,11 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           sLen[i * KS_N + et] = (bg < p.n_bgroups && b < p.B) ? (p.lens ? p.lens[b] : p.Tmax) : 0;   // read back with lds_s32
         }
 #pragma unroll
-        for (int k = 0; k < PP; ++k) {
-          const int b = bg * KS_N + pb[k], unit = unit0 + pu[k];
-          const bool in = bg < p.n_bgroups && b < p.B && unit < p.H;
-          hprev[i][k] = (p.h0 && in) ? p.h0[((size_t)dir * p.B + b) * p.H + unit] : 0.f;
-          cst[i][k] = (GATES == 4 && p.c0 && in) ? p.c0[((size_t)dir * p.B + b) * p.H + unit] : 0.f;
+        for (int u = 0; u < UPT; ++u) {
+          const int b = bg * KS_N + bq;
+          const bool in = bg < p.n_bgroups && b < p.B && u < nvalid;
+          hprev[i][u] = (p.h0 && in) ? p.h0[((size_t)dir * p.B + b) * p.H + ubase + u] : 0.f;
+          cst[i][u] = (GATES == 4 && p.c0 && in) ? p.c0[((size_t)dir * p.B + b) * p.H + ubase + u] : 0.f;
         }
       }
       ks_named_bar(2, 256);
@@ -599,12 +598,12 @@ rnn_ks_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         before[i] += (unsigned)Tg[i];
         const int bg = slot + (k0 + i) * p.slots;
         if (alive && bg < p.n_bgroups && (p.hT || p.cT)) {   // carry the state out (streaming)
+          const int b = bg * KS_N + bq;
 #pragma unroll
-          for (int k = 0; k < PP; ++k) {
-            const int b = bg * KS_N + pb[k], unit = unit0 + pu[k];
-            if (b < p.B && unit < p.H) {
-              if (p.hT) p.hT[((size_t)dir * p.B + b) * p.H + unit] = hprev[i][k];
-              if (GATES == 4 && p.cT) p.cT[((size_t)dir * p.B + b) * p.H + unit] = cst[i][k];
+          for (int u = 0; u < UPT; ++u) {
+            if (b < p.B && u < nvalid) {
+              if (p.hT) p.hT[((size_t)dir * p.B + b) * p.H + ubase + u] = hprev[i][u];
+              if (GATES == 4 && p.cT) p.cT[((size_t)dir * p.B + b) * p.H + ubase + u] = cst[i][u];
             }
           }
         }
