@@ -55,7 +55,7 @@ struct Tune {
   std::atomic<int> rnn_in_flight{3};
   std::atomic<int> rnn_max_slots{0};
   std::atomic<int> gx_bf16{0};
-  std::atomic<int> rnn_ksplit{1};
+  std::atomic<int> rnn_ksplit{0};
   std::atomic<int> rnn_ring_gsz{0};
 };
 extern Tune g_tune;

@@ -34,7 +34,7 @@ namespace tc {
 constexpr int RT_BK = 64;
 constexpr int RT_N = 64;                       // W_hh rows per CTA = 2 halves x 32 columns
 constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk (8 KB)
-constexpr int RT_GROUP = 4;        // K chunks handled per elected issue region (2 when only one group of 4 would fit)
+constexpr int RT_GROUP = 4;        // most K chunks per ring slot / elected issue region
 constexpr int RT_MAX_GROUPS = 4;   // barrier slots; the ring holds 2 groups of 4 chunks or up to 4 groups of 2
 constexpr int RT_MAX_NIF = 3;      // batch groups in flight per CTA (each with its own TMEM accumulator)
 // (Consecutive tcgen05.mma into the same accumulator do not stall each other -- tested with 4 independent
@@ -43,34 +43,47 @@ constexpr int RT_THREADS = 64 + 256;
 constexpr long long RT_TIMEOUT_CYCLES = 4000000000LL;
 constexpr int RT_SMEM_LIMIT = 227 * 1024;
 
-// Shared-memory plan: [W slice: nkc x 8 KB][h ring: groups x 4 stages x BP*128 B][h store staging][barriers].
+// Shared-memory plan: [W slice: nkc x 8 KB][h ring: slots x gsz stages x BP*128 B][h store staging][row times][barriers].
 // The MMA is M = BP (64 or 128 batch rows): with M = 64 only the 64 valid rows are read from shared memory.
 // Every elected issue region (elect.sync + single-lane branch + reconvergence) costs ~200 cycles on top
 // of ~35 cycles per tcgen05.mma / TMA instruction (scripts/mma_microbench.py), so the producer and the MMA
-// warp work in groups of RT_GROUP chunks: one region issues 4 TMA loads, one region issues 16 MMAs.
+// warp work in groups of `gsz` chunks: one region issues one TMA box of gsz chunks, one region issues 4*gsz MMAs.
+// The ring slot is the unit of flow control: a slot is refilled when its MMAs have completed.  The h stream is bound
+// by the SM's TMA intake (~35 B/clk: 152 KB per step at H = 1200), so the ring should keep the TMA unit busy ACROSS
+// steps: with two slots the unit idles while the last two slots of a step drain; three slots of three chunks let it
+// run ahead into the next group's step.  The kernel has no static shared memory, so the dynamic window starts on a
+// 1 KB boundary and the plan may use all of the 227 KB.
 struct RtPlan {
-  int groups, gsz, stage_bytes, stage_off, stg_off, bar_off, total;
+  int groups, gsz, stage_bytes, stage_off, stg_off, st_off, bar_off, total;
 };
-__host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U, int small_groups = 0) {
+__host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U, int want_gsz = 0) {
   RtPlan pl;
   pl.stage_bytes = BP * RT_BK * 2;
   const int w_bytes = nkc * RT_W_BYTES;
-  const int stg = BP * U * 2;                    // h (bf16) staging for coalesced stores
-  const int stg_al = (stg + 1023) / 1024 * 1024;
-  const int room = RT_SMEM_LIMIT - 2048 - 256 - w_bytes - stg_al;   // 1 KB align slack + 1 KB static
-  int gsz = RT_GROUP, groups = room / (pl.stage_bytes * gsz);
-  if (groups > 2) groups = 2;
-  if (groups < 2 || small_groups) {   // a single group cannot overlap TMA with the MMAs: use smaller groups instead
-    gsz = 2;
-    groups = room / (pl.stage_bytes * gsz);
-    if (groups > RT_MAX_GROUPS) groups = RT_MAX_GROUPS;
+  const int stg = (BP * U * 2 + 127) / 128 * 128;   // h (bf16) staging for coalesced stores
+  const int st = BP * 4;                            // time index of every row of the group (-1 = inactive)
+  const int room = RT_SMEM_LIMIT - 256 - w_bytes - stg - st;
+  const int stages = room > 0 ? room / pl.stage_bytes : 0;
+  int gsz, groups;
+  if (want_gsz > 0) {
+    gsz = want_gsz;
+    groups = stages / gsz;
+  } else if (stages >= 9) {
+    gsz = 3; groups = 3;          // the ring runs ahead across steps
+  } else if (stages >= 8) {
+    gsz = 4; groups = 2;
+  } else {
+    gsz = 2; groups = stages / 2;
   }
+  if (gsz > nkc) { gsz = nkc; groups = gsz ? stages / gsz : 0; }
+  if (groups > RT_MAX_GROUPS) groups = RT_MAX_GROUPS;
   pl.groups = groups;
   pl.gsz = gsz;
   pl.stage_off = w_bytes;
   pl.stg_off = w_bytes + groups * gsz * pl.stage_bytes;
-  pl.bar_off = pl.stg_off + stg_al;
-  pl.total = pl.bar_off + 256 + 1024;
+  pl.st_off = pl.stg_off + stg;
+  pl.bar_off = pl.st_off + st;
+  pl.total = pl.bar_off + 256;
   return pl;
 }
 
@@ -94,7 +107,7 @@ struct RnnTcParams {
   int slots;       // ... by `slots` independent CTA sets per direction (set k takes groups k, k+slots, ...),
                    // NIF groups of a set in flight at a time
   int U;      // hidden units per CTA (2 * units per half)
-  int small_groups;   // ring in groups of 2 K chunks even when two groups of 4 fit (DSB_RNN_GSZ=2)
+  int ring_gsz;       // K chunks per ring slot, 0 = default (rt_plan)
   int nkc;    // K chunks of 64 (HP / 64)
   unsigned long long* dbg;   // optional [grid][128] cycle counters (DSB_RNN_DEBUG=1)
 };
@@ -175,8 +188,12 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   constexpr int U = 2 * UH;
   constexpr int TMEM_COLS = NIF == 1 ? 64 : (NIF == 2 ? 128 : 256);
   extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  const RtPlan pl = rt_plan(p.nkc, p.BP, U, p.small_groups);
+  unsigned char* smem = smem_dyn;
+  if ((smem_u32(smem_dyn) & 1023u) != 0) {   // the 128B-swizzled tiles need 1 KB alignment (no static shared memory here)
+    if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
+    return;
+  }
+  const RtPlan pl = rt_plan(p.nkc, p.BP, U, p.ring_gsz);
   unsigned char* sW = smem;
   unsigned char* sA = smem + pl.stage_off;
   unsigned char* sStg = smem + pl.stg_off;
@@ -410,7 +427,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     // h store staging sH [BP][U] bf16 + row validity sT [BP].  Single-buffered: the next write happens after
     // this CTA's publish of the item (behind the second named barrier), i.e. after every read of it.
     __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(sStg);
-    __shared__ int sT[128];
+    int* sT = reinterpret_cast<int*>(smem + pl.st_off);
     const bool vec2 = ((p.H & 1) == 0) && ((UH & 1) == 0);
     unsigned long long e_load = 0, e_wait = 0, e_math = 0, e_bar = 0, e_pub = 0;
 
@@ -678,8 +695,8 @@ bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* laun
   const int UH = 32 / L.gates, U = 2 * UH;
   const int cpd = cdiv(L.H, U);
   const int HP = (L.H + 63) / 64 * 64;
-  const tc::RtPlan pl = tc::rt_plan(HP / 64, rt_bp(B), U);
-  if (B < 1 || pl.groups < 1 || pl.total > tc::RT_SMEM_LIMIT || cpd > sms) return false;
+  const tc::RtPlan pl = tc::rt_plan(HP / 64, rt_bp(B), U, g_tune.rnn_ring_gsz.load());
+  if (B < 1 || pl.groups < 1 || pl.gsz < 1 || pl.total > tc::RT_SMEM_LIMIT || cpd > sms) return false;
   if (cpd_out) *cpd_out = cpd;
   if (launches_out) *launches_out = (L.dirs * cpd <= sms) ? 1 : L.dirs;
   return true;
@@ -811,8 +828,8 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   // h exchange buffer as {64 k, rows, K chunks}: one box {64, BP, RT_GROUP} = RT_GROUP consecutive chunk tiles
   uint64_t dh[3] = {(uint64_t)RT_BK, (uint64_t)n_bgroups * 2 * L.dirs * BP, (uint64_t)nkc};
   uint64_t sh[3] = {2, (uint64_t)HP * 2, (uint64_t)RT_BK * 2};
-  static const int small_groups = (getenv("DSB_RNN_GSZ") && atoi(getenv("DSB_RNN_GSZ")) == 2) ? 1 : 0;
-  const int gsz = rt_plan(nkc, BP, 2 * (32 / L.gates), small_groups).gsz;
+  const int ring_gsz = g_tune.rnn_ring_gsz.load();
+  const int gsz = rt_plan(nkc, BP, 2 * (32 / L.gates), ring_gsz).gsz;
   uint32_t bh[3] = {RT_BK, (uint32_t)BP, (uint32_t)gsz};
   if (int e = make_tmap_bf16(&th, hbuf, 3, dh, sh, bh, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
 
@@ -828,8 +845,8 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.n_bgroups = n_bgroups; p.slots = slots;
   p.B = B; p.H = L.H; p.HP = HP; p.BP = BP; p.T = T; p.Tmax = Tmax;
   p.dirs = L.dirs; p.cpd = cpd; p.U = 2 * (32 / L.gates); p.nkc = nkc;
-  p.small_groups = small_groups;
-  const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates), small_groups).total;
+  p.ring_gsz = ring_gsz;
+  const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates), ring_gsz).total;
   static const int split_env = getenv("DSB_RNN_SPLIT") ? atoi(getenv("DSB_RNN_SPLIT")) : 1;
   const bool split = L.gates == 3 && BP == 64 && split_env;
   const void* fn = nullptr;
@@ -876,7 +893,8 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
                              "epi.wait_mma", "epi.math_store", "epi.bar", "epi.publish", "mma.wait_rest",
                              "prod.wait_empty"};
     const int items = cdiv(n_bgroups, slots) * Tmax;   // (step, group) items per CTA (upper bound for ragged groups)
-    fprintf(stderr, "[rnn_tc debug] H=%d B=%d Tmax=%d grid=%d groups=%d slots=%d in flight=%d  cycles/item (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid, n_bgroups, slots, nif);
+    const RtPlan dpl = rt_plan(nkc, BP, 2 * (32 / L.gates), ring_gsz);
+    fprintf(stderr, "[rnn_tc debug] H=%d B=%d Tmax=%d grid=%d groups=%d slots=%d in flight=%d ring=%dx%d  cycles/item (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid, n_bgroups, slots, nif, dpl.groups, dpl.gsz);
     for (int k = 0; k < 12; ++k) {
       double sum = 0, mx = 0;
       for (int c = 0; c < grid; ++c) { double v = (double)h[c * 128 + k] / items; sum += v; mx = v > mx ? v : mx; }
