@@ -82,7 +82,8 @@ const Knob* knobs(int* n) {
                            {"rnn_max_slots", &dsb::g_tune.rnn_max_slots, 0, 1 << 20},
                            {"gx_bf16", &dsb::g_tune.gx_bf16, 0, 1},
                            {"rnn_ksplit", &dsb::g_tune.rnn_ksplit, 0, 1},
-                           {"rnn_ring_gsz", &dsb::g_tune.rnn_ring_gsz, 0, 4}};
+                           {"rnn_ring_gsz", &dsb::g_tune.rnn_ring_gsz, 0, 4},
+                           {"rnn_producers", &dsb::g_tune.rnn_producers, 1, 2}};
   *n = (int)(sizeof(k) / sizeof(k[0]));
   return k;
 }

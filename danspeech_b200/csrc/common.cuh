@@ -57,6 +57,7 @@ struct Tune {
   std::atomic<int> gx_bf16{0};
   std::atomic<int> rnn_ksplit{0};
   std::atomic<int> rnn_ring_gsz{0};
+  std::atomic<int> rnn_producers{2};
 };
 extern Tune g_tune;
 

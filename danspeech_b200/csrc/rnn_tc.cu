@@ -39,7 +39,7 @@ constexpr int RT_MAX_GROUPS = 4;   // barrier slots; the ring holds 2 groups of 
 constexpr int RT_MAX_NIF = 3;      // batch groups in flight per CTA (each with its own TMEM accumulator)
 // (Consecutive tcgen05.mma into the same accumulator do not stall each other -- tested with 4 independent
 // accumulators: no change -- so a single 64-column TMEM accumulator per batch group is used.)
-constexpr int RT_THREADS = 64 + 256;
+constexpr int RT_THREADS = 64 + 256 + 32;   // producer, MMA issuer, 8 epilogue warps, second producer
 constexpr long long RT_TIMEOUT_CYCLES = 4000000000LL;
 constexpr int RT_SMEM_LIMIT = 227 * 1024;
 
@@ -68,9 +68,7 @@ __host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U, int want_gsz =
   if (want_gsz > 0) {
     gsz = want_gsz;
     groups = stages / gsz;
-  } else if (stages >= 9) {
-    gsz = 3; groups = 3;          // the ring runs ahead across steps
-  } else if (stages >= 8) {
+  } else if (stages >= 8) {      // (three slots of three chunks fit too and were measured slower: the cost is per box)
     gsz = 4; groups = 2;
   } else {
     gsz = 2; groups = stages / 2;
@@ -108,6 +106,7 @@ struct RnnTcParams {
                    // NIF groups of a set in flight at a time
   int U;      // hidden units per CTA (2 * units per half)
   int ring_gsz;       // K chunks per ring slot, 0 = default (rt_plan)
+  int n_producers;    // TMA producer warps (1 or 2)
   int nkc;    // K chunks of 64 (HP / 64)
   unsigned long long* dbg;   // optional [grid][128] cycle counters (DSB_RNN_DEBUG=1)
 };
@@ -230,9 +229,15 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (warp == 0) {
-    // ---- TMA producer: whole warp in warp-uniform control flow, one elected lane issues (elect_one_sync) ----
-    if (elect_one_sync()) {
+  if (warp == 0 || warp == 10) {
+    // ---- TMA producers: whole warp in warp-uniform control flow, one elected lane issues (elect_one_sync).
+    // Measured (scripts/tma_microbench.py): ONE warp gets a TMA box into flight every ~700 cycles whatever its size
+    // (8 KB or 64 KB, tensor box or bulk copy, 1 or 8 boxes in flight), two warps together every ~500.  The h stream
+    // of a step is five boxes, so two producer warps take alternate ring slots: warp 0 the even ones, warp 10 the odd.
+    const int pi = warp == 0 ? 0 : 1;
+    const int NP = p.n_producers;
+    if (pi >= NP) goto done;
+    if (pi == 0 && elect_one_sync()) {
       // resident W_hh slice, loaded once
       mbar_arrive_expect_tx(wbar, (uint32_t)p.nkc * RT_W_BYTES);
       for (int kc = 0; kc < p.nkc; ++kc)
@@ -241,48 +246,19 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     __syncwarp();
     bool ok = true;
     unsigned long long d_spin = 0, d_fence = 0, d_issue = 0, d_empty = 0;
-    // ring positions of the next group to arm / to load (slot index + phase kept incrementally: a 64-bit
-    // modulo per group costs the single issuing warp hundreds of cycles)
-    int arm_slot = 0, load_slot = 0;
-    uint32_t arm_phase = 0;
-    // Arming a group (waiting for its slot, arrive.expect_tx on its stages) does not depend on h, so the first
-    // `n_groups` groups of a step are armed BEFORE the step barrier is polled; after the barrier only the
-    // proxy fence and the TMA issues remain on the critical path.
-    // One TMA per group: the h buffer is mapped as a 3-D tensor {64 k, BP rows, nkc chunks}, so a box
-    // {64, BP, RT_GROUP} lands as RT_GROUP consecutive 128B-swizzled K-chunk tiles (a TMA instruction costs
-    // ~240 cycles of issue; chunks beyond nkc are zero-filled and never used by the MMAs).
-    auto arm_group = [&]() -> bool {
-      const int grp = arm_slot;
-      if (!__all_sync(0xffffffffu, wait_abortable(&gempty[grp], arm_phase ^ 1, p.abort_flag))) return false;
-      if (elect_one_sync()) mbar_arrive_expect_tx(&full[grp], (uint32_t)(gsz * pl.stage_bytes));
-      __syncwarp();
-      if (++arm_slot == n_groups) { arm_slot = 0; arm_phase ^= 1; }
-      return true;
-    };
-    auto load_group = [&](int g, int row0) {
-      const int grp = load_slot;
-      if (++load_slot == n_groups) load_slot = 0;
-      int gg = g + g_rot;
-      if (gg >= gps) gg -= gps;
-      if (elect_one_sync()) tma_load_3d(sA + grp * gsz * pl.stage_bytes, &tmap_h, &full[grp], 0, row0, gg * gsz);
-      __syncwarp();
-    };
-    // one step of one group: `steps_before` = steps this group-in-flight index has completed in earlier waves
+    // ring position of the next slot use (slot index + phase kept incrementally: a 64-bit modulo per group costs the
+    // single issuing warp hundreds of cycles); `turn` says whose slot use it is
+    int cur_slot = 0, turn = 0;
+    uint32_t cur_phase = 0;
+    // One TMA per ring slot: the h buffer is mapped as a 3-D tensor {64 k, BP rows, nkc chunks}, so a box
+    // {64, BP, gsz} lands as gsz consecutive 128B-swizzled K-chunk tiles (chunks beyond nkc are zero-filled and
+    // never used by the MMAs).
     auto item = [&](int i, int s, int bg, unsigned steps_before) -> bool {
       long long c0 = clock64();
-      // One group at a time: arm first, so that after the barrier only the proxy fence and the TMA issues remain on
-      // the critical path.  Several groups in flight: the barrier of this item is usually open already (its group
-      // published while the other groups ran), and the ring slots only free up as the MMAs of the previous item
-      // complete -- poll FIRST, so that the loads go out the moment a slot is free and the MMA warp does not sit
-      // through an L2 round trip between two items.
-      const int pre = NIF == 1 ? min(gps, n_groups) : 0;
-      for (int g = 0; g < pre; ++g)
-        if (!arm_group()) return false;
-      d_empty += clock64() - c0;
-      c0 = clock64();
       if (steps_before + (unsigned)s > 0) {
         // set-wide barrier: every CTA of this set has published h_{s-1} of this group (at s = 0 of a later wave:
-        // has finished the group that used this accumulator / counter before)
+        // has finished the group that used this accumulator / counter before).  With several groups in flight it is
+        // usually open already (the group published while the others ran).
         const unsigned target = (unsigned)p.cpd * (steps_before + (unsigned)s);
         const unsigned* ctr = ctr0 + i * kRnnCounterStride;
         long long t0 = 0;
@@ -303,16 +279,24 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         d_fence += clock64() - c1;
       }
       long long c2 = clock64();
-      if (p.dbg && s == 100 && i == 0 && lane == 0) p.dbg[blockIdx.x * 128 + 15] = c2;
+      if (p.dbg && s == 100 && i == 0 && lane == 0 && pi == 0) p.dbg[blockIdx.x * 128 + 15] = c2;
       const int row0 = ((bg * 2 + (s & 1)) * p.dirs + dir) * p.BP;
       for (int g = 0; g < gps; ++g) {
-        if (g >= pre) {
+        if (turn == pi) {
           long long w0 = clock64();
-          if (!arm_group()) return false;
+          if (!__all_sync(0xffffffffu, wait_abortable(&gempty[cur_slot], cur_phase ^ 1, p.abort_flag))) return false;
           d_empty += clock64() - w0;
+          int gg = g + g_rot;
+          if (gg >= gps) gg -= gps;
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full[cur_slot], (uint32_t)(gsz * pl.stage_bytes));
+            tma_load_3d(sA + cur_slot * gsz * pl.stage_bytes, &tmap_h, &full[cur_slot], 0, row0, gg * gsz);
+          }
+          __syncwarp();
+          if (p.dbg && s == 100 && i == 0 && g < 8 && lane == 0) p.dbg[blockIdx.x * 128 + 16 + g] = clock64();
         }
-        load_group(g, row0);
-        if (p.dbg && s == 100 && i == 0 && g < 8 && lane == 0) p.dbg[blockIdx.x * 128 + 16 + g] = clock64();
+        if (++turn == NP) turn = 0;
+        if (++cur_slot == n_groups) { cur_slot = 0; cur_phase ^= 1; }
       }
       d_issue += clock64() - c2;
       return true;
@@ -335,7 +319,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < NIF; ++i) before[i] += (unsigned)Tg[i];
     }
-    if (p.dbg && lane == 0) {
+    if (p.dbg && lane == 0 && pi == 0) {
       p.dbg[blockIdx.x * 128 + 0] = d_spin;
       p.dbg[blockIdx.x * 128 + 1] = d_fence;
       p.dbg[blockIdx.x * 128 + 2] = d_issue;
@@ -630,6 +614,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       p.dbg[blockIdx.x * 128 + 9] = e_pub;
     }
   }
+done:
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -846,6 +831,7 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.B = B; p.H = L.H; p.HP = HP; p.BP = BP; p.T = T; p.Tmax = Tmax;
   p.dirs = L.dirs; p.cpd = cpd; p.U = 2 * (32 / L.gates); p.nkc = nkc;
   p.ring_gsz = ring_gsz;
+  p.n_producers = g_tune.rnn_producers.load();
   const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates), ring_gsz).total;
   static const int split_env = getenv("DSB_RNN_SPLIT") ? atoi(getenv("DSB_RNN_SPLIT")) : 1;
   const bool split = L.gates == 3 && BP == 64 && split_env;

@@ -11,7 +11,8 @@ OUT = os.path.join(ROOT, "build", "libdsb_microbench.so")
 
 def build():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    srcs = [os.path.join(HERE, "microbench.cu"), os.path.join(CSRC, "common.cu")]
+    srcs = [os.path.join(HERE, "microbench.cu"), os.path.join(HERE, "tma_bench.cu"), os.path.join(CSRC, "common.cu"),
+            os.path.join(CSRC, "gemm_tc.cu")]      # gemm_tc.cu: make_tmap_bf16
     if os.path.exists(OUT) and all(os.path.getmtime(OUT) > os.path.getmtime(s) for s in srcs):
         return OUT
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
