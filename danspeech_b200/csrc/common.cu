@@ -80,7 +80,6 @@ struct Knob { const char* name; std::atomic<int>* v; int lo, hi; };
 const Knob* knobs(int* n) {
   static const Knob k[] = {{"rnn_in_flight", &dsb::g_tune.rnn_in_flight, 1, 3},
                            {"rnn_max_slots", &dsb::g_tune.rnn_max_slots, 0, 1 << 20},
-                           {"gx_bf16", &dsb::g_tune.gx_bf16, 0, 1},
                            {"rnn_ksplit", &dsb::g_tune.rnn_ksplit, 0, 1},
                            {"rnn_ring_gsz", &dsb::g_tune.rnn_ring_gsz, 0, 4},
                            {"rnn_producers", &dsb::g_tune.rnn_producers, 1, 2}};

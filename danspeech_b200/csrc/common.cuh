@@ -54,10 +54,9 @@ struct ProfScope {
 struct Tune {
   std::atomic<int> rnn_in_flight{3};
   std::atomic<int> rnn_max_slots{0};
-  std::atomic<int> gx_bf16{0};
   std::atomic<int> rnn_ksplit{0};
   std::atomic<int> rnn_ring_gsz{0};
-  std::atomic<int> rnn_producers{2};
+  std::atomic<int> rnn_producers{1};
 };
 extern Tune g_tune;
 

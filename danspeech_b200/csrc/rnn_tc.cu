@@ -231,9 +231,11 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 
   if (warp == 0 || warp == 10) {
     // ---- TMA producers: whole warp in warp-uniform control flow, one elected lane issues (elect_one_sync).
-    // Measured (scripts/tma_microbench.py): ONE warp gets a TMA box into flight every ~700 cycles whatever its size
-    // (8 KB or 64 KB, tensor box or bulk copy, 1 or 8 boxes in flight), two warps together every ~500.  The h stream
-    // of a step is five boxes, so two producer warps take alternate ring slots: warp 0 the even ones, warp 10 the odd.
+    // Measured (scripts/tma_microbench.py, one CTA): ONE warp gets a TMA box into flight every ~700 cycles whatever
+    // its size (8 KB or 64 KB, tensor box or bulk copy, 1 or 8 boxes in flight), two warps together every ~500.  A
+    // second producer warp on alternate ring slots (dsb_tune_set("rnn_producers", 2)) did NOT shorten the h stream
+    // of a step inside this kernel, though: with all CTAs of a direction pulling the same h the boxes land ~940
+    // cycles apart whoever issues them.  Default: one producer (warp 0).
     const int pi = warp == 0 ? 0 : 1;
     const int NP = p.n_producers;
     if (pi >= NP) goto done;
@@ -831,7 +833,9 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.B = B; p.H = L.H; p.HP = HP; p.BP = BP; p.T = T; p.Tmax = Tmax;
   p.dirs = L.dirs; p.cpd = cpd; p.U = 2 * (32 / L.gates); p.nkc = nkc;
   p.ring_gsz = ring_gsz;
-  p.n_producers = g_tune.rnn_producers.load();
+  // two producers own alternate ring slots, which only works when the ring has an even number of them (a producer
+  // must never be two uses of the same slot ahead of the MMAs: the slot barriers carry one parity bit)
+  p.n_producers = (g_tune.rnn_producers.load() == 2 && rt_plan(nkc, BP, 2 * (32 / L.gates), ring_gsz).groups % 2 == 0) ? 2 : 1;
   const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates), ring_gsz).total;
   static const int split_env = getenv("DSB_RNN_SPLIT") ? atoi(getenv("DSB_RNN_SPLIT")) : 1;
   const bool split = L.gates == 3 && BP == 64 && split_env;

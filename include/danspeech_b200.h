@@ -52,11 +52,10 @@ int dsb_profile_read(int stage, double* total_ms, int* spans);
  *   "rnn_in_flight"  1..3  batch groups of 64 sequences in flight per CTA in the persistent recurrence (default 3;
  *                          1 = one group of up to 128 rows at a time)
  *   "rnn_max_slots"  >= 0  cap on the independent CTA sets of the recurrence (0 = as many as fit, default)
- *   "gx_bf16"        0/1   gate pre-activations of the input projection stored as bf16 (default 0 = fp32)
  *   "rnn_ksplit"     0/1   1 = recurrence on CTA pairs that split K (csrc/rnn_ks.cu; parity-green, measured slower
  *                          than the default one-CTA-per-W_hh-slice kernel: DESIGN.md section 5), default 0
  *   "rnn_ring_gsz"   0..4  K chunks of 64 per slot of the recurrence's h ring (0 = default: two slots of four)
- *   "rnn_producers"  1..2  TMA producer warps of the recurrence (default 2: alternate ring slots)
+ *   "rnn_producers"  1..2  TMA producer warps of the recurrence (default 1; 2 = alternate ring slots, measured equal)
  * dsb_tune_set returns DSB_ERR_INVALID for an unknown key or an out-of-range value; dsb_tune_get returns the value
  * or -1 for an unknown key. */
 int dsb_tune_set(const char* key, int value);

@@ -31,7 +31,7 @@ for B in BS:
         if (nif > 1 and B <= 64) or (nif == 1 and ks == 1 and B > 64):
             continue
         N.tune(rnn_in_flight=max(nif, 2) if ks else nif, rnn_ksplit=ks, rnn_ring_gsz=int(os.environ.get("RING_GSZ", "0")),
-               rnn_producers=int(os.environ.get("PRODUCERS", "2")))
+               rnn_producers=int(os.environ.get("PRODUCERS", "1")))
         probs, _ = model(x, lens)
         torch.cuda.synchronize()
         L.dsb_profile_reset()
