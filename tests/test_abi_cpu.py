@@ -155,3 +155,23 @@ def test_reference_citations_resolve():
                 bad.append((rel, m.group(0), "line range"))
     assert not bad, bad[:10]
     assert checked > 150
+
+
+def test_tuning_knobs_are_validated(lib):
+    """dsb_tune_set / dsb_tune_get: known keys only, values inside their ranges, defaults = production settings."""
+    assert lib.dsb_tune_get(b"rnn_in_flight") == 3 and lib.dsb_tune_get(b"rnn_ksplit") == 0
+    assert lib.dsb_tune_get(b"rnn_max_slots") == 0 and lib.dsb_tune_get(b"rnn_producers") == 1
+    assert lib.dsb_tune_get(b"no_such_knob") == -1
+    assert lib.dsb_tune_set(b"no_such_knob", 1) != 0 and b"unknown key" in lib.dsb_last_error()
+    assert lib.dsb_tune_set(b"rnn_in_flight", 4) != 0 and b"outside" in lib.dsb_last_error()
+    assert lib.dsb_tune_set(b"rnn_in_flight", 2) == 0 and lib.dsb_tune_get(b"rnn_in_flight") == 2
+    assert lib.dsb_tune_set(b"rnn_in_flight", 3) == 0
+    from danspeech_b200 import _native as N
+    prev = N.tune(rnn_max_slots=1)
+    assert prev == {"rnn_max_slots": 0} and lib.dsb_tune_get(b"rnn_max_slots") == 1
+    N.tune(**prev)
+    assert lib.dsb_tune_get(b"rnn_max_slots") == 0
+
+
+def test_forward_status_needs_a_model(lib):
+    assert lib.dsb_forward_status(None) != 0

@@ -464,3 +464,20 @@ def test_audio_parser_windows_and_config_errors():
         SpectrogramAudioParser(dict(window="kaiser"))
     with pytest.raises(NotImplementedError):
         SpectrogramAudioParser(dict(window_size=0.025))
+
+
+def test_recognize_batches_merge_plan():
+    """transcribe_batches runs up to `merge` consecutive batches through one pass of the model, within a row and a
+    sample budget, never mixing host lists with pinned tensors; order is kept."""
+    from danspeech_b200.DanSpeechRecognizer import DanSpeechRecognizer as D
+    d = D.__new__(D)
+    short = [np.zeros(1000)] * 64
+    assert d._merge_plan([short] * 7, 3) == [[0, 1, 2], [3, 4, 5], [6]]
+    assert d._merge_plan([short] * 7, 1) == [[k] for k in range(7)]
+    assert d._merge_plan([short] * 4, 2) == [[0, 1], [2, 3]]
+    assert d._merge_plan([[np.zeros(10)] * 100, [np.zeros(10)] * 100, [np.zeros(10)] * 20], 3) == [[0], [1, 2]]   # 192 rows
+    long = [np.zeros(40 * 16000)] * 64                       # 3 x 64 x 40 s exceeds the sample budget of a pass
+    assert d._merge_plan([long] * 4, 3) == [[0, 1], [2, 3]]
+    pinned = (torch.zeros(8, 100), [100] * 8)
+    assert d._merge_plan([short, pinned, pinned, short], 3) == [[0], [1, 2], [3]]
+    assert d._merge_plan([], 3) == []
