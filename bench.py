@@ -538,7 +538,7 @@ def run_ours(args):
     extras = {}
     if not args.no_extras:
         probs_bench = None
-        if rank == 0 and not args.no_cpu_baseline:
+        if rank == 0 and not args.no_cpu_baseline and world == 1:
             spect, _ = parser.parse_device(audio_dev[:BATCH], n_dev[:BATCH], n, out=spect_buf[:BATCH])
             probs_bench = eng.model(spect.view(BATCH, 1, 161, -1), torch.IntTensor([T] * BATCH))[0].cpu().numpy()
         extras["probs_bench"] = probs_bench
@@ -605,7 +605,8 @@ def run_ours(args):
             stages[k].update({"TFLOP/s": round(tf, 2), "frac_tensor": round(tf / peak, 4)})
 
     cpu, cpu_batch, parity = None, None, None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (under torchrun the other ranks spin in a barrier
+                                                     # on the same host cores and OMP_NUM_THREADS is forced to 1)
         v, sec, threads, ref_texts, ref_probs = cpu_reference_rtfx(args.cpu_sample, 2, 1, want_outputs=True)
         cpu = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port", "cpu_model": cpu_model_name(),
                "sample": "batch %d (the reference engine's own batch size, DanSpeechRecognizer.py:220-223): %d x 15 s "
