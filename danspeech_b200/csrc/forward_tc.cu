@@ -97,8 +97,7 @@ int finalize_tc(dsb_model* m, cudaStream_t st) {
     int cpd = 0, launches = 0;
     R.tc_recurrence = rnn_tc_supported(R, 64, sms, &cpd, &launches);
     if (R.tc_recurrence) {
-      const int HP = (R.H + 63) / 64 * 64;
-      if (int e = dev_alloc_tc(m, &R.w_hh_pack, (int64_t)R.dirs * cpd * 64 * HP)) return e;
+      if (int e = dev_alloc_tc(m, &R.w_hh_pack, (int64_t)rnn_tc_pack_elems(R))) return e;
       if (int e = pack_whh_tc(R, R.w_hh_pack, st)) return e;
     }
     // the K-split CTA-pair kernel shares the exchange buffers and counters of the one-CTA kernel (groups of 64 rows)

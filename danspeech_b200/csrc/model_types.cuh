@@ -86,6 +86,7 @@ int pack_conv_w_tc(const ConvLayer& L, bool first, __nv_bfloat16* out, cudaStrea
 int conv_block_tc(const __nv_bfloat16* x, const ConvLayer& L, bool first, const int32_t* d_len, int B, int Tp,
                   __nv_bfloat16* out, bool rnn_layout, int64_t out_ld, cudaStream_t st, const int* seg = nullptr);
 bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* launches_out);
+size_t rnn_tc_pack_elems(const RnnLayer& L);
 int pack_whh_tc(const RnnLayer& L, __nv_bfloat16* out, cudaStream_t st);
 int combine_dirs_tc(const float* y, int dirs, int T, int B, int H, const int32_t* d_len, __nv_bfloat16* xb, int ldx,
                     float* xf, cudaStream_t st);

@@ -32,8 +32,11 @@ namespace dsb {
 namespace tc {
 
 constexpr int RT_BK = 64;
-constexpr int RT_N = 64;                       // W_hh rows per CTA = 2 halves x 32 columns
-constexpr int RT_W_BYTES = RT_N * RT_BK * 2;   // one resident W chunk (8 KB)
+// W_hh rows per CTA = 2 halves x HS accumulator columns.  Default: HS = 32 (64 rows, 8 KB per K chunk); "narrow" slices
+// for wide layers whose 64-row slice does not fit shared memory (H > ~1500): HS = 24 (48 rows, 6 KB per K chunk).
+__host__ __device__ constexpr int rt_hs(bool narrow) { return narrow ? 24 : 32; }
+__host__ __device__ constexpr int rt_rows(bool narrow) { return 2 * rt_hs(narrow); }
+__host__ __device__ constexpr int rt_units(int gates, bool narrow) { return 2 * (rt_hs(narrow) / gates); }
 constexpr int RT_GROUP = 4;        // most K chunks per ring slot / elected issue region
 constexpr int RT_MAX_GROUPS = 4;   // barrier slots; the ring holds 2 groups of 4 chunks or up to 4 groups of 2
 constexpr int RT_MAX_NIF = 3;      // batch groups in flight per CTA (each with its own TMEM accumulator)
@@ -56,10 +59,10 @@ constexpr int RT_SMEM_LIMIT = 227 * 1024;
 struct RtPlan {
   int groups, gsz, stage_bytes, stage_off, stg_off, st_off, bar_off, total;
 };
-__host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U, int want_gsz = 0) {
+__host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U, int want_gsz = 0, bool narrow = false) {
   RtPlan pl;
   pl.stage_bytes = BP * RT_BK * 2;
-  const int w_bytes = nkc * RT_W_BYTES;
+  const int w_bytes = nkc * rt_rows(narrow) * RT_BK * 2;
   const int stg = (BP * U * 2 + 127) / 128 * 128;   // h (bf16) staging for coalesced stores
   const int st = BP * 4;                            // time index of every row of the group (-1 = inactive)
   const int room = RT_SMEM_LIMIT - 256 - w_bytes - stg - st;
@@ -179,11 +182,14 @@ __device__ __forceinline__ int rt_group_steps(const RnnTcParams& p, int bg) {
 // every epilogue warp would idle through the MUFU-bound gate math.  Lane l+16 computes the second half of lane l's
 // hidden units on values handed over by shuffle and hands h back; loads, stores and the recurrent state stay with
 // lanes 0-15 (splitting those as well doubled the number of memory requests and was measured slower).
-template <int GATES, bool SPLITM, int NIF>
+template <int GATES, bool SPLITM, int NIF, bool NARROW>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
               const RnnTcParams p) {
-  constexpr int UH = 32 / GATES;   // units per 32-column half
+  constexpr int HS = rt_hs(NARROW);        // accumulator columns per half
+  constexpr int RT_N = 2 * HS;             // W_hh rows of this CTA
+  constexpr int RT_W_BYTES = RT_N * RT_BK * 2;
+  constexpr int UH = HS / GATES;           // units per half
   constexpr int U = 2 * UH;
   constexpr int TMEM_COLS = NIF == 1 ? 64 : (NIF == 2 ? 128 : 256);
   extern __shared__ unsigned char smem_dyn[];
@@ -192,7 +198,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     if (threadIdx.x == 0) atomicExch(p.abort_flag, 1);
     return;
   }
-  const RtPlan pl = rt_plan(p.nkc, p.BP, U, p.ring_gsz);
+  const RtPlan pl = rt_plan(p.nkc, p.BP, U, p.ring_gsz, NARROW);
   unsigned char* sW = smem;
   unsigned char* sA = smem + pl.stage_off;
   unsigned char* sStg = smem + pl.stg_off;
@@ -409,7 +415,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 #pragma unroll
     for (int u = 0; u < UH; ++u)
       bhn[u] = (GATES == 3 && p.b_hn && j0 + u < p.H) ? p.b_hn[(size_t)dir * p.H + j0 + u] : 0.f;
-    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HS);
     // h store staging sH [BP][U] bf16 + row validity sT [BP].  Single-buffered: the next write happens after
     // this CTA's publish of the item (behind the second named barrier), i.e. after every read of it.
     __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(sStg);
@@ -626,10 +632,10 @@ done:
 }
 
 // W_hh [dirs][G*H][H] fp32 -> per-CTA slices [dirs][cpd][64 rows][HP] bf16.  Row n of a slice:
-// half = n/32, r = n%32, u = r/G, g = r%G  <->  W_hh[g*H + c*U + half*UH + u][:]  (zero rows/cols beyond H).
+// half = n/HS, r = n%HS, u = r/G, g = r%G  <->  W_hh[g*H + c*U + half*UH + u][:]  (zero rows/cols beyond H).
 __global__ void pack_whh_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int dirs, int cpd,
-                                int G, int H, int HP, int U) {
-  const int UH = 32 / G;
+                                int G, int H, int HP, int U, int HS) {
+  const int UH = HS / G, RT_N = 2 * HS;
   const int64_t total = (int64_t)dirs * cpd * RT_N * HP;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % HP);
@@ -638,7 +644,7 @@ __global__ void pack_whh_kernel(const float* __restrict__ w, __nv_bfloat16* __re
     rr /= RT_N;
     const int c = (int)(rr % cpd);
     const int d = (int)(rr / cpd);
-    const int half = n / 32, r = n % 32, u = r / G, g = r % G;
+    const int half = n / HS, r = n % HS, u = r / G, g = r % G;
     const int j = c * U + half * UH + u;
     float v = 0.f;
     if (u < UH && j < H && k < H) v = w[((int64_t)d * G * H + (int64_t)g * H + j) * H + k];
@@ -678,11 +684,20 @@ int rnn_tc_max_in_flight() {
 }
 static int rt_bp(int B) { return (B <= 64 || rnn_tc_max_in_flight() > 1) ? 64 : 128; }
 
+// Picks the W_hh slicing of a layer: 64-row slices when they fit next to a ring of at least one slot, else 48-row
+// ("narrow") slices -- more CTAs per direction, which for wide bidirectional layers means one launch per direction.
+bool rnn_tc_narrow(const RnnLayer& L, int B) {
+  const int HP = (L.H + 63) / 64 * 64;
+  const tc::RtPlan pl = tc::rt_plan(HP / 64, rt_bp(B), tc::rt_units(L.gates, false), g_tune.rnn_ring_gsz.load(), false);
+  return pl.groups < 1 || pl.gsz < 1 || pl.total > tc::RT_SMEM_LIMIT;
+}
+
 bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* launches_out) {
-  const int UH = 32 / L.gates, U = 2 * UH;
+  const bool narrow = rnn_tc_narrow(L, B);
+  const int U = tc::rt_units(L.gates, narrow);
   const int cpd = cdiv(L.H, U);
   const int HP = (L.H + 63) / 64 * 64;
-  const tc::RtPlan pl = tc::rt_plan(HP / 64, rt_bp(B), U, g_tune.rnn_ring_gsz.load());
+  const tc::RtPlan pl = tc::rt_plan(HP / 64, rt_bp(B), U, g_tune.rnn_ring_gsz.load(), narrow);
   if (B < 1 || pl.groups < 1 || pl.gsz < 1 || pl.total > tc::RT_SMEM_LIMIT || cpd > sms) return false;
   if (cpd_out) *cpd_out = cpd;
   if (launches_out) *launches_out = (L.dirs * cpd <= sms) ? 1 : L.dirs;
@@ -694,11 +709,17 @@ size_t rnn_tc_hbuf_elems(const RnnLayer& L, int B) {
   return (size_t)cdiv(B, BP) * 2 * L.dirs * BP * HP;
 }
 
+size_t rnn_tc_pack_elems(const RnnLayer& L) {
+  const bool narrow = rnn_tc_narrow(L, 64);
+  return (size_t)L.dirs * cdiv(L.H, tc::rt_units(L.gates, narrow)) * tc::rt_rows(narrow) * ((L.H + 63) / 64 * 64);
+}
+
 int pack_whh_tc(const RnnLayer& L, __nv_bfloat16* out, cudaStream_t st) {
-  const int U = 2 * (32 / L.gates), cpd = cdiv(L.H, U), HP = (L.H + 63) / 64 * 64;
-  const int64_t total = (int64_t)L.dirs * cpd * tc::RT_N * HP;
+  const bool narrow = rnn_tc_narrow(L, 64);
+  const int U = tc::rt_units(L.gates, narrow), cpd = cdiv(L.H, U), HP = (L.H + 63) / 64 * 64;
+  const int64_t total = (int64_t)rnn_tc_pack_elems(L);
   tc::pack_whh_kernel<<<(int)(cdiv64(total, 256) < 2048 ? cdiv64(total, 256) : 2048), 256, 0, st>>>(
-      L.w_hh, out, L.dirs, cpd, L.gates, L.H, HP, U);
+      L.w_hh, out, L.dirs, cpd, L.gates, L.H, HP, U, tc::rt_hs(narrow));
   DSB_CHECK_LAUNCH();
   return 0;
 }
@@ -809,14 +830,16 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
     if (int e = rnn_tc_init_hbuf(h0, hbuf, L.dirs, B, L.H, HP, BP, n_bgroups, st)) return e;
 
   CUtensorMap tw, th;
-  uint64_t dw[2] = {(uint64_t)HP, (uint64_t)L.dirs * cpd * RT_N}, sw[2] = {2, (uint64_t)HP * 2};
-  uint32_t bw[2] = {RT_BK, RT_N};
+  const bool narrow = rnn_tc_narrow(L, B);
+  const int U = rt_units(L.gates, narrow);
+  uint64_t dw[2] = {(uint64_t)HP, (uint64_t)L.dirs * cpd * rt_rows(narrow)}, sw[2] = {2, (uint64_t)HP * 2};
+  uint32_t bw[2] = {RT_BK, (uint32_t)rt_rows(narrow)};
   if (int e = make_tmap_bf16(&tw, L.w_hh_pack, 2, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   // h exchange buffer as {64 k, rows, K chunks}: one box {64, BP, RT_GROUP} = RT_GROUP consecutive chunk tiles
   uint64_t dh[3] = {(uint64_t)RT_BK, (uint64_t)n_bgroups * 2 * L.dirs * BP, (uint64_t)nkc};
   uint64_t sh[3] = {2, (uint64_t)HP * 2, (uint64_t)RT_BK * 2};
   const int ring_gsz = g_tune.rnn_ring_gsz.load();
-  const int gsz = rt_plan(nkc, BP, 2 * (32 / L.gates), ring_gsz).gsz;
+  const int gsz = rt_plan(nkc, BP, U, ring_gsz, narrow).gsz;
   uint32_t bh[3] = {RT_BK, (uint32_t)BP, (uint32_t)gsz};
   if (int e = make_tmap_bf16(&th, hbuf, 3, dh, sh, bh, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
 
@@ -831,21 +854,23 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
   p.h0 = h0; p.c0 = c0; p.hT = hT; p.cT = cT;
   p.n_bgroups = n_bgroups; p.slots = slots;
   p.B = B; p.H = L.H; p.HP = HP; p.BP = BP; p.T = T; p.Tmax = Tmax;
-  p.dirs = L.dirs; p.cpd = cpd; p.U = 2 * (32 / L.gates); p.nkc = nkc;
+  p.dirs = L.dirs; p.cpd = cpd; p.U = U; p.nkc = nkc;
   p.ring_gsz = ring_gsz;
   // two producers own alternate ring slots, which only works when the ring has an even number of them (a producer
   // must never be two uses of the same slot ahead of the MMAs: the slot barriers carry one parity bit)
-  p.n_producers = (g_tune.rnn_producers.load() == 2 && rt_plan(nkc, BP, 2 * (32 / L.gates), ring_gsz).groups % 2 == 0) ? 2 : 1;
-  const size_t smem = (size_t)rt_plan(nkc, BP, 2 * (32 / L.gates), ring_gsz).total;
+  p.n_producers = (g_tune.rnn_producers.load() == 2 && rt_plan(nkc, BP, U, ring_gsz, narrow).groups % 2 == 0) ? 2 : 1;
+  const size_t smem = (size_t)rt_plan(nkc, BP, U, ring_gsz, narrow).total;
   static const int split_env = getenv("DSB_RNN_SPLIT") ? atoi(getenv("DSB_RNN_SPLIT")) : 1;
   const bool split = L.gates == 3 && BP == 64 && split_env;
   const void* fn = nullptr;
-#define RT_PICK(G, S)                                                                          \
-  fn = nif == 1 ? (const void*)rnn_tc_kernel<G, S, 1> : nif == 2 ? (const void*)rnn_tc_kernel<G, S, 2> \
-                                                                 : (const void*)rnn_tc_kernel<G, S, 3>
+#define RT_PICK2(G, S, W)                                                                             \
+  fn = nif == 1 ? (const void*)rnn_tc_kernel<G, S, 1, W> : nif == 2 ? (const void*)rnn_tc_kernel<G, S, 2, W> \
+                                                                   : (const void*)rnn_tc_kernel<G, S, 3, W>
+#define RT_PICK(G, S) do { if (narrow) { RT_PICK2(G, S, true); } else { RT_PICK2(G, S, false); } } while (0)
   if (L.gates == 3) { if (split) RT_PICK(3, true); else RT_PICK(3, false); }
   else if (L.gates == 4) RT_PICK(4, false);
   else RT_PICK(1, false);
+#undef RT_PICK2
 #undef RT_PICK
   DSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool debug = getenv("DSB_RNN_DEBUG") != nullptr;
@@ -883,7 +908,7 @@ int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B
                              "epi.wait_mma", "epi.math_store", "epi.bar", "epi.publish", "mma.wait_rest",
                              "prod.wait_empty"};
     const int items = cdiv(n_bgroups, slots) * Tmax;   // (step, group) items per CTA (upper bound for ragged groups)
-    const RtPlan dpl = rt_plan(nkc, BP, 2 * (32 / L.gates), ring_gsz);
+    const RtPlan dpl = rt_plan(nkc, BP, U, ring_gsz, narrow);
     fprintf(stderr, "[rnn_tc debug] H=%d B=%d Tmax=%d grid=%d groups=%d slots=%d in flight=%d ring=%dx%d  cycles/item (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid, n_bgroups, slots, nif, dpl.groups, dpl.gsz);
     for (int k = 0; k < 12; ++k) {
       double sum = 0, mx = 0;

@@ -107,3 +107,38 @@ def test_headline_bf16_logits_and_asserted_transcript_rate(headline):
     assert agree >= BF16_MIN_FRAME_AGREEMENT
     assert tr["cer"] <= BF16_MAX_CER
     assert frames["max_flipped_margin"] <= BF16_MAX_FLIPPED_MARGIN
+
+
+def test_headline_beam64_lm_on_model_output_matches_oracle(headline, tmp_path):
+    """BASELINE config 3 on the headline shape: beam width 64 + synthetic 3-gram LM over the MODEL's probabilities of the
+    benchmarked batch (T' = 751), GPU prefix beam search against the CPU oracle (oracle/ctc_beam.cpp) on the 8 sampled
+    utterances, and the whole batch decoded through the public API.  north_star: top-1 identical on >= 99.5 % of the
+    utterances, beam scores within 1e-3."""
+    from danspeech_b200 import Recognizer
+    from danspeech_b200.deepspeech.decoder import BeamCTCDecoder
+    from danspeech_b200.pretrained_models import build_model
+    from oracle.beam import CTCBeamDecoderOracle
+    arpa = syn.write_synthetic_arpa(str(tmp_path / "lm.arpa"), n_words=2000, seed=0)
+    rec = Recognizer(model=build_model("DanSpeechPrimary", seed=0).set_precision("fp32"))
+    eng = rec.danspeech_recognizer
+    x, lens = eng.audio_parser.parse_batch(headline["auds"])
+    probs, sizes = eng.model(x, lens)
+    sub = probs[SAMPLE].contiguous()
+    gpu = BeamCTCDecoder(syn.LABELS, arpa, 1.3, 0.2, 40, 1.0, 64, 6, 0)
+    ref = CTCBeamDecoderOracle(syn.LABELS, arpa, 1.3, 0.2, 40, 1.0, 64, 6, 0)
+    out, scores, ts, out_len = [t.cpu().numpy() for t in gpu.decode_device(sub, sizes[SAMPLE])]
+    r_out, r_scores, r_ts, r_len = ref.decode(sub.cpu().numpy(), sizes[SAMPLE].tolist())
+    same = 0
+    for b in range(len(SAMPLE)):
+        n, rn = out_len[b, 0], r_len[b, 0]
+        if n == rn and np.array_equal(out[b, 0, :n], r_out[b, 0, :rn]):
+            same += 1
+            assert abs(scores[b, 0] - r_scores[b, 0]) <= 1e-3 * max(1.0, abs(r_scores[b, 0])), b
+            assert np.array_equal(ts[b, 0, :n], r_ts[b, 0, :rn]), b            # character offsets of the top beam
+    print("beam-64 + LM on model output, T' = 751: top-1 identical on %d / %d utterances" % (same, len(SAMPLE)))
+    assert same == len(SAMPLE)
+    # the public API on the whole batch (top beam only) agrees with the decoder object
+    rec.update_decoder(lm=arpa, alpha=1.3, beta=0.2, beam_width=64)
+    texts = rec.recognize_batch(headline["auds"])
+    want, _ = ref.decode_strings(sub.cpu().numpy(), sizes[SAMPLE].tolist())
+    assert [texts[i] for i in SAMPLE] == [w[0] for w in want]

@@ -528,10 +528,13 @@ def test_back_to_back_parse_batch_does_not_reuse_a_busy_staging_buffer():
         assert not torch.equal(sb, ref_a)
 
 
-def test_wide_layer_small_ring_and_large_batch_fallback():
-    """H = 1600: the resident W_hh slice leaves room for one group of two K chunks with 64-row groups (persistent
-    kernel, degenerate ring) and for none with 128-row groups (batch 70 -> per-step fp32 recurrence)."""
-    kw = dict(rnn_hidden_size=1600, rnn_layers=1)
+@pytest.mark.parametrize("H", [1600, 2000])
+def test_wide_layer_small_ring_and_large_batch_fallback(H):
+    """Wide layers on the persistent recurrence.  H = 1600: the resident 64-row W_hh slice leaves room for one ring
+    slot of two K chunks (degenerate ring).  H = 2000 (the GPUStreamingRNN width, streaming_model_GPU.py:11-15): a
+    64-row slice does not fit at all, the layer runs on 48-row ("narrow") slices, 125 CTAs per direction, one launch
+    per direction.  Batch 2 and batch 70 (two groups of 64 rows in flight)."""
+    kw = dict(rnn_hidden_size=H, rnn_layers=1)
     cfg = case_config("TestModel", kw)
     sd = syn.make_state_dict(seed=21, **cfg)
     m = _model("TestModel", kw, seed=21, precision="bf16")
@@ -710,3 +713,34 @@ def test_spectrogram_windows_match_reference_golden(window):
     for i, c in enumerate([a[:8640], a[8640:8640 + 6240], a[8640 + 6240:]]):
         o = sp.parse_audio(c, is_last=(i == 2))
         assert rel_err(o.cpu().numpy(), g["stream_%s_%d" % (window, i)]) < FP32_TOL
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_streaming_cpu_streaming_rnn_shape_matches_oracle(precision, tol):
+    """BASELINE config 4 shape (CPUStreamingRNN: 2 conv, 5 x 800 uni-GRU, lookahead 20) against the ORACLE (the CPU
+    restatement of MaskConvStream / BatchRNNStream / LookaheadStream, model.py:156-284,517-537), not against this
+    repo's other precision: three different streams in lock step over the engine's chunk schedule."""
+    from danspeech_b200.audio.parsers import InferenceSpectrogramAudioParser
+    cfg = case_config("CPUStreamingRNN", {})
+    sd = syn.make_state_dict(seed=8, **cfg)
+    m = _model("CPUStreamingRNN", {}, seed=8, precision=precision)
+    S, n_chunks = 3, 4
+    auds = [syn.synthetic_audio(8640 + 6240 * (n_chunks - 1), seed=170 + i) for i in range(S)]
+    specs = []
+    for a in auds:
+        sp = InferenceSpectrogramAudioParser()
+        specs.append([sp.parse_audio(c, is_last=(i == n_chunks - 1)).cpu() for i, c in enumerate(_stream_chunks(a))])
+    oracles = [om.StreamingOracle(sd, cfg["rnn_layers"], context=cfg["context"]) for _ in range(S)]
+    worst = 0.0
+    for i in range(n_chunks):
+        x = torch.stack([specs[s][i] for s in range(S)]).view(S, 1, 161, -1)
+        o = m(x.cuda(), i == 0, i == n_chunks - 1)
+        for s in range(S):
+            ref = oracles[s].forward(specs[s][i].view(1, 1, 161, -1), i == 0, i == n_chunks - 1)
+            if ref is None:
+                assert o is None
+            else:
+                assert tuple(o[s].shape) == tuple(ref[0].shape)
+                worst = max(worst, logit_rel_err(o[s].cpu().numpy(), ref[0].numpy()))
+    print("CPUStreamingRNN shape, %s: worst logit rel err vs oracle %.2e" % (precision, worst))
+    assert worst < tol
