@@ -82,7 +82,10 @@ const Knob* knobs(int* n) {
                            {"rnn_max_slots", &dsb::g_tune.rnn_max_slots, 0, 1 << 20},
                            {"rnn_ksplit", &dsb::g_tune.rnn_ksplit, 0, 1},
                            {"rnn_ring_gsz", &dsb::g_tune.rnn_ring_gsz, 0, 4},
-                           {"rnn_producers", &dsb::g_tune.rnn_producers, 1, 2}};
+                           {"rnn_producers", &dsb::g_tune.rnn_producers, 1, 2},
+                           {"rnn_pair", &dsb::g_tune.rnn_pair, 0, 1},
+                           {"rnn_batch_minor", &dsb::g_tune.rnn_batch_minor, 0, 1},
+                           {"rnn_pair_in_flight", &dsb::g_tune.rnn_pair_in_flight, 1, 3}};
   *n = (int)(sizeof(k) / sizeof(k[0]));
   return k;
 }

@@ -224,19 +224,32 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
     // the persistent kernel's shared-memory plan depends on the batch-group size (64 or 128 rows): wide layers that
     // fit with 64 rows may not fit with 128, in which case this batch takes the per-step fp32 recurrence
     const bool tc_rnn = R.tc_recurrence && rnn_tc_supported(R, B, dev_sms, nullptr, nullptr);
+    // the CTA-pair recurrence reads batch-minor pre-activations and writes batch-minor outputs (coalesced per warp)
+    const bool bminor = tc_rnn && rnn_batch_minor(R, B);
     prof_begin(ST_PROJ, st);
-    if (int e = gemm_bias_tc(ws.xb, R.in_ld, R.w_ih_tc, R.in_ld, tc_rnn ? R.b_ih_tc : R.b_ih, ws.gates, N, (int)M, N,
-                             R.in_size, st))
+    if (bminor) {
+      if (int e = gemm_bias_rows_tc(ws.xb, R.in_ld, R.w_ih_tc, R.in_ld, R.b_ih_tc, ws.gates, M, (int)M, N, R.in_size, st))
+        return e;
+    } else if (int e = gemm_bias_tc(ws.xb, R.in_ld, R.w_ih_tc, R.in_ld, tc_rnn ? R.b_ih_tc : R.b_ih, ws.gates, N, (int)M,
+                                    N, R.in_size, st)) {
       return e;
+    }
     prof_end(ST_PROJ, st);
     prof_begin(ST_RNN, st);
     const int next_ld = (H + 7) / 8 * 8;
     if (tc_rnn) {
       used_tc_rnn = true;
-      if (int e = rnn_layer_tc(R, ws.gates, ws.d_len, B, Tp, Tmax, ws.ydir, ws.hbuf, ws.sync_words, m->d_abort, st)) return e;
-      if (int e = combine_dirs_tc(ws.ydir, R.dirs, Tp, B, H, ws.d_len, last ? nullptr : ws.xb, next_ld,
-                                  last ? ws.xf : nullptr, st))
+      if (int e = rnn_layer_tc(R, ws.gates, ws.d_len, B, Tp, Tmax, ws.ydir, ws.hbuf, ws.sync_words, m->d_abort, st,
+                               nullptr, nullptr, nullptr, nullptr, bminor))
         return e;
+      if (bminor) {
+        if (int e = combine_dirs_t_tc(ws.ydir, R.dirs, Tp, B, H, ws.d_len, last ? nullptr : ws.xb, next_ld,
+                                      last ? ws.xf : nullptr, st))
+          return e;
+      } else if (int e = combine_dirs_tc(ws.ydir, R.dirs, Tp, B, H, ws.d_len, last ? nullptr : ws.xb, next_ld,
+                                         last ? ws.xf : nullptr, st)) {
+        return e;
+      }
     } else {
       if (int e = rnn_layer_f32(m, R, ws.gates, ws.d_len, B, Tmax, Tp, ws.xf, ws.hstate, ws.cstate, st)) return e;
       if (!last) {

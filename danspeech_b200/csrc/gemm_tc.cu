@@ -61,27 +61,30 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                : "memory");
 }
+// bias_row: the bias belongs to the ROWS of C (operands swapped: C^T = W * A^T, see gemm_bias_rows_tc)
 __device__ __forceinline__ void store_chunk16(const uint32_t (&r)[16], float* __restrict__ C, int64_t ldc, int row, int M,
-                                              int N, int col, const float* __restrict__ bias, bool vec_ok) {
+                                              int N, int col, const float* __restrict__ bias, bool vec_ok, bool bias_row) {
   if (row >= M) return;
   float* dst = C + (int64_t)row * ldc + col;
+  const float rb = (bias && bias_row) ? __ldg(bias + row) : 0.f;
+  const float* cb = (bias && !bias_row) ? bias : nullptr;
   if (vec_ok && col + 16 <= N) {
 #pragma unroll
     for (int j = 0; j < 16; j += 8) {
       float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]) + (bias ? __ldg(bias + col + j + i) : 0.f);
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]) + (cb ? __ldg(cb + col + j + i) : rb);
       st_global_v8(dst + j, v);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (col + j < N) dst[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + col + j) : 0.f);
+      if (col + j < N) dst[j] = __uint_as_float(r[j]) + (cb ? __ldg(cb + col + j) : rb);
   }
 }
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_addr, float* __restrict__ C, int64_t ldc, int row, int M, int N,
-                                              int n0, const float* __restrict__ bias, bool vec_ok) {
+                                              int n0, const float* __restrict__ bias, bool vec_ok, bool bias_row) {
   static_assert(BN % 16 == 0, "BN must be a multiple of 16");
   uint32_t ra[16], rb[16];
   tmem_ld16(t_addr, ra);
@@ -89,11 +92,11 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_addr, float* __restrict
   for (int c0 = 0; c0 < BN; c0 += 32) {
     tmem_ld_wait_dep(ra);
     if (c0 + 16 < BN) tmem_ld16(t_addr + c0 + 16, rb);
-    store_chunk16(ra, C, ldc, row, M, N, n0 + c0, bias, vec_ok);
+    store_chunk16(ra, C, ldc, row, M, N, n0 + c0, bias, vec_ok, bias_row);
     if (c0 + 16 < BN) {
       tmem_ld_wait_dep(rb);
       if (c0 + 32 < BN) tmem_ld16(t_addr + c0 + 32, ra);
-      store_chunk16(rb, C, ldc, row, M, N, n0 + c0 + 16, bias, vec_ok);
+      store_chunk16(rb, C, ldc, row, M, N, n0 + c0 + 16, bias, vec_ok, bias_row);
     }
   }
 }
@@ -110,7 +113,7 @@ struct GemmSmem {
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K) {
+               const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K, int bias_row) {
   using S = GemmSmem<BN>;
   constexpr int TMEM_COLS = 512;
   constexpr int ACC_STRIDE = 256;
@@ -212,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t t_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN>(t_addr, C, ldc, row, M, N, n0, bias, vec_ok);
+      epilogue_tile<BN>(t_addr, C, ldc, row, M, N, n0, bias, vec_ok, bias_row != 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -249,7 +252,7 @@ struct Gemm2Smem {
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K) {
+                const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K, int bias_row) {
   using S = Gemm2Smem<BN>;
   constexpr int STAGES2 = S::STAGES2;
   constexpr int TMEM_COLS = 512;
@@ -359,7 +362,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t t_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN>(t_addr, C, ldc, row, M, N, n0, bias, vec_ok);
+      epilogue_tile<BN>(t_addr, C, ldc, row, M, N, n0, bias, vec_ok, bias_row != 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));   // the leader's barrier
@@ -380,7 +383,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
 template <int BN>
 static int launch_gemm2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
-                        float* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+                        float* C, int64_t ldc, int M, int N, int K, cudaStream_t st, int bias_row = 0) {
   CUtensorMap ta, tb;
   uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}, strA[2] = {2, (uint64_t)lda * 2};
   uint32_t boxA[2] = {BK, BM};
@@ -396,14 +399,14 @@ static int launch_gemm2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16
   const int tiles = cdiv(M, 2 * BM) * cdiv(N, BN);
   int pairs = sms / 2;
   if (tiles < pairs) pairs = tiles;
-  gemm_tc2_kernel<BN><<<2 * pairs, GEMM_THREADS, Gemm2Smem<BN>::TOTAL, st>>>(ta, tb, bias, C, ldc, M, N, K);
+  gemm_tc2_kernel<BN><<<2 * pairs, GEMM_THREADS, Gemm2Smem<BN>::TOTAL, st>>>(ta, tb, bias, C, ldc, M, N, K, bias_row);
   DSB_CHECK_LAUNCH();
   return 0;
 }
 
 template <int BN>
 static int launch_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
-                       float* C, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+                       float* C, int64_t ldc, int M, int N, int K, cudaStream_t st, int bias_row = 0) {
   CUtensorMap ta, tb;
   uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}, strA[2] = {2, (uint64_t)lda * 2};
   uint32_t boxA[2] = {BK, BM};
@@ -418,7 +421,7 @@ static int launch_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16*
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int grid = tiles < sms ? tiles : sms;
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(ta, tb, bias, C, ldc, M, N, K);
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(ta, tb, bias, C, ldc, M, N, K, bias_row);
   DSB_CHECK_LAUNCH();
   return 0;
 }
@@ -440,6 +443,20 @@ int gemm_bias_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
   if (N > 128) return tc::launch_gemm<256>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
   if (N > 64) return tc::launch_gemm<128>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
   return tc::launch_gemm<64>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+}
+
+// Ct [N, ldc] = (A * W^T + bias)^T: the same product with the operands swapped on the tensor cores (W rows become the
+// accumulator rows), so that the output is batch-minor -- what the CTA-pair recurrence (rnn_pair.cu) reads coalesced:
+// its epilogue threads own one sequence each, a warp owns 32 consecutive (t, b) rows of one gate column.
+int gemm_bias_rows_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
+                      float* Ct, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+  if ((lda & 7) || (ldw & 7)) return set_error(DSB_ERR_INVALID, "gemm_bias_rows_tc: lda/ldw must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return set_error(DSB_ERR_INVALID, "gemm_bias_rows_tc: operands must be 16-byte aligned");
+  if (N >= 256 && M >= 256) return tc::launch_gemm2<256>(W, ldw, A, lda, bias, Ct, ldc, N, M, K, st, 1);
+  if (M > 128) return tc::launch_gemm<256>(W, ldw, A, lda, bias, Ct, ldc, N, M, K, st, 1);
+  if (M > 64) return tc::launch_gemm<128>(W, ldw, A, lda, bias, Ct, ldc, N, M, K, st, 1);
+  return tc::launch_gemm<64>(W, ldw, A, lda, bias, Ct, ldc, N, M, K, st, 1);
 }
 
 }  // namespace dsb

@@ -99,9 +99,23 @@ int rnn_tc_max_in_flight();
 size_t rnn_tc_hbuf_elems(const RnnLayer& L, int B);
 int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
                  __nv_bfloat16* hbuf, unsigned int* sync_words, int* abort_flag, cudaStream_t st,
-                 const float* h0 = nullptr, const float* c0 = nullptr, float* hT = nullptr, float* cT = nullptr);
+                 const float* h0 = nullptr, const float* c0 = nullptr, float* hT = nullptr, float* cT = nullptr,
+                 bool batch_minor = false);
+bool rnn_batch_minor(const RnnLayer& L, int B);
 int rnn_tc_init_hbuf(const float* h0, __nv_bfloat16* hbuf, int dirs, int B, int H, int HP, int BP, int n_bgroups,
                      cudaStream_t st);
+// CTA-pair recurrence on tcgen05.mma.cta_group::2 (rnn_pair.cu): same contract and W_hh slices as rnn_layer_tc
+bool rnn_tc_narrow(const RnnLayer& L, int B);
+bool rnn_pair_supported(const RnnLayer& L, int B, int sms);
+// batch_minor: gx is [dirs*G*H][T*B] (gemm_bias_rows_tc) and y is written as [dirs][H][T*B] (combine_dirs_t_tc)
+int rnn_layer_pair(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
+                   __nv_bfloat16* hbuf, unsigned int* sync_words, int* abort_flag, cudaStream_t st,
+                   const float* h0 = nullptr, const float* c0 = nullptr, float* hT = nullptr, float* cT = nullptr,
+                   bool batch_minor = false);
+int gemm_bias_rows_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias,
+                      float* Ct, int64_t ldc, int M, int N, int K, cudaStream_t st);
+int combine_dirs_t_tc(const float* yt, int dirs, int T, int B, int H, const int32_t* d_len, __nv_bfloat16* xb, int ldx,
+                      float* xf, cudaStream_t st);
 // K-split CTA-pair recurrence (rnn_ks.cu): same contract as rnn_layer_tc, batch groups of 64 rows
 bool rnn_ks_supported(const RnnLayer& L, int sms, int* pairs_out, int* launches_out);
 size_t rnn_ks_pack_elems(const RnnLayer& L);

@@ -24,150 +24,12 @@
 // 2*B*3H*H flop per step per direction and is reported against the tensor roof.
 //
 // Every wait is bounded: a stuck barrier sets an abort flag instead of hanging the GPU.
-#include "tc_common.cuh"
-#include "model_types.cuh"
+#include "rnn_tc.cuh"
 #include <cstdlib>
 
 namespace dsb {
 namespace tc {
 
-constexpr int RT_BK = 64;
-// W_hh rows per CTA = 2 halves x HS accumulator columns.  Default: HS = 32 (64 rows, 8 KB per K chunk); "narrow" slices
-// for wide layers whose 64-row slice does not fit shared memory (H > ~1500): HS = 24 (48 rows, 6 KB per K chunk).
-__host__ __device__ constexpr int rt_hs(bool narrow) { return narrow ? 24 : 32; }
-__host__ __device__ constexpr int rt_rows(bool narrow) { return 2 * rt_hs(narrow); }
-__host__ __device__ constexpr int rt_units(int gates, bool narrow) { return 2 * (rt_hs(narrow) / gates); }
-constexpr int RT_GROUP = 4;        // most K chunks per ring slot / elected issue region
-constexpr int RT_MAX_GROUPS = 4;   // barrier slots; the ring holds 2 groups of 4 chunks or up to 4 groups of 2
-constexpr int RT_MAX_NIF = 3;      // batch groups in flight per CTA (each with its own TMEM accumulator)
-// (Consecutive tcgen05.mma into the same accumulator do not stall each other -- tested with 4 independent
-// accumulators: no change -- so a single 64-column TMEM accumulator per batch group is used.)
-constexpr int RT_THREADS = 64 + 256 + 32;   // producer, MMA issuer, 8 epilogue warps, second producer
-constexpr long long RT_TIMEOUT_CYCLES = 4000000000LL;
-constexpr int RT_SMEM_LIMIT = 227 * 1024;
-
-// Shared-memory plan: [W slice: nkc x 8 KB][h ring: slots x gsz stages x BP*128 B][h store staging][row times][barriers].
-// The MMA is M = BP (64 or 128 batch rows): with M = 64 only the 64 valid rows are read from shared memory.
-// Every elected issue region (elect.sync + single-lane branch + reconvergence) costs ~200 cycles on top
-// of ~35 cycles per tcgen05.mma / TMA instruction (scripts/mma_microbench.py), so the producer and the MMA
-// warp work in groups of `gsz` chunks: one region issues one TMA box of gsz chunks, one region issues 4*gsz MMAs.
-// The ring slot is the unit of flow control: a slot is refilled when its MMAs have completed.  The h stream is bound
-// by the SM's TMA intake (~35 B/clk: 152 KB per step at H = 1200), so the ring should keep the TMA unit busy ACROSS
-// steps: with two slots the unit idles while the last two slots of a step drain; three slots of three chunks let it
-// run ahead into the next group's step.  The kernel has no static shared memory, so the dynamic window starts on a
-// 1 KB boundary and the plan may use all of the 227 KB.
-struct RtPlan {
-  int groups, gsz, stage_bytes, stage_off, stg_off, st_off, bar_off, total;
-};
-__host__ __device__ inline RtPlan rt_plan(int nkc, int BP, int U, int want_gsz = 0, bool narrow = false) {
-  RtPlan pl;
-  pl.stage_bytes = BP * RT_BK * 2;
-  const int w_bytes = nkc * rt_rows(narrow) * RT_BK * 2;
-  const int stg = (BP * U * 2 + 127) / 128 * 128;   // h (bf16) staging for coalesced stores
-  const int st = BP * 4;                            // time index of every row of the group (-1 = inactive)
-  const int room = RT_SMEM_LIMIT - 256 - w_bytes - stg - st;
-  const int stages = room > 0 ? room / pl.stage_bytes : 0;
-  int gsz, groups;
-  if (want_gsz > 0) {
-    gsz = want_gsz;
-    groups = stages / gsz;
-  } else if (stages >= 8) {      // (three slots of three chunks fit too and were measured slower: the cost is per box)
-    gsz = 4; groups = 2;
-  } else {
-    gsz = 2; groups = stages / 2;
-  }
-  if (gsz > nkc) { gsz = nkc; groups = gsz ? stages / gsz : 0; }
-  if (groups > RT_MAX_GROUPS) groups = RT_MAX_GROUPS;
-  pl.groups = groups;
-  pl.gsz = gsz;
-  pl.stage_off = w_bytes;
-  pl.stg_off = w_bytes + groups * gsz * pl.stage_bytes;
-  pl.st_off = pl.stg_off + stg;
-  pl.bar_off = pl.st_off + st;
-  pl.total = pl.bar_off + 256;
-  return pl;
-}
-
-struct RnnTcParams {
-  const float* gx;          // [T*B][dirs*G*H]
-  const float* b_hn;        // [dirs][H] GRU n-gate hidden bias (else nullptr)
-  float* y;                 // [dirs][T][B][H]
-  __nv_bfloat16* hbuf;      // [n_bgroups][2][dirs][BP][HP]
-  const int32_t* lens;      // [B] sorted descending, or nullptr (every sequence runs Tmax steps)
-  unsigned int* counters;   // [dirs][slots][NIF] step counters, kRnnCounterStride words apart
-  int* abort_flag;
-  const float* h0;          // [dirs][B][H] initial hidden state or nullptr (zeros)
-  const float* c0;          // LSTM cell state, likewise
-  float* hT;                // [dirs][B][H] final hidden state or nullptr
-  float* cT;
-  int B, H, HP, BP, T, Tmax;
-  int dirs;   // directions in gx / y / hbuf / counters
-  int dir0;   // first direction handled by this launch
-  int cpd;    // CTAs per (direction, slot)
-  int n_bgroups;   // the batch is processed in groups of BP rows ...
-  int slots;       // ... by `slots` independent CTA sets per direction (set k takes groups k, k+slots, ...),
-                   // NIF groups of a set in flight at a time
-  int U;      // hidden units per CTA (2 * units per half)
-  int ring_gsz;       // K chunks per ring slot, 0 = default (rt_plan)
-  int n_producers;    // TMA producer warps (1 or 2)
-  int nkc;    // K chunks of 64 (HP / 64)
-  unsigned long long* dbg;   // optional [grid][128] cycle counters (DSB_RNN_DEBUG=1)
-};
-
-__device__ __forceinline__ bool wait_abortable(uint64_t* bar, uint32_t parity, int* abort_flag) {
-  long long t0 = 0;
-  unsigned n = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++n & 0xFF) == 0) {
-      if (*(volatile int*)abort_flag) return false;
-      long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > RT_TIMEOUT_CYCLES) {
-        atomicExch(abort_flag, 1);
-        return false;
-      }
-    }
-  }
-  return true;
-}
-
-__device__ __forceinline__ bool bar_red_and(bool pred, int id, int nthreads) {
-  uint32_t r;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.u32 q, %1, 0;\n\t"
-      "barrier.cta.red.and.pred p, %2, %3, q;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(r)
-      : "r"((uint32_t)pred), "r"(id), "r"(nthreads)
-      : "memory");
-  return r != 0;
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-// tanh.approx.f32 is only good to ~5e-4 absolute, which is visible after 9 recurrent layers; the
-// exp-based form below is accurate to ~1e-6 and still a handful of instructions.
-__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
-
-// Steps of batch group bg: the lengths are sorted descending (forward() rejects anything else, like
-// pack_padded_sequence behind model.py:117), so the group's first row is its longest sequence.
-__device__ __forceinline__ int rt_group_steps(const RnnTcParams& p, int bg) {
-  if (bg >= p.n_bgroups) return 0;
-  if (!p.lens) return p.Tmax;
-  const int l = p.lens[bg * p.BP];
-  return l < p.Tmax ? l : p.Tmax;
-}
 
 // NIF batch groups of a CTA set are in flight at a time.  One step of one group is a serial chain -- all-gather of
 // h (publish -> barrier -> TMA: ~3.4 k cycles of latency) -> 76 MMAs (~4.5 k) -> gate math and publish (~2.7 k) --
@@ -217,7 +79,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   const int slot = set % p.slots;
   const int c = blockIdx.x % p.cpd;
   // every CTA walks the K chunks in its own rotation so that the readers do not hit the same L2 lines together
-  const int g_rot = (int)(((long long)c * gps) / p.cpd);   // rotation in whole ring groups
+  // (neighbouring CTAs share a rotation: the CTA-pair kernel, rnn_pair.cu, then accumulates in the same order)
+  const int g_rot = (int)(((long long)(c >> 1) * gps) / ((p.cpd + 1) >> 1));   // rotation in whole ring groups
   unsigned* const ctr0 = p.counters + (size_t)((dir * p.slots + slot) * NIF) * kRnnCounterStride;
 
   if (warp == 0 && lane == 0) {
@@ -692,6 +555,16 @@ bool rnn_tc_narrow(const RnnLayer& L, int B) {
   return pl.groups < 1 || pl.gsz < 1 || pl.total > tc::RT_SMEM_LIMIT;
 }
 
+// True when this layer / batch takes the CTA-pair kernel and no other kernel has been asked for: the caller then hands
+// over batch-minor pre-activations and gets batch-minor outputs (see rnn_layer_pair).
+bool rnn_batch_minor(const RnnLayer& L, int B) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool ks = L.ks_recurrence && g_tune.rnn_ksplit.load() && rnn_tc_max_in_flight() > 1;
+  return !ks && g_tune.rnn_batch_minor.load() && rnn_pair_supported(L, B, sms);
+}
+
 bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* launches_out) {
   const bool narrow = rnn_tc_narrow(L, B);
   const int U = tc::rt_units(L.gates, narrow);
@@ -706,7 +579,8 @@ bool rnn_tc_supported(const RnnLayer& L, int B, int sms, int* cpd_out, int* laun
 
 size_t rnn_tc_hbuf_elems(const RnnLayer& L, int B) {
   const int HP = (L.H + 63) / 64 * 64, BP = rt_bp(B);
-  return (size_t)cdiv(B, BP) * 2 * L.dirs * BP * HP;
+  // an even number of groups: the CTA-pair kernel (rnn_pair.cu) streams a (zero) buffer for the missing partner of the last group
+  return (size_t)((cdiv(B, BP) + 1) / 2 * 2) * 2 * L.dirs * BP * HP;
 }
 
 size_t rnn_tc_pack_elems(const RnnLayer& L) {
@@ -757,6 +631,57 @@ __global__ void combine_dirs_vec4_kernel(const float* __restrict__ y, int dirs, 
 }
 }  // namespace tc
 
+namespace tc {
+// Batch-minor per-direction outputs yt [dirs][H][T*B] (rnn_pair.cu) -> next-layer operand x[t*B+b][j] = bf16(fwd + bwd)
+// for t < len_b, else 0 (and / or the fp32 copy): a 64 x 64 tile transpose through shared memory, coalesced both ways.
+__global__ void __launch_bounds__(256) combine_dirs_t_kernel(const float* __restrict__ yt, int dirs, int T, int B, int H,
+                                                             const int32_t* __restrict__ lens,
+                                                             __nv_bfloat16* __restrict__ xb, int ldx,
+                                                             float* __restrict__ xf) {
+  __shared__ float tile[64][65];
+  const int64_t M = (int64_t)T * B;
+  const int64_t m0 = (int64_t)blockIdx.x * 64;
+  const int j0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
+  {
+    const int64_t m = m0 + tx;
+    bool live = false;
+    if (m < M) {
+      const int b = (int)(m % B), t = (int)(m / B);
+      live = t < lens[b];
+    }
+    for (int jj = ty; jj < 64; jj += 4) {
+      const int j = j0 + jj;
+      float v = 0.f;
+      if (live && j < H) {
+        v = yt[(int64_t)j * M + m];
+        if (dirs == 2) v += yt[((int64_t)H + j) * M + m];
+      }
+      tile[jj][tx] = v;
+    }
+  }
+  __syncthreads();
+  for (int mm = ty; mm < 64; mm += 4) {
+    const int64_t m = m0 + mm;
+    const int j = j0 + tx;
+    if (m < M && j < H) {
+      const float v = tile[tx][mm];
+      if (xb) xb[m * ldx + j] = __float2bfloat16_rn(v);
+      if (xf) xf[m * H + j] = v;
+    }
+  }
+}
+}  // namespace tc
+
+int combine_dirs_t_tc(const float* yt, int dirs, int T, int B, int H, const int32_t* d_len, __nv_bfloat16* xb, int ldx,
+                      float* xf, cudaStream_t st) {
+  const int64_t M = (int64_t)T * B;
+  dim3 grid((unsigned)cdiv64(M, 64), (unsigned)cdiv(H, 64));
+  tc::combine_dirs_t_kernel<<<grid, 256, 0, st>>>(yt, dirs, T, B, H, d_len, xb, ldx, xf);
+  DSB_CHECK_LAUNCH();
+  return 0;
+}
+
 int combine_dirs_tc(const float* y, int dirs, int T, int B, int H, const int32_t* d_len, __nv_bfloat16* xb, int ldx,
                     float* xf, cudaStream_t st) {
   if ((H & 3) == 0 && (ldx & 3) == 0) {
@@ -805,13 +730,19 @@ int rnn_tc_init_hbuf(const float* h0, __nv_bfloat16* hbuf, int dirs, int B, int 
 // are [dirs][B][H] fp32 and may alias (streaming state carried across chunks, model.py:219-237).
 int rnn_layer_tc(const RnnLayer& L, const float* gx, const int32_t* d_len, int B, int T, int Tmax, float* y,
                  __nv_bfloat16* hbuf, unsigned int* sync_words, int* abort_flag, cudaStream_t st, const float* h0,
-                 const float* c0, float* hT, float* cT) {
+                 const float* c0, float* hT, float* cT, bool batch_minor) {
   using namespace tc;
+  if (batch_minor) {   // the caller asked rnn_batch_minor() first
+    if (!rnn_batch_minor(L, B)) return set_error(DSB_ERR_INVALID, "rnn_layer_tc: batch-minor layout needs the CTA-pair kernel");
+    return rnn_layer_pair(L, gx, d_len, B, T, Tmax, y, hbuf, sync_words, abort_flag, st, h0, c0, hT, cT, true);
+  }
   if (L.ks_recurrence && g_tune.rnn_ksplit.load() && rnn_tc_max_in_flight() > 1)
     return rnn_layer_ks(L, gx, d_len, B, T, Tmax, y, hbuf, sync_words, abort_flag, st, h0, c0, hT, cT);
   int dev = 0, sms = 148, cpd = 0, launches = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (rnn_pair_supported(L, B, sms))
+    return rnn_layer_pair(L, gx, d_len, B, T, Tmax, y, hbuf, sync_words, abort_flag, st, h0, c0, hT, cT);
   if (!rnn_tc_supported(L, B, sms, &cpd, &launches))
     return set_error(DSB_ERR_UNSUPPORTED, "rnn_layer_tc: shape H=%d B=%d not supported", L.H, B);
   const int HP = (L.H + 63) / 64 * 64, BP = rt_bp(B), nkc = HP / 64;

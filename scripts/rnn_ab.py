@@ -15,7 +15,7 @@ LAYERS = int(os.environ.get("LAYERS", "9"))
 BS = [int(b) for b in os.environ.get("BATCHES", "64,128,192").split(",")]
 NIFS = [int(b) for b in os.environ.get("NIFS", "1,2,3").split(",")]
 REPS = int(os.environ.get("REPS", "3"))
-KSPLITS = [int(b) for b in os.environ.get("KSPLITS", "0,1").split(",")]
+KSPLITS = [int(b) for b in os.environ.get("KSPLITS", "0,1").split(",")]   # 0 one CTA, 1 K-split pairs, 2 cta_group::2 pairs
 T = 1 + int(SECONDS * 16000) // 160
 BIDIR = os.environ.get("BIDIR", "1") == "1"
 H = int(os.environ.get("HIDDEN", "1200"))
@@ -28,10 +28,16 @@ for B in BS:
     lens = torch.IntTensor([T] * B)
     ref = None
     for nif, ks in [(n, k) for n in NIFS for k in KSPLITS]:
-        if (nif > 1 and B <= 64) or (nif == 1 and ks == 1 and B > 64):
+        if (nif > 1 and B <= 64) or (nif == 1 and ks == 1 and B > 64) or (ks == 2 and B <= 64):
             continue
-        N.tune(rnn_in_flight=max(nif, 2) if ks else nif, rnn_ksplit=ks, rnn_ring_gsz=int(os.environ.get("RING_GSZ", "0")),
-               rnn_producers=int(os.environ.get("PRODUCERS", "1")))
+        if ks == 2:     # cta_group::2 pairs: nif = PAIR ITEMS (two groups each) in flight
+            if B < 128 * nif and nif > 1 and B <= 128:
+                continue
+            N.tune(rnn_in_flight=3, rnn_ksplit=0, rnn_pair=1, rnn_pair_in_flight=nif,
+                   rnn_ring_gsz=int(os.environ.get("RING_GSZ", "0")))
+        else:
+            N.tune(rnn_in_flight=max(nif, 2) if ks else nif, rnn_ksplit=ks, rnn_pair=0,
+                   rnn_ring_gsz=int(os.environ.get("RING_GSZ", "0")), rnn_producers=int(os.environ.get("PRODUCERS", "1")))
         probs, _ = model(x, lens)
         torch.cuda.synchronize()
         L.dsb_profile_reset()
@@ -53,4 +59,4 @@ for B in BS:
                           "proj_ms_per_64": round(prof["rnn_input_proj"][0] / REPS * 64 / B, 3),
                           "conv_ms_per_64": round(prof["conv"][0] / REPS * 64 / B, 3),
                           "max_prob_diff_vs_first": diff}), flush=True)
-N.tune(rnn_in_flight=3, rnn_ksplit=1)
+N.tune(rnn_in_flight=3, rnn_ksplit=0, rnn_pair=1, rnn_pair_in_flight=2)

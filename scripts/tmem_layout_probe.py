@@ -27,7 +27,7 @@ def rng(a):
 
 L = ctypes.CDLL(_mb.build())
 torch.zeros(1).cuda()
-for cg, M, Nn in ((1, 64, 64), (1, 128, 64), (2, 128, 64), (2, 256, 64), (2, 128, 32)):
+for cg, M, Nn in ((1, 64, 64), (2, 128, 64), (2, 128, 128), (2, 256, 64)):
     buf = np.zeros((cg, 128, 128), np.float32)
     rc = L.dsb_debug_layout_probe(cg, M, Nn, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
     print("== cta_group::%d M=%d N=%d rc=%d" % (cg, M, Nn, rc))

@@ -582,11 +582,12 @@ def one_cta_set():
     N.tune(**prev)
 
 
-@pytest.fixture(params=[1, 0], ids=["ksplit", "one_cta"])
+@pytest.fixture(params=["pair", "ksplit", "one_cta"])
 def ksplit(request):
-    """Both persistent recurrence kernels: CTA pairs that split K (rnn_ks.cu, the default) and one CTA per W_hh slice."""
+    """The three persistent recurrence kernels: CTA pairs on cta_group::2 MMAs (rnn_pair.cu, the default for two or more
+    groups of 64 sequences), CTA pairs that split K (rnn_ks.cu) and one CTA per W_hh slice (rnn_tc.cu)."""
     from danspeech_b200 import _native as N
-    prev = N.tune(rnn_ksplit=request.param)
+    prev = N.tune(rnn_ksplit=int(request.param == "ksplit"), rnn_pair=int(request.param == "pair"))
     yield request.param
     N.tune(**prev)
 
