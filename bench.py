@@ -56,8 +56,8 @@ def parse_args():
     ap.add_argument("--no-beam", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the secondary workloads (streaming, sweep, fp32 mode, library bar)")
-    ap.add_argument("--merge", type=int, default=3,
-                    help="batches of 64 that share one pass of the model (1..3; 1 = one batch per pass)")
+    ap.add_argument("--merge", type=int, default=4,
+                    help="batches of 64 that share one pass of the model (1..4; 1 = one batch per pass)")
     return ap.parse_args()
 
 
@@ -409,7 +409,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     L = N.lib()
-    merge = max(1, min(3, args.merge))
+    merge = max(1, min(4, args.merge))
 
     model = build_model(MODEL, seed=0).set_precision(args.precision)
     rec = Recognizer(model=model, device=dev)
@@ -642,7 +642,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "precision_mode": args.precision, "utterances_per_gpu": BATCH,
                    "batches_in_flight": merge,
                    "step": "one batch of 64 x 15 s; up to %d consecutive batches share one pass of the model "
-                           "(the recurrence keeps their groups of 64 sequences in flight per CTA), K steps = %s passes"
+                           "(the CTA-pair recurrence multiplies two groups of 64 sequences per MMA, two such items in flight), K steps = %s passes"
                            % (merge, "+".join(str(m) for m in passes_for(args.steps, merge))),
                    "l2": "working set per step (weights >= 325 MB + activations > 1 GB) exceeds the 126 MB L2",
                    "sharding": "independent utterance batches per rank, no collective on the data path"},

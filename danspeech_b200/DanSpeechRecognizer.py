@@ -184,11 +184,12 @@ class DanSpeechRecognizer(object):
             results[i] = decoded_output[pos] if show_all else decoded_output[pos][0]
         return results
 
-    # Batches that transcribe_batches runs through ONE pass of the model: the persistent recurrence keeps up to three
-    # groups of 64 sequences in flight per CTA (csrc/rnn_tc.cu), so three batches of 64 cost far less than three passes.
-    batches_in_flight = 3
-    max_merged_rows = 192
-    max_merged_samples = 192 * 30 * 16000     # bound on rows x longest recording of a merged pass (workspace size)
+    # Batches that transcribe_batches runs through ONE pass of the model: the CTA-pair recurrence (csrc/rnn_pair.cu)
+    # multiplies two groups of 64 sequences per MMA and keeps two such items in flight per CTA pair, so four batches of
+    # 64 cost far less than four passes (the one-CTA kernel, csrc/rnn_tc.cu, takes a single batch).
+    batches_in_flight = 4
+    max_merged_rows = 256
+    max_merged_samples = 256 * 30 * 16000     # bound on rows x longest recording of a merged pass (workspace size)
 
     def _merge_plan(self, batches, merge):
         """Consecutive batches -> passes of at most `merge` batches within the row / sample budgets."""

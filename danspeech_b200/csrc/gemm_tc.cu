@@ -61,7 +61,9 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                : "memory");
 }
-// bias_row: the bias belongs to the ROWS of C (operands swapped: C^T = W * A^T, see gemm_bias_rows_tc)
+// bias_row: the bias belongs to the ROWS of C (operands swapped: C^T = W * A^T, see gemm_bias_rows_tc).  The kernels
+// then also walk the ROW blocks fastest: the rows are the weights (small, L2-resident), the columns the activations,
+// which should stream from HBM once and not once per row block.
 __device__ __forceinline__ void store_chunk16(const uint32_t (&r)[16], float* __restrict__ C, int64_t ldc, int row, int M,
                                               int N, int col, const float* __restrict__ bias, bool vec_ok, bool bias_row) {
   if (row >= M) return;
@@ -156,7 +158,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+      const int mb = bias_row ? tile % m_blocks : tile / n_blocks, nb = bias_row ? tile / m_blocks : tile % n_blocks;
+      const int m0 = mb * BM, n0 = nb * BN;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one_sync()) {
@@ -210,7 +213,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t acc_phase = 0;
     const bool vec_ok = (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0 && (BN & 7) == 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+      const int mb = bias_row ? tile % m_blocks : tile / n_blocks, nb = bias_row ? tile / m_blocks : tile % n_blocks;
+      const int m0 = mb * BM, n0 = nb * BN;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -299,7 +303,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-      const int m0 = (tile / n_blocks) * 2 * BM + rank * BM, n0 = (tile % n_blocks) * BN + rank * (BN / 2);
+      const int mb = bias_row ? tile % m_blocks : tile / n_blocks, nb = bias_row ? tile / m_blocks : tile % n_blocks;
+      const int m0 = mb * 2 * BM + rank * BM, n0 = nb * BN + rank * (BN / 2);
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait_trap(&empty[stage], phase ^ 1);
         if (elect_one_sync()) {
@@ -357,7 +362,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t acc_phase = 0;
     const bool vec_ok = (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0 && (BN & 7) == 0;
     for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-      const int m0 = (tile / n_blocks) * 2 * BM + rank * BM, n0 = (tile % n_blocks) * BN;
+      const int mb = bias_row ? tile % m_blocks : tile / n_blocks, nb = bias_row ? tile / m_blocks : tile % n_blocks;
+      const int m0 = mb * 2 * BM + rank * BM, n0 = nb * BN;
       mbar_wait_trap(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;

@@ -265,7 +265,6 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           if (go && s < Tg[i]) {
             named_bar_sync(2 + i, 256 + 32);
             long long q0 = clock64();
-            if (*(volatile int*)p.abort_flag) { go = false; break; }
             if (elect_one_sync()) {
               // h_t of the item: ONE TMA store of the staged [64][U2] box into the group's exchange buffer (rows the
               // sequences of which have ended carry their last state: every row only feeds its own accumulator row)
@@ -285,6 +284,7 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
               }
             }
             __syncwarp();
+            if (*(volatile int*)p.abort_flag) { go = false; break; }   // (after the publish: off the step's critical path)
             const long long q1 = clock64();
             d_pub += q1 - q0;
             if (p.dbg && i == 0 && s == 99 && lane == 0) p.dbg[blockIdx.x * 128 + 66] = q1;
@@ -361,11 +361,15 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     // No thread of the epilogue waits for another one: h_t goes from registers to the exchange buffer (bf16 pairs), the
     // thread ARRIVES on the item's named barrier and carries on with its y stores and the next pre-activations; the
     // publisher warp completes the barrier and pays for the release.
-    auto item = [&](int i, int s, int bg, int b, bool row_ok, int len, unsigned steps_before, float (&hp)[UH],
-                    float (&cs)[UH], float (&gxv)[GATES][UH]) -> bool {
+    auto item = [&](int i, int s, int steps, int bg, int b, bool row_ok, int len, unsigned steps_before,
+                    float (&hp)[UH], float (&cs)[UH], float (&gxv)[GATES][UH]) -> bool {
       long long e1 = clock64();
-      const bool active = row_ok && s < len;
-      const int t = dir == 0 ? s : len - 1 - s;
+      // Every sequence of the item is at the SAME time index in a step (the batch-minor loads / stores of a warp are then
+      // one line each however ragged the batch is): forwards t = s; backwards the item walks t = steps-1 .. 0 and a
+      // shorter sequence JOINS at t = len-1 with its initial state -- the same arithmetic per sequence as starting
+      // them together (pack_padded_sequence semantics, model.py:117-120), just at a later step.
+      const int t = dir == 0 ? s : steps - 1 - s;
+      const bool active = row_ok && t < len;
       const bool ok = wait_abortable(&dfull[i], (uint32_t)((steps_before + (unsigned)s) & 1u), p.abort_flag);
       long long e2 = clock64();
       if (p.dbg && s == 100 && i == 0 && et == 64) p.dbg[blockIdx.x * 128 + 65] = e2;
@@ -415,7 +419,10 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       }
       if (!ok) return false;
       // pre-activations of the group's next step: nobody waits on them before the group's next item
-      if (row_ok && s + 1 < len) load_gx(gxv, dir == 0 ? s + 1 : len - 2 - s, b);
+      {
+        const int tn = dir == 0 ? s + 1 : steps - 2 - s;
+        if (row_ok && s + 1 < steps && tn < len) load_gx(gxv, tn, b);
+      }
       long long e5 = clock64();
       // y_t (fp32) straight from registers: nobody waits on these stores
       if (ok && active && !(p.skip & 2)) {
@@ -472,13 +479,13 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 #pragma unroll
           for (int g = 0; g < GATES; ++g) gxr[i][g][u] = 0.f;
         }
-        if (rok[i] && ln[i] > 0) load_gx(gxr[i], dir == 0 ? 0 : ln[i] - 1, bb[i]);
+        if (rok[i] && Tg[i] > 0 && (dir == 0 ? 0 : Tg[i] - 1) < ln[i]) load_gx(gxr[i], dir == 0 ? 0 : Tg[i] - 1, bb[i]);
       }
       for (int s = 0; s < Tw && alive; ++s) {
 #pragma unroll
         for (int i = 0; i < NIF; ++i)
           if (alive && s < Tg[i])
-            alive = item(i, s, bgs[i], bb[i], rok[i], ln[i], before[i], hprev[i], cst[i], gxr[i]);
+            alive = item(i, s, Tg[i], bgs[i], bb[i], rok[i], ln[i], before[i], hprev[i], cst[i], gxr[i]);
       }
 #pragma unroll
       for (int i = 0; i < NIF; ++i) {

@@ -137,10 +137,25 @@ __device__ __forceinline__ void red_relaxed_gpu_add(unsigned* p, unsigned v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-// tanh.approx.f32 is only good to ~5e-4 absolute, which is visible after 9 recurrent layers; the
-// exp-based form below is accurate to ~1e-6 and still a handful of instructions.
-__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+// Gate non-linearities on the MUFU pipe: ex2.approx / rcp.approx with flush-to-zero, two MUFU operations each.
+// (__expf / __fdividef expand to the same MUFU instructions plus range handling for denormal results -- a compare, two
+// predicated multiplies and a squaring per call -- which a sigmoid / tanh does not need: 1 + denormal == 1.)
+// tanh.approx.f32 is only good to ~5e-4 absolute, which is visible after 9 recurrent layers; the exp-based form is
+// accurate to ~1e-6.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  return fmaf(-2.0f, rcp_ftz(ex2_ftz(2.8853900817779268f * x) + 1.0f), 1.0f);
+}
 
 // Steps of batch group bg: the lengths are sorted descending (forward() rejects anything else, like
 // pack_padded_sequence behind model.py:117), so the group's first row is its longest sequence.

@@ -161,6 +161,10 @@ def test_tuning_knobs_are_validated(lib):
     """dsb_tune_set / dsb_tune_get: known keys only, values inside their ranges, defaults = production settings."""
     assert lib.dsb_tune_get(b"rnn_in_flight") == 3 and lib.dsb_tune_get(b"rnn_ksplit") == 0
     assert lib.dsb_tune_get(b"rnn_max_slots") == 0 and lib.dsb_tune_get(b"rnn_producers") == 1
+    # the CTA-pair recurrence (rnn_pair.cu) with batch-minor pre-activations is the production path for >= 2 groups
+    assert lib.dsb_tune_get(b"rnn_pair") == 1 and lib.dsb_tune_get(b"rnn_batch_minor") == 1
+    assert lib.dsb_tune_get(b"rnn_pair_in_flight") == 2
+    assert lib.dsb_tune_set(b"rnn_pair_in_flight", 4) != 0 and b"outside" in lib.dsb_last_error()
     assert lib.dsb_tune_get(b"no_such_knob") == -1
     assert lib.dsb_tune_set(b"no_such_knob", 1) != 0 and b"unknown key" in lib.dsb_last_error()
     assert lib.dsb_tune_set(b"rnn_in_flight", 4) != 0 and b"outside" in lib.dsb_last_error()

@@ -475,8 +475,8 @@ def test_recognize_batches_merge_plan():
     assert d._merge_plan([short] * 7, 3) == [[0, 1, 2], [3, 4, 5], [6]]
     assert d._merge_plan([short] * 7, 1) == [[k] for k in range(7)]
     assert d._merge_plan([short] * 4, 2) == [[0, 1], [2, 3]]
-    assert d._merge_plan([[np.zeros(10)] * 100, [np.zeros(10)] * 100, [np.zeros(10)] * 20], 3) == [[0], [1, 2]]   # 192 rows
-    long = [np.zeros(40 * 16000)] * 64                       # 3 x 64 x 40 s exceeds the sample budget of a pass
+    assert d._merge_plan([[np.zeros(10)] * 140, [np.zeros(10)] * 140, [np.zeros(10)] * 20], 3) == [[0], [1, 2]]   # 256 rows
+    long = [np.zeros(50 * 16000)] * 64                       # 3 x 64 x 50 s exceeds the sample budget of a pass
     assert d._merge_plan([long] * 4, 3) == [[0, 1], [2, 3]]
     pinned = (torch.zeros(8, 100), [100] * 8)
     assert d._merge_plan([short, pinned, pinned, short], 3) == [[0], [1, 2], [3]]
