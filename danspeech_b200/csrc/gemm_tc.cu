@@ -471,6 +471,10 @@ int gemm_bias_rows_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* 
 extern "C" int dsb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* C,
                              int64_t ldc, int M, int N, int K, void* stream) {
   DSB_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, "dsb_gemm_bf16: bad argument");
+  static const bool rows = getenv("DSB_GEMM_ROWS") != nullptr;   // diagnostic: C is then [N, ldc] (the transposed product)
+  if (rows)
+    return dsb::gemm_bias_rows_tc(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W),
+                                  ldw, bias, C, ldc, M, N, K, (cudaStream_t)stream);
   return dsb::gemm_bias_tc(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W),
                            ldw, bias, C, ldc, M, N, K, (cudaStream_t)stream);
 }

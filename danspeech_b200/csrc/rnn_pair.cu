@@ -274,11 +274,11 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
               const long long q2 = clock64();
               bulk_wait_group0();
               const long long q3 = clock64();
-              // The bulk store has COMPLETED here: h_t sits in L2, the point of coherence of every reader (the other
-              // CTAs' TMA loads, after their ld.acquire + proxy fence).  A releasing red would add a MEMBAR.GPU that
-              // waits for every outstanding access of this SM -- the epilogue's y stores and pre-activation loads,
-              // 3 - 6 k cycles measured -- and orders nothing the exchange needs.
-              red_relaxed_gpu_add(ctr0 + (size_t)i * 2 * kRnnCounterStride, 1u);   // publish h_t of this group
+              // The bulk store has COMPLETED here (its writes are visible to this thread); the releasing red makes them
+              // visible to whoever acquires the counter.  A relaxed red is ~7 % faster per step -- no MEMBAR.GPU waiting
+              // for the SM's other outstanding accesses -- and WRONG: measured, readers on other SMs then now and again
+              // stream a stale row of h_t (results differ from run to run).
+              red_release_gpu_add(ctr0 + (size_t)i * 2 * kRnnCounterStride, 1u);   // publish h_t of this group
               if (p.dbg && i == 0 && s == 100) {
                 p.dbg[blockIdx.x * 128 + 120] = q0; p.dbg[blockIdx.x * 128 + 121] = q2; p.dbg[blockIdx.x * 128 + 122] = q3;
               }
@@ -523,7 +523,7 @@ done:
 // The pair kernel takes the layers the one-CTA kernel takes with 64-row slices, when a direction's CTA count is even
 // and there are at least two batch groups to pair.
 bool rnn_pair_supported(const RnnLayer& L, int B, int sms) {
-  if (!g_tune.rnn_pair.load() || rnn_tc_max_in_flight() < 2 || B <= 64) return false;
+  if (!g_tune.rnn_pair.load() || rnn_tc_max_in_flight() < 2 || B < g_tune.rnn_pair_min_rows.load()) return false;
   if (rnn_tc_narrow(L, B)) return false;
   const int U = tc::rt_units(L.gates, false), cpd = cdiv(L.H, U), HP = (L.H + 63) / 64 * 64;
   if (cpd & 1) return false;

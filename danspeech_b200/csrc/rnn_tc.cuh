@@ -133,10 +133,6 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ void red_relaxed_gpu_add(unsigned* p, unsigned v) {
-  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // Gate non-linearities on the MUFU pipe: ex2.approx / rcp.approx with flush-to-zero, two MUFU operations each.
 // (__expf / __fdividef expand to the same MUFU instructions plus range handling for denormal results -- a compare, two
 // predicated multiplies and a squaring per call -- which a sigmoid / tanh does not need: 1 + denormal == 1.)

@@ -745,3 +745,20 @@ def test_streaming_cpu_streaming_rnn_shape_matches_oracle(precision, tol):
                 worst = max(worst, logit_rel_err(o[s].cpu().numpy(), ref[0].numpy()))
     print("CPUStreamingRNN shape, %s: worst logit rel err vs oracle %.2e" % (precision, worst))
     assert worst < tol
+
+
+@pytest.mark.parametrize("B", [64, 192])
+def test_pair_recurrence_is_deterministic_at_the_headline_shape(B):
+    """The h exchange of the CTA-pair recurrence (TMA store -> releasing counter -> acquire -> TMA load on other SMs) leaves
+    no window for a reader to stream a stale row: repeated passes of the Primary-shaped model (9 x 1200 bi-GRU, T' = 751,
+    one group with an idle partner / three groups) are BIT-identical.  (A relaxed counter update passed every tolerance
+    test and failed this one.)"""
+    m = _model("DanSpeechPrimary", {}, seed=0, precision="bf16")
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((B, 1, 161, 1501), generator=gen, device="cuda")
+    lens = torch.IntTensor([1501] * B)
+    first, _ = m(x, lens)
+    first = first.clone()
+    for _ in range(3):
+        again, _ = m(x, lens)
+        assert torch.equal(again, first)
