@@ -111,7 +111,7 @@ def launch_count():
     return int(lib().dsb_kernel_launch_count())
 
 
-STAGES = ("spectrogram", "conv", "rnn_input_proj", "rnn_recurrence", "tail", "greedy", "beam")
+STAGES = ("spectrogram", "conv", "rnn_input_proj", "rnn_recurrence", "tail", "greedy", "beam", "rnn_combine")
 
 
 def profile_read():

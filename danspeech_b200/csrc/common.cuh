@@ -40,7 +40,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
   } while (0)
 
 // Stage timers (CUDA events on the launching stream), enabled by dsb_profile_enable().
-enum Stage { ST_SPECT = 0, ST_CONV, ST_PROJ, ST_RNN, ST_TAIL, ST_GREEDY, ST_BEAM, ST_COUNT };
+enum Stage { ST_SPECT = 0, ST_CONV, ST_PROJ, ST_RNN, ST_TAIL, ST_GREEDY, ST_BEAM, ST_COMBINE, ST_COUNT };
 void prof_begin(int stage, cudaStream_t st);
 void prof_end(int stage, cudaStream_t st);
 struct ProfScope {

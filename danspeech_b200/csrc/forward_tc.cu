@@ -242,6 +242,8 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
       if (int e = rnn_layer_tc(R, ws.gates, ws.d_len, B, Tp, Tmax, ws.ydir, ws.hbuf, ws.sync_words, m->d_abort, st,
                                nullptr, nullptr, nullptr, nullptr, bminor))
         return e;
+      prof_end(ST_RNN, st);
+      prof_begin(ST_COMBINE, st);
       if (bminor) {
         if (int e = combine_dirs_t_tc(ws.ydir, R.dirs, Tp, B, H, ws.d_len, last ? nullptr : ws.xb, next_ld,
                                       last ? ws.xf : nullptr, st))
@@ -250,6 +252,7 @@ int forward_tc(dsb_model* m, const float* spect, const int32_t* h_out_len, int B
                                          last ? ws.xf : nullptr, st)) {
         return e;
       }
+      prof_end(ST_COMBINE, st);   // (the prof_end(ST_RNN) below is then a no-op)
     } else {
       if (int e = rnn_layer_f32(m, R, ws.gates, ws.d_len, B, Tmax, Tp, ws.xf, ws.hstate, ws.cstate, st)) return e;
       if (!last) {

@@ -620,6 +620,14 @@ int rnn_layer_pair(const RnnLayer& L, const float* gx, const int32_t* d_len, int
     attrs[1].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 2;
+    // Profilers cannot replay a cooperative cluster launch (ncu: LaunchFailed).  DSB_RNN_NONCOOP=1 drops the cooperative
+    // attribute for a profiling run on an otherwise idle GPU, where the <= 148 single-CTA-per-SM blocks are co-resident
+    // anyway; production keeps it (it is what makes spinning on the other CTAs safe next to other work).
+    static const bool noncoop = getenv("DSB_RNN_NONCOOP") != nullptr;
+    if (noncoop) {
+      attrs[0] = attrs[1];
+      cfg.numAttrs = 1;
+    }
     const cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
     if (le != cudaSuccess)
       return set_error(DSB_ERR_CUDA, "rnn_layer_pair: launch failed: %s", cudaGetErrorString(le));

@@ -40,7 +40,8 @@ uint64_t dsb_kernel_launch_count(void);
 
 /* Stage timers: when enabled, the library brackets each stage of the path with CUDA events on the
  * caller's stream.  Stages: 0 spectrogram, 1 conv stack, 2 RNN input projections, 3 RNN recurrence,
- * 4 lookahead/fc/softmax, 5 greedy decode, 6 beam decode.  dsb_profile_read synchronises on the
+ * 4 lookahead/fc/softmax, 5 greedy decode, 6 beam decode, 7 direction sum + layout change between recurrent layers
+ * (bf16 mode).  dsb_profile_read synchronises on the
  * recorded events and returns the summed milliseconds and the number of spans since the last reset. */
 void dsb_profile_enable(int on);
 void dsb_profile_reset(void);
