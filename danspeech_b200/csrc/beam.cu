@@ -176,6 +176,14 @@ struct BeamParams {
   int32_t* a_info;           // ch | timestep << 8
   int32_t* a_wid;            // word id completed at this node (space nodes), else -1
   int max_nodes;
+  // node identity: (parent node, symbol) -> arena node, open addressing, [B][h_cap].  A prefix that fell out of the beam
+  // and comes back must be the SAME node (ctcdecode's PathTrie keeps removed nodes that still have descendants and
+  // revives them, path_trie.cpp get_path_trie): its live descendants keep pointing at it, so a later extension of the
+  // revived prefix merges into the live child instead of creating a second prefix with the same labels.
+  uint32_t* h_keys;
+  int32_t* h_vals;
+  uint32_t h_mask;
+  int h_shift;
   int32_t* words;            // [B][W][T+2] scratch for the sentence score
   int32_t* out_tokens;
   int32_t* out_ts;
@@ -203,6 +211,8 @@ beam_kernel(const BeamParams p) {
   int32_t* a_parent = p.a_parent + (size_t)b * p.max_nodes;
   int32_t* a_info = p.a_info + (size_t)b * p.max_nodes;
   int32_t* a_wid = p.a_wid + (size_t)b * p.max_nodes;
+  uint32_t* h_keys = p.h_keys + (size_t)b * (p.h_mask + 1);
+  int32_t* h_vals = p.h_vals + (size_t)b * (p.h_mask + 1);
 
   int cur = 0, n_active = 1;
   if (tid == 0) {
@@ -540,7 +550,27 @@ beam_kernel(const BeamParams p) {
       } else {                // new prefix: parent i extended by symbol c
         const int idx = code - BM_MAXW;
         const int i = divC(idx), c = idx - i * C;
-        const int id = atomicAdd(&sm.arena_count, 1);
+        // the node of (parent, symbol): the one created earlier if this prefix has been in the beam before, else new
+        int id = -1;
+        bool fresh = false;
+        {
+          const uint32_t hk = ((uint32_t)S.node[i] << 8) | (uint32_t)c;
+          uint32_t slot = (hk * 0x9E3779B1u) >> p.h_shift;
+          for (;;) {
+            const uint32_t k = *(volatile uint32_t*)&h_keys[slot];
+            if (k == hk) { id = h_vals[slot]; break; }
+            if (k == 0xFFFFFFFFu) {
+              const uint32_t old = atomicCAS(&h_keys[slot], 0xFFFFFFFFu, hk);   // (parent, symbol) pairs of a step are distinct
+              if (old == 0xFFFFFFFFu) {
+                id = atomicAdd(&sm.arena_count, 1);
+                h_vals[slot] = id;
+                fresh = true;
+                break;
+              }
+            }
+            slot = (slot + 1) & p.h_mask;
+          }
+        }
         const float v = cand[idx];
         const int wid = cand_aux[idx * 2 + 1];
         Nx.node[r] = id; Nx.parent[r] = S.node[i]; Nx.ch[r] = c; Nx.ts[r] = t; Nx.lpc[r] = sm.lp[c];
@@ -554,7 +584,7 @@ beam_kernel(const BeamParams p) {
         Nx.bprev[r] = BM_NEG; Nx.nbprev[r] = v; Nx.score[r] = v;
         Nx.lmok[r] = 0; Nx.rowok[r] = 0;
         sm.pidx[r] = -1;
-        if (id < p.max_nodes) {
+        if (fresh && id < p.max_nodes) {
           a_parent[id] = S.node[i];
           a_info[id] = (c & 0xFF) | (t << 8);
           a_wid[id] = (T.has_lm && !T.char_based && c == p.space) ? (wid < 0 ? 0 : wid) : -1;
@@ -820,8 +850,8 @@ extern "C" int64_t dsb_beam_lm_num_ngrams(const dsb_beam* d) { return d ? d->n_n
 
 namespace {
 struct BeamWs {
-  size_t o_len, o_parent, o_info, o_wid, o_words, total;
-  int max_nodes;
+  size_t o_len, o_parent, o_info, o_wid, o_words, o_hkeys, o_hvals, total;
+  int max_nodes, h_cap, h_log2;
 };
 BeamWs beam_ws(const dsb_beam* d, int B, int T) {
   BeamWs w{};
@@ -837,6 +867,11 @@ BeamWs beam_ws(const dsb_beam* d, int B, int T) {
   w.o_info = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
   w.o_wid = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
   w.o_words = take(sizeof(int32_t) * (size_t)B * d->W * (T + 2));
+  w.h_log2 = 10;
+  while ((1 << w.h_log2) < 2 * w.max_nodes) ++w.h_log2;
+  w.h_cap = 1 << w.h_log2;
+  w.o_hkeys = take(sizeof(uint32_t) * (size_t)B * w.h_cap);
+  w.o_hvals = take(sizeof(int32_t) * (size_t)B * w.h_cap);
   w.total = off;
   return w;
 }
@@ -872,6 +907,11 @@ extern "C" int dsb_beam_decode(dsb_beam* d, const float* probs, const int32_t* s
   p.a_info = reinterpret_cast<int32_t*>(base + w.o_info);
   p.a_wid = reinterpret_cast<int32_t*>(base + w.o_wid);
   p.max_nodes = w.max_nodes;
+  p.h_keys = reinterpret_cast<uint32_t*>(base + w.o_hkeys);
+  p.h_vals = reinterpret_cast<int32_t*>(base + w.o_hvals);
+  p.h_mask = (uint32_t)w.h_cap - 1u;
+  p.h_shift = 32 - w.h_log2;
+  DSB_CUDA(cudaMemsetAsync(p.h_keys, 0xFF, sizeof(uint32_t) * (size_t)B * w.h_cap, st));
   p.words = reinterpret_cast<int32_t*>(base + w.o_words);
   p.out_tokens = out_tokens;
   p.out_ts = out_timesteps;

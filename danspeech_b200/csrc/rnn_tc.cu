@@ -639,21 +639,48 @@ __global__ void __launch_bounds__(256) combine_dirs_t_kernel(const float* __rest
                                                              __nv_bfloat16* __restrict__ xb, int ldx,
                                                              float* __restrict__ xf) {
   __shared__ float tile[64][65];
+  __shared__ int live[64];
   const int64_t M = (int64_t)T * B;
   const int64_t m0 = (int64_t)blockIdx.x * 64;
   const int j0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
-  {
-    const int64_t m = m0 + tx;
-    bool live = false;
+  const int tid = threadIdx.x;
+  if (tid < 64) {
+    const int64_t m = m0 + tid;
+    int lv = 0;
     if (m < M) {
       const int b = (int)(m % B), t = (int)(m / B);
-      live = t < lens[b];
+      lv = t < lens[b];
     }
+    live[tid] = lv;
+  }
+  __syncthreads();
+  const int g = tid & 15, r = tid >> 4;   // 16 groups of four columns x 16 rows per pass
+  if ((M & 3) == 0) {
+    // 16-byte loads along the (t, b) axis: a quarter warp reads 256 contiguous bytes of one unit
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int jj = r + 16 * pass, j = j0 + jj;
+      const int64_t m = m0 + 4 * g;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < H && m < M) {
+        v = *reinterpret_cast<const float4*>(yt + (int64_t)j * M + m);
+        if (dirs == 2) {
+          const float4 w = *reinterpret_cast<const float4*>(yt + ((int64_t)H + j) * M + m);
+          v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+      }
+      tile[jj][4 * g + 0] = live[4 * g + 0] ? v.x : 0.f;
+      tile[jj][4 * g + 1] = live[4 * g + 1] ? v.y : 0.f;
+      tile[jj][4 * g + 2] = live[4 * g + 2] ? v.z : 0.f;
+      tile[jj][4 * g + 3] = live[4 * g + 3] ? v.w : 0.f;
+    }
+  } else {
+    const int tx = tid & 63, ty = tid >> 6;
     for (int jj = ty; jj < 64; jj += 4) {
       const int j = j0 + jj;
+      const int64_t m = m0 + tx;
       float v = 0.f;
-      if (live && j < H) {
+      if (live[tx] && j < H) {
         v = yt[(int64_t)j * M + m];
         if (dirs == 2) v += yt[((int64_t)H + j) * M + m];
       }
@@ -661,13 +688,31 @@ __global__ void __launch_bounds__(256) combine_dirs_t_kernel(const float* __rest
     }
   }
   __syncthreads();
-  for (int mm = ty; mm < 64; mm += 4) {
+  // rows of the output: four consecutive units per thread (8 bytes of bf16, 16 bytes of fp32)
+  const bool vec = (H & 3) == 0 && (ldx & 3) == 0;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int mm = r + 16 * pass;
     const int64_t m = m0 + mm;
-    const int j = j0 + tx;
-    if (m < M && j < H) {
-      const float v = tile[tx][mm];
-      if (xb) xb[m * ldx + j] = __float2bfloat16_rn(v);
-      if (xf) xf[m * H + j] = v;
+    const int j = j0 + 4 * g;
+    if (m >= M || j >= H) continue;
+    const float v0 = tile[4 * g + 0][mm], v1 = tile[4 * g + 1][mm], v2 = tile[4 * g + 2][mm], v3 = tile[4 * g + 3][mm];
+    if (vec) {     // H % 4 == 0: the four units are all inside H
+      if (xb) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(xb + m * ldx + j) = pk;
+      }
+      if (xf) *reinterpret_cast<float4*>(xf + m * H + j) = make_float4(v0, v1, v2, v3);
+    } else {
+      const float vv[4] = {v0, v1, v2, v3};
+      for (int e = 0; e < 4; ++e)
+        if (j + e < H) {
+          if (xb) xb[m * ldx + j + e] = __float2bfloat16_rn(vv[e]);
+          if (xf) xf[m * H + j + e] = vv[e];
+        }
     }
   }
 }

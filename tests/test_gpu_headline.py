@@ -34,6 +34,7 @@ FP32_TOL, BF16_TOL = 1e-4, 2e-2
 BF16_MIN_FRAME_AGREEMENT = 0.975     # fraction of the 8 x 751 frames whose argmax equals the oracle's
 BF16_MAX_CER = 0.10                  # character error rate of the greedy transcripts against the oracle's
 BF16_MAX_FLIPPED_MARGIN = 0.3        # no frame whose oracle top1-top2 log-prob margin exceeds this may flip
+TS_MIN_AGREEMENT = 0.7               # beam search: fraction of character time steps equal to the oracle's
 
 
 @pytest.fixture(scope="module")
@@ -138,21 +139,16 @@ def test_headline_beam64_lm_on_model_output_matches_oracle(headline, tmp_path):
             ts_all += int(n)
     print("beam-64 + LM on model output, T' = 751: top-1 identical on %d / %d utterances; relative score differences %s; "
           "character time steps equal at %d / %d positions" % (same, len(SAMPLE), ["%.1e" % r for r in rel], ts_same, ts_all))
-    # KNOWN GAP: on the output of this random-weight network -- near-uniform probabilities, a beam
-    # of 64 full of near-ties over 751 steps -- the two searches do not always keep the same prefixes: measured on the
-    # B200, 13 of 16 utterances (7 of these 8) end with the identical top beam; on the others the beams diverge at an
-    # early word and neither search is consistently the better one (GPU score lower on one, higher on two).  The
-    # oracle itself is unpinned here (ctcdecode is absent; SURVEY B notes nth_element non-determinism at the beam
-    # boundary).  north_star asks for 99.5 %; what is asserted is the measured rate, so that a regression shows.
-    assert same >= len(SAMPLE) - 2
-    # Scores (approximate CTC score of the hypothesis, ~580 here): the same hypothesis scores within 1e-3 relative in
-    # the median and 5e-3 at worst (the accumulated mass depends on which merges happened while the prefix was in the
-    # beam).
-    assert sorted(rel)[len(rel) // 2] <= 1.5e-3 and max(rel) <= 5e-3
+    # Top beam identical on every sampled utterance, scores equal to float rounding.  (Until the GPU search gave a prefix
+    # that re-enters the beam its OLD trie node back -- ctcdecode's PathTrie keeps removed nodes that still have live
+    # descendants -- duplicates of one prefix crept into the beam on this near-uniform output and only 13 of 16
+    # utterances agreed; with node identity all 64 hypotheses and their scores agree.)
+    assert same == len(SAMPLE)
+    assert max(rel) <= 1e-5
     # Character time steps (the decoder's second output; the engine drops them, DanSpeechRecognizer.py:224-231): a
     # PathTrie node keeps the frame of its best symbol probability, also across the steps during which its prefix is
-    # out of the beam; the GPU arena re-creates such a prefix with the frame of its re-entry.  Tokens are unaffected.
-    assert ts_same >= 0.6 * ts_all
+    # out of the beam; the GPU keeps that frame only while the prefix is live.  Tokens and scores are unaffected.
+    assert ts_same >= TS_MIN_AGREEMENT * ts_all
     # the public API on the whole batch (top beam only) agrees with the decoder object
     rec.update_decoder(lm=arpa, alpha=1.3, beta=0.2, beam_width=64)
     texts = rec.recognize_batch(headline["auds"])
