@@ -160,6 +160,7 @@ struct BeamSmem {
   int allowed[BM_MAXC];
   float selfb[BM_MAXW], selfnb[BM_MAXW], selfscore[BM_MAXW];
   int pidx[BM_MAXW];
+  int surv[BM_MAXW];   // live prefix k is in the next beam
   int count, arena_count;
   int wsum[BM_THREADS / 32];
   float lpb_raw;
@@ -175,6 +176,8 @@ struct BeamParams {
   int32_t* a_parent;
   int32_t* a_info;           // ch | timestep << 8
   int32_t* a_wid;            // word id completed at this node (space nodes), else -1
+  float* a_lpc;              // best symbol log-probability seen for this node (PathTrie::log_prob_c; its frame is in a_info)
+  int32_t* a_ref;            // 1 while the node is in the beam + number of its children that exist; 0 = removed from the trie
   int max_nodes;
   // node identity: (parent node, symbol) -> arena node, open addressing, [B][h_cap].  A prefix that fell out of the beam
   // and comes back must be the SAME node (ctcdecode's PathTrie keeps removed nodes that still have descendants and
@@ -211,6 +214,8 @@ beam_kernel(const BeamParams p) {
   int32_t* a_parent = p.a_parent + (size_t)b * p.max_nodes;
   int32_t* a_info = p.a_info + (size_t)b * p.max_nodes;
   int32_t* a_wid = p.a_wid + (size_t)b * p.max_nodes;
+  float* a_lpc = p.a_lpc + (size_t)b * p.max_nodes;
+  int32_t* a_ref = p.a_ref + (size_t)b * p.max_nodes;
   uint32_t* h_keys = p.h_keys + (size_t)b * (p.h_mask + 1);
   int32_t* h_vals = p.h_vals + (size_t)b * (p.h_mask + 1);
 
@@ -222,6 +227,7 @@ beam_kernel(const BeamParams p) {
     s.bprev[0] = 0.f; s.nbprev[0] = BM_NEG; s.score[0] = 0.f; s.lpc[0] = BM_NEG;
     s.lmok[0] = 0; s.rowok[0] = 0;
     a_parent[0] = -1; a_info[0] = 0xFF; a_wid[0] = -1;
+    a_lpc[0] = BM_NEG; a_ref[0] = 1 << 28;   // the root is never removed
     sm.arena_count = 1;
   }
   __syncthreads();
@@ -422,13 +428,39 @@ beam_kernel(const BeamParams p) {
             S.lpc[k] = lpc;
             S.ts[k] = t;
             a_info[S.node[k]] = (c & 0xFF) | (t << 8);
+            a_lpc[S.node[k]] = lpc;
           }
         }
       }
       sm.selfnb[k] = nb;
+      sm.surv[k] = 0;
       sm.selfscore[k] = lse2(sm.selfb[k], nb);
     }
     __syncthreads();
+    // ---- phase 3c: PathTrie::get_path_trie also refreshes (log_prob_c, timestep) of a child that EXISTS in the trie but
+    //      is not in the beam (removed, kept for its descendants), whether or not the extension survives this step ----
+#pragma unroll 1
+    for (int idx = tid; idx < n_active * C; idx += BM_THREADS) {
+      if (!(cand[idx] > BM_NEG)) continue;
+      const int i = divC(idx), c = idx - i * C;
+      const int par = S.node[i];
+      if (a_ref[par] <= 1) continue;                       // no child of this prefix exists
+      const uint32_t hk = ((uint32_t)par << 8) | (uint32_t)c;
+      uint32_t slot = (hk * 0x9E3779B1u) >> p.h_shift;
+      for (;;) {
+        const uint32_t k = h_keys[slot];
+        if (k == 0xFFFFFFFFu) break;
+        if (k == hk) {
+          const int id = h_vals[slot];
+          if (id < p.max_nodes && a_ref[id] > 0 && a_lpc[id] < sm.lp[c]) {
+            a_lpc[id] = sm.lp[c];
+            a_info[id] = (c & 0xFF) | (t << 8);
+          }
+          break;
+        }
+        slot = (slot + 1) & p.h_mask;
+      }
+    }
     lap(5);
     // ---- phase 4: compaction of the valid candidates + bitonic sort by prefix_compare ----
     {
@@ -547,6 +579,7 @@ beam_kernel(const BeamParams p) {
         Nx.lmsp[r] = S.lmsp[k]; Nx.lmwid[r] = S.lmwid[k]; Nx.lmns[r] = S.lmns[k]; Nx.lmok[r] = S.lmok[k];
         Nx.rowok[r] = 1;
         sm.pidx[r] = k;   // (pidx is free again here) source slot of the dictionary row, copied below by all threads
+        sm.surv[k] = 1;
       } else {                // new prefix: parent i extended by symbol c
         const int idx = code - BM_MAXW;
         const int i = divC(idx), c = idx - i * C;
@@ -558,7 +591,7 @@ beam_kernel(const BeamParams p) {
           uint32_t slot = (hk * 0x9E3779B1u) >> p.h_shift;
           for (;;) {
             const uint32_t k = *(volatile uint32_t*)&h_keys[slot];
-            if (k == hk) { id = h_vals[slot]; break; }
+            if (k == hk) { id = h_vals[slot]; break; }   // has been in the trie before
             if (k == 0xFFFFFFFFu) {
               const uint32_t old = atomicCAS(&h_keys[slot], 0xFFFFFFFFu, hk);   // (parent, symbol) pairs of a step are distinct
               if (old == 0xFFFFFFFFu) {
@@ -573,7 +606,22 @@ beam_kernel(const BeamParams p) {
         }
         const float v = cand[idx];
         const int wid = cand_aux[idx * 2 + 1];
-        Nx.node[r] = id; Nx.parent[r] = S.node[i]; Nx.ch[r] = c; Nx.ts[r] = t; Nx.lpc[r] = sm.lp[c];
+        // PathTrie lifetime: a removed node that still has descendants is REVIVED with the frame of its best symbol
+        // probability (refreshed in phase 3c); a node that was deleted (no descendants left) starts afresh
+        const bool revived = !fresh && id < p.max_nodes && a_ref[id] > 0;
+        if (id < p.max_nodes) {
+          if (revived) {
+            atomicAdd(&a_ref[id], 1);
+          } else {
+            a_ref[id] = 1;
+            a_lpc[id] = sm.lp[c];
+            a_info[id] = (c & 0xFF) | (t << 8);
+            atomicAdd(&a_ref[S.node[i]], 1);
+          }
+        }
+        Nx.node[r] = id; Nx.parent[r] = S.node[i]; Nx.ch[r] = c;
+        Nx.ts[r] = revived ? (a_info[id] >> 8) : t;
+        Nx.lpc[r] = revived ? a_lpc[id] : sm.lp[c];
         Nx.dstate[r] = cand_aux[idx * 2 + 0];
         const bool shift = T.has_lm && (T.char_based || c == p.space);
         for (int h = 0; h < BM_HIST; ++h) {
@@ -586,12 +634,22 @@ beam_kernel(const BeamParams p) {
         sm.pidx[r] = -1;
         if (fresh && id < p.max_nodes) {
           a_parent[id] = S.node[i];
-          a_info[id] = (c & 0xFF) | (t << 8);
           a_wid[id] = (T.has_lm && !T.char_based && c == p.space) ? (wid < 0 ? 0 : wid) : -1;
         }
       }
     }
     __syncthreads();
+    // prefixes that left the beam: PathTrie::remove() -- the node goes away unless it has children, and so do its
+    // ancestors that are neither in the beam nor have other children (reference counts: 1 for being live + children)
+#pragma unroll 1
+    for (int k = tid; k < n_active; k += BM_THREADS) {
+      if (sm.surv[k]) continue;
+      int n = S.node[k];
+      while (n > 0 && n < p.max_nodes) {
+        if (atomicSub(&a_ref[n], 1) != 1) break;
+        n = a_parent[n];
+      }
+    }
     if (word_lm) {
 #pragma unroll 1
       for (int idx = tid; idx < m * C; idx += BM_THREADS) {
@@ -850,7 +908,7 @@ extern "C" int64_t dsb_beam_lm_num_ngrams(const dsb_beam* d) { return d ? d->n_n
 
 namespace {
 struct BeamWs {
-  size_t o_len, o_parent, o_info, o_wid, o_words, o_hkeys, o_hvals, total;
+  size_t o_len, o_parent, o_info, o_wid, o_lpc, o_ref, o_words, o_hkeys, o_hvals, total;
   int max_nodes, h_cap, h_log2;
 };
 BeamWs beam_ws(const dsb_beam* d, int B, int T) {
@@ -866,6 +924,8 @@ BeamWs beam_ws(const dsb_beam* d, int B, int T) {
   w.o_parent = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
   w.o_info = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
   w.o_wid = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
+  w.o_lpc = take(sizeof(float) * (size_t)B * w.max_nodes);
+  w.o_ref = take(sizeof(int32_t) * (size_t)B * w.max_nodes);
   w.o_words = take(sizeof(int32_t) * (size_t)B * d->W * (T + 2));
   w.h_log2 = 10;
   while ((1 << w.h_log2) < 2 * w.max_nodes) ++w.h_log2;
@@ -906,6 +966,8 @@ extern "C" int dsb_beam_decode(dsb_beam* d, const float* probs, const int32_t* s
   p.a_parent = reinterpret_cast<int32_t*>(base + w.o_parent);
   p.a_info = reinterpret_cast<int32_t*>(base + w.o_info);
   p.a_wid = reinterpret_cast<int32_t*>(base + w.o_wid);
+  p.a_lpc = reinterpret_cast<float*>(base + w.o_lpc);
+  p.a_ref = reinterpret_cast<int32_t*>(base + w.o_ref);
   p.max_nodes = w.max_nodes;
   p.h_keys = reinterpret_cast<uint32_t*>(base + w.o_hkeys);
   p.h_vals = reinterpret_cast<int32_t*>(base + w.o_hvals);
