@@ -444,15 +444,16 @@ beam_kernel(const BeamParams p) {
       if (!(cand[idx] > BM_NEG)) continue;
       const int i = divC(idx), c = idx - i * C;
       const int par = S.node[i];
-      if (a_ref[par] <= 1) continue;                       // no child of this prefix exists
+      // (a_ref and h_keys change through atomics, which act on L2: read them past the L1)
+      if (__ldcg(&a_ref[par]) <= 1) continue;              // no child of this prefix exists
       const uint32_t hk = ((uint32_t)par << 8) | (uint32_t)c;
       uint32_t slot = (hk * 0x9E3779B1u) >> p.h_shift;
       for (;;) {
-        const uint32_t k = h_keys[slot];
+        const uint32_t k = __ldcg(&h_keys[slot]);
         if (k == 0xFFFFFFFFu) break;
         if (k == hk) {
-          const int id = h_vals[slot];
-          if (id < p.max_nodes && a_ref[id] > 0 && a_lpc[id] < sm.lp[c]) {
+          const int id = __ldcg(&h_vals[slot]);
+          if (id < p.max_nodes && __ldcg(&a_ref[id]) > 0 && a_lpc[id] < sm.lp[c]) {
             a_lpc[id] = sm.lp[c];
             a_info[id] = (c & 0xFF) | (t << 8);
           }
@@ -591,7 +592,7 @@ beam_kernel(const BeamParams p) {
           uint32_t slot = (hk * 0x9E3779B1u) >> p.h_shift;
           for (;;) {
             const uint32_t k = *(volatile uint32_t*)&h_keys[slot];
-            if (k == hk) { id = h_vals[slot]; break; }   // has been in the trie before
+            if (k == hk) { id = __ldcg(&h_vals[slot]); break; }   // has been in the trie before
             if (k == 0xFFFFFFFFu) {
               const uint32_t old = atomicCAS(&h_keys[slot], 0xFFFFFFFFu, hk);   // (parent, symbol) pairs of a step are distinct
               if (old == 0xFFFFFFFFu) {
@@ -608,7 +609,7 @@ beam_kernel(const BeamParams p) {
         const int wid = cand_aux[idx * 2 + 1];
         // PathTrie lifetime: a removed node that still has descendants is REVIVED with the frame of its best symbol
         // probability (refreshed in phase 3c); a node that was deleted (no descendants left) starts afresh
-        const bool revived = !fresh && id < p.max_nodes && a_ref[id] > 0;
+        const bool revived = !fresh && id < p.max_nodes && __ldcg(&a_ref[id]) > 0;
         if (id < p.max_nodes) {
           if (revived) {
             atomicAdd(&a_ref[id], 1);
