@@ -20,6 +20,18 @@
 // counter of ITS group's CTA set (the rank-r CTAs of all pairs of the direction).  An odd group count leaves the last
 // item's second half empty (rows inactive, its exchange buffer stays zero).
 //
+// Roles per CTA (352 threads): warp 0 TMA producer (h_{t-1} boxes of ITS group into the shared ring; both CTAs'
+// completions are counted on the leader's barriers); warp 1 MMA issuer (leader CTA only; tcgen05.commit multicast
+// frees the ring slot / signals the accumulator in both CTAs); warps 2-9 epilogue -- tcgen05.ld, gate math (ex2 / rcp
+// on the MUFU pipe, fp32 state in registers), h_t staged as bf16 pairs, bar.arrive, then the fp32 y stores and the
+// pre-activations of the group's next step into registers; no epilogue warp ever waits for another one -- and warp 10,
+// the publisher: completes the item's named barrier, stores the staged [64][2U] box into the exchange buffer with ONE
+// TMA store, waits for its completion and bumps the group's counter with red.release.gpu.
+// Layouts (batch_minor, the default inside forward_tc): pre-activations [dirs*G*H][T*B] and outputs [dirs][H][T*B], so
+// that a warp (32 consecutive sequences) touches one 128-byte line per column; the backward direction walks
+// t = steps-1 .. 0 for ALL sequences of an item (a shorter one joins at t = len-1 with its initial state), which keeps
+// that true for ragged batches.  Numbers and the measurements behind each choice: profiles/r02_ncu_pair_recurrence.md.
+//
 // Every wait is bounded: a stuck barrier sets the abort flag instead of hanging the GPU.
 #include "rnn_tc.cuh"
 #include <cstdlib>
