@@ -18,6 +18,11 @@
 // these tile shapes, scripts/mma_microbench.py).
 // Warp roles as in gemm_tc.cu: TMA producer / single-thread tcgen05.mma issuer / 4 epilogue warps, with the
 // accumulator double-buffered in TMEM so that the epilogue of a tile overlaps the next tile's MMAs.
+// PACK = 2 (the 32-channel blocks 1 and 2): a tile covers TWO neighbouring output frequency rows d0 = 2*dp, d0 + 1.
+// With N = 32 a tcgen05.mma costs ~53 cycles whatever little it computes (the small-MMA floor), so the 32-channel
+// blocks were bound by their instruction count.  Input row f = sd*d0 - pd + r feeds output row d0 through tap kh = r
+// and output row d0 + 1 through tap kh = r - sd: with the weights packed as [r][kw][W[kh=r] ; W[kh=r-sd]] (zero blocks
+// where a tap does not exist) ONE MMA of N = 64 (~59 cycles) does both, over KH + sd input rows instead of 2 * KH.
 // Algorithmic flops = 2*T'*Cout*Dout*Cin*kH*kW per utterance.
 #include "tc_common.cuh"
 #include "model_types.cuh"
@@ -45,7 +50,7 @@ struct ConvTcParams {
 
 // One ring slot = one "group": block 1: CV_G1 kh taps (A tiles + weight tiles); blocks 2/3: one kh = a block of
 // 128 + KW - 1 frames and the KW weight taps.
-template <int NOUT, int CIN>
+template <int NOUT, int CIN, int PACK>
 struct ConvSmem {
   static constexpr bool FIRST = CIN == 16;
   static constexpr int ROW = CIN * 2;
@@ -53,22 +58,24 @@ struct ConvSmem {
   static constexpr int A_ROWS = FIRST ? CV_BM : CV_BM + kConvKW - 1;             // frames per box
   static constexpr int A_SLOT = FIRST ? CV_G1 * A_TILE : (A_ROWS * ROW + 1023) / 1024 * 1024;
   static constexpr int A_TX = FIRST ? CV_G1 * A_TILE : A_ROWS * ROW;             // bytes one A box delivers
-  static constexpr int B_TILE = NOUT * ROW;
+  static constexpr int NP = NOUT * PACK;                                          // accumulator columns of a tile
+  static constexpr int B_TILE = NP * ROW;
   static constexpr int B_SLOT = (FIRST ? CV_G1 : kConvKW) * B_TILE;
   static_assert(A_TILE % 1024 == 0 && B_TILE % 1024 == 0, "tiles must keep the swizzle phase");
-  static constexpr int GROUPS = FIRST ? 4 : (NOUT <= 32 ? 4 : 2);                // ring depth
+  static constexpr int GROUPS = FIRST ? 4 : (NP <= 64 ? 4 : 2);                  // ring depth
   static constexpr int BAR_OFF = GROUPS * (A_SLOT + B_SLOT);
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
-template <int NOUT, int CIN>
+template <int NOUT, int CIN, int PACK>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvTcParams p) {
-  using S = ConvSmem<NOUT, CIN>;
+  using S = ConvSmem<NOUT, CIN, PACK>;
   constexpr bool FIRST = S::FIRST;
-  constexpr int TMEM_COLS = NOUT <= 32 ? 64 : 256;
-  constexpr int ACC_STRIDE = NOUT <= 32 ? 32 : 128;
+  constexpr int NP = S::NP;
+  constexpr int TMEM_COLS = NP <= 32 ? 64 : 256;
+  constexpr int ACC_STRIDE = NP <= 32 ? 32 : 128;
   constexpr uint32_t SWZ = CIN == 32 ? 4u : 6u;          // SWIZZLE_64B : SWIZZLE_32B
   constexpr uint32_t SBO = 8 * S::ROW;
   extern __shared__ unsigned char smem_dyn[];
@@ -83,7 +90,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t_blocks = (p.Tp + CV_BM - 1) / CV_BM;
-  const int n_tiles = p.B * p.Dout * t_blocks;
+  const int DoutP = (p.Dout + PACK - 1) / PACK;   // tiles along the output frequency axis
+  const int KHP = p.KH + (PACK - 1) * p.sd;       // input rows per tile
+  const int n_tiles = p.B * DoutP * t_blocks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
@@ -104,18 +113,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  // tile -> (b, d, t0); frames fastest so that neighbouring CTAs share input rows in L2
+  // tile -> (b, d = first output row of the tile, t0); frames fastest so that neighbouring CTAs share input rows in L2
   auto decode = [&](int tile, int& b, int& d, int& t0) {
     const int tb = tile % t_blocks;
     const int r = tile / t_blocks;
-    d = r % p.Dout;
-    b = r / p.Dout;
+    d = (r % DoutP) * PACK;
+    b = r / DoutP;
     t0 = tb * CV_BM;
   };
-  // kh taps that fall inside the input rows for output row d; number of ring slots ("groups") the tile uses
+  // input rows r (of KHP) that fall inside the input for the tile starting at output row d -- rows that would only
+  // feed an output row past Dout are left out too; number of ring slots ("groups") the tile uses
   auto tile_shape = [&](int d, int& kh_lo, int& n_kh, int& n_grp) {
     kh_lo = max(0, p.pd - p.sd * d);
-    n_kh = min(p.KH - 1, p.Din - 1 + p.pd - p.sd * d) - kh_lo + 1;
+    const int r_max = (d + PACK - 1 < p.Dout) ? KHP - 1 : p.KH - 1 + (p.Dout - 1 - d) * p.sd;
+    n_kh = min(r_max, p.Din - 1 + p.pd - p.sd * d) - kh_lo + 1;
     n_grp = FIRST ? (n_kh + CV_G1 - 1) / CV_G1 : n_kh;
   };
 
@@ -151,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(CV_BM, NOUT);
+    constexpr uint32_t idesc = make_idesc_bf16(CV_BM, NP);
     const uint64_t desc0 = make_smem_desc(0, 16, SBO, SWZ);
     const uint32_t a_lo = smem_u32(sA) >> 4, b_lo = smem_u32(sB) >> 4;
     int grp = 0;
@@ -221,17 +232,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         nb = p.nb;
       }
       const bool live = valid && (p.lens == nullptr || t < p.lens[b]);
-      __nv_bfloat16* dst = nullptr;
-      if (valid)
-        dst = p.rnn_layout ? p.out + ((int64_t)t * nb + b) * p.out_ld + (int64_t)d * NOUT
-                           : p.out + (((int64_t)b * p.Dout + d) * p.Tp + t) * NOUT;
       const uint32_t t_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-      for (int c0 = 0; c0 < NOUT; c0 += 32) {
+      for (int c0 = 0; c0 < NP; c0 += 32) {
+        const int dd = d + c0 / NOUT, cc = c0 % NOUT;   // output row and first channel of these 32 accumulator columns
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && dd < p.Dout) {
+          __nv_bfloat16* dst = p.rnn_layout ? p.out + ((int64_t)t * nb + b) * p.out_ld + (int64_t)dd * NOUT
+                                            : p.out + (((int64_t)b * p.Dout + dd) * p.Tp + t) * NOUT;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint32_t w[4];
@@ -239,13 +249,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             for (int h = 0; h < 4; ++h) {
               float v0 = 0.f, v1 = 0.f;
               if (live) {
-                v0 = fminf(fmaxf(__uint_as_float(r[j + 2 * h]) + __ldg(p.bias + c0 + j + 2 * h), 0.f), 20.f);
-                v1 = fminf(fmaxf(__uint_as_float(r[j + 2 * h + 1]) + __ldg(p.bias + c0 + j + 2 * h + 1), 0.f), 20.f);
+                v0 = fminf(fmaxf(__uint_as_float(r[j + 2 * h]) + __ldg(p.bias + cc + j + 2 * h), 0.f), 20.f);
+                v1 = fminf(fmaxf(__uint_as_float(r[j + 2 * h + 1]) + __ldg(p.bias + cc + j + 2 * h + 1), 0.f), 20.f);
               }
               __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
               w[h] = *reinterpret_cast<uint32_t*>(&pk);
             }
-            *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(dst + cc + j) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }
@@ -293,27 +303,32 @@ __global__ void im2col_time_kernel(const float* __restrict__ spect, __nv_bfloat1
   }
 }
 
-// folded fp32 weights [kh][cin][11][cout] -> bf16 [(kh*KW + kw)][cout][cin_pad]
+// folded fp32 weights [kh][cin][11][cout] -> bf16 [(r*KW + kw)][pack*cout][cin_pad]: block q of the rows holds tap
+// kh = r - q*sd (zeros where that tap does not exist), r < KH + (pack-1)*sd; pack = 1: plain [(kh*KW + kw)][cout][cin_pad]
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int KH, int cin,
-                                   int cout, int first) {
+                                   int cout, int first, int pack, int sd) {
   const int KW = first ? 1 : kConvKW, CP = first ? 16 : cin;
-  const int64_t total = (int64_t)KH * KW * cout * CP;
+  const int KHP = KH + (pack - 1) * sd, NP = pack * cout;
+  const int64_t total = (int64_t)KHP * KW * NP * CP;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % CP);
     int64_t r = i / CP;
-    const int co = (int)(r % cout);
-    r /= cout;
-    const int kw = (int)(r % KW), kh = (int)(r / KW);
-    float v;
-    if (first) v = ci < kConvKW ? w[(((int64_t)kh * cin + 0) * kConvKW + ci) * cout + co] : 0.f;
-    else v = w[(((int64_t)kh * cin + ci) * kConvKW + kw) * cout + co];
+    const int n = (int)(r % NP);
+    r /= NP;
+    const int kw = (int)(r % KW), rr = (int)(r / KW);
+    const int qq = n / cout, co = n % cout, kh = rr - qq * sd;
+    float v = 0.f;
+    if (kh >= 0 && kh < KH) {
+      if (first) v = ci < kConvKW ? w[(((int64_t)kh * cin + 0) * kConvKW + ci) * cout + co] : 0.f;
+      else v = w[(((int64_t)kh * cin + ci) * kConvKW + kw) * cout + co];
+    }
     out[i] = __float2bfloat16_rn(v);
   }
 }
 
-template <int NOUT, int CIN>
+template <int NOUT, int CIN, int PACK>
 static int launch_conv(const __nv_bfloat16* x, const ConvLayer& L, const ConvTcParams& p, cudaStream_t st) {
-  using S = ConvSmem<NOUT, CIN>;
+  using S = ConvSmem<NOUT, CIN, PACK>;
   CUtensorMap tx, tw;
   const CUtensorMapSwizzle swz = CIN == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   const uint64_t frame = (uint64_t)CIN * 2;
@@ -323,18 +338,19 @@ static int launch_conv(const __nv_bfloat16* x, const ConvLayer& L, const ConvTcP
     uint32_t bx[4] = {CIN, (uint32_t)S::A_ROWS, 1, 1};
     if (int e = make_tmap_bf16(&tx, x, 4, dx, sx, bx, swz)) return e;
   }
-  // weights [(kh*KW + kw)][NOUT][CIN]; taps past the last one are out-of-bounds zero fill
-  uint64_t dw[3] = {(uint64_t)CIN, (uint64_t)NOUT, (uint64_t)p.KH * p.KW};
-  uint64_t sw[3] = {2, frame, (uint64_t)NOUT * frame};
-  uint32_t bw[3] = {CIN, NOUT, S::FIRST ? (uint32_t)CV_G1 : (uint32_t)kConvKW};
+  // weights [(r*KW + kw)][NOUT*PACK][CIN]; rows past the last one are out-of-bounds zero fill
+  const int KHP = p.KH + (PACK - 1) * p.sd;
+  uint64_t dw[3] = {(uint64_t)CIN, (uint64_t)S::NP, (uint64_t)KHP * p.KW};
+  uint64_t sw[3] = {2, frame, (uint64_t)S::NP * frame};
+  uint32_t bw[3] = {CIN, (uint32_t)S::NP, S::FIRST ? (uint32_t)CV_G1 : (uint32_t)kConvKW};
   if (int e = make_tmap_bf16(&tw, L.w_tc, 3, dw, sw, bw, swz)) return e;
   // per device (and a cheap host-side call): set on every launch, not once per process
-  DSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NOUT, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  DSB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NOUT, CIN, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles = p.B * p.Dout * cdiv(p.Tp, CV_BM);
-  conv_tc_kernel<NOUT, CIN><<<tiles < sms ? tiles : sms, CV_THREADS, S::TOTAL, st>>>(S::FIRST ? tw : tx, tw, p);
+  const int tiles = p.B * cdiv(p.Dout, PACK) * cdiv(p.Tp, CV_BM);
+  conv_tc_kernel<NOUT, CIN, PACK><<<tiles < sms ? tiles : sms, CV_THREADS, S::TOTAL, st>>>(S::FIRST ? tw : tx, tw, p);
   DSB_CHECK_LAUNCH();
   return 0;
 }
@@ -352,10 +368,19 @@ int im2col_time_tc(const float* spect, __nv_bfloat16* x1, int B, int T, int Tp, 
   return 0;
 }
 
+// output rows per tile (see the header): block 1 (Cin = 1, bound by re-reading its expanded input rows from L2) four,
+// the other 32-channel block two, the 96-channel block one
+static int conv_pack(const ConvLayer& L, bool first) { return L.cout == 32 ? (first ? 4 : 2) : 1; }
+
+size_t conv_w_tc_elems(const ConvLayer& L, bool first) {
+  const int pack = conv_pack(L, first);
+  return (size_t)(L.kh + (pack - 1) * L.sd) * (first ? 1 : kConvKW) * pack * L.cout * (first ? 16 : L.cin);
+}
+
 int pack_conv_w_tc(const ConvLayer& L, bool first, __nv_bfloat16* out, cudaStream_t st) {
-  const int64_t total = (int64_t)L.kh * (first ? 1 : kConvKW) * L.cout * (first ? 16 : L.cin);
+  const int64_t total = (int64_t)conv_w_tc_elems(L, first);
   tc::pack_conv_w_kernel<<<(int)(cdiv64(total, 256) < 2048 ? cdiv64(total, 256) : 2048), 256, 0, st>>>(
-      L.w, out, L.kh, L.cin, L.cout, first ? 1 : 0);
+      L.w, out, L.kh, L.cin, L.cout, first ? 1 : 0, conv_pack(L, first), L.sd);
   DSB_CHECK_LAUNCH();
   return 0;
 }
@@ -379,9 +404,9 @@ int conv_block_tc(const __nv_bfloat16* x, const ConvLayer& L, bool first, const 
   p.pt = first ? 0 : kConvPT;
   p.rnn_layout = rnn_layout ? 1 : 0;
   p.out_ld = out_ld;
-  if (first && L.cout == 32) return tc::launch_conv<32, 16>(x, L, p, st);
-  if (!first && L.cin == 32 && L.cout == 32) return tc::launch_conv<32, 32>(x, L, p, st);
-  if (!first && L.cin == 32 && L.cout == 96) return tc::launch_conv<96, 32>(x, L, p, st);
+  if (first && L.cout == 32) return tc::launch_conv<32, 16, 4>(x, L, p, st);
+  if (!first && L.cin == 32 && L.cout == 32) return tc::launch_conv<32, 32, 2>(x, L, p, st);
+  if (!first && L.cin == 32 && L.cout == 96) return tc::launch_conv<96, 32, 1>(x, L, p, st);
   return set_error(DSB_ERR_UNSUPPORTED, "conv_block_tc: unsupported block (cin=%d, cout=%d)", L.cin, L.cout);
 }
 

@@ -70,8 +70,7 @@ int finalize_tc(dsb_model* m, cudaStream_t st) {
   for (size_t i = 0; i < m->convs.size(); ++i) {
     ConvLayer& L = m->convs[i];
     const bool first = i == 0;
-    const int64_t n = (int64_t)L.kh * (first ? 1 : kConvKW) * L.cout * (first ? 16 : L.cin);
-    if (int e = dev_alloc_tc(m, &L.w_tc, n)) return e;
+    if (int e = dev_alloc_tc(m, &L.w_tc, (int64_t)conv_w_tc_elems(L, first))) return e;
     if (int e = pack_conv_w_tc(L, first, L.w_tc, st)) return e;
   }
   bool first_rnn = true;

@@ -17,7 +17,7 @@ struct ConvLayer {
   float* w = nullptr;      // BN-folded weights [cout][cin][kh][11] fp32
   float* bias = nullptr;   // BN-folded bias [cout]
   // bf16 tensor-core path
-  __nv_bfloat16* w_tc = nullptr;   // [kh][kw][cout][cin_pad] (conv2/3) or [kh][cout][16] (conv1, kw padded to 16)
+  __nv_bfloat16* w_tc = nullptr;   // [r][kw][pack*cout][cin_pad] (conv2/3) or [r][pack*cout][16] (conv1, kw padded to 16), conv_tc.cu
 };
 
 struct RnnLayer {
@@ -82,6 +82,7 @@ int gemm_bias_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
                  float* C, int64_t ldc, int M, int N, int K, cudaStream_t st);
 size_t conv1_tiles_elems(int B, int Tp);   // bf16 elements of the block-1 operand tiles
 int im2col_time_tc(const float* spect, __nv_bfloat16* x1, int B, int T, int Tp, cudaStream_t st);
+size_t conv_w_tc_elems(const ConvLayer& L, bool first);   // bf16 elements of the packed weights
 int pack_conv_w_tc(const ConvLayer& L, bool first, __nv_bfloat16* out, cudaStream_t st);
 int conv_block_tc(const __nv_bfloat16* x, const ConvLayer& L, bool first, const int32_t* d_len, int B, int Tp,
                   __nv_bfloat16* out, bool rnn_layout, int64_t out_ld, cudaStream_t st, const int* seg = nullptr);
