@@ -582,12 +582,14 @@ def one_cta_set():
     N.tune(**prev)
 
 
-@pytest.fixture(params=["pair", "ksplit", "one_cta"])
+@pytest.fixture(params=["pair", "pair_rowmajor", "ksplit", "one_cta"])
 def ksplit(request):
-    """The three persistent recurrence kernels: CTA pairs on cta_group::2 MMAs (rnn_pair.cu, the default for two or more
-    groups of 64 sequences), CTA pairs that split K (rnn_ks.cu) and one CTA per W_hh slice (rnn_tc.cu)."""
+    """The persistent recurrence kernels: CTA pairs on cta_group::2 MMAs (rnn_pair.cu, the default) with batch-minor
+    pre-activations / outputs or with the row-major layouts of the other kernels, CTA pairs that split K (rnn_ks.cu)
+    and one CTA per W_hh slice (rnn_tc.cu)."""
     from danspeech_b200 import _native as N
-    prev = N.tune(rnn_ksplit=int(request.param == "ksplit"), rnn_pair=int(request.param == "pair"))
+    prev = N.tune(rnn_ksplit=int(request.param == "ksplit"), rnn_pair=int(request.param.startswith("pair")),
+                  rnn_batch_minor=int(request.param != "pair_rowmajor"))
     yield request.param
     N.tune(**prev)
 
