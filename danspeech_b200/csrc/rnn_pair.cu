@@ -34,7 +34,9 @@
 //
 // Every wait is bounded: a stuck barrier sets the abort flag instead of hanging the GPU.
 #include "rnn_tc.cuh"
+#include <algorithm>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 namespace dsb {
@@ -45,6 +47,10 @@ constexpr int RP_PUB_WARP = 10;
 constexpr int RP_HS = 32;              // accumulator columns per epilogue thread
 constexpr int RP_N = 64;               // W_hh rows per CTA = half of the pair's N
 constexpr int RP_W_BYTES = RP_N * RT_BK * 2;
+constexpr int RP_DBG = 256;            // debug words per CTA: 128 counters + an event trace of steps 100 / 101
+// event slot of (item in flight i, step s in {100, 101}, event e < 20)
+#define RP_EV(i, s, e) (blockIdx.x * RP_DBG + 128 + ((i) * 2 + ((s) - 100)) * 20 + (e))
+#define RP_TRACE(i, s) (p.dbg && ((s) == 100 || (s) == 101) && (i) < 3)
 
 template <int GATES, int NIF>
 __global__ void __launch_bounds__(RP_THREADS, 1)
@@ -144,7 +150,8 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         d_fence += clock64() - c1;
       }
       long long c2 = clock64();
-      if (p.dbg && s == 100 && i == 0 && lane == 0) p.dbg[blockIdx.x * 128 + 15] = c2;
+      if (p.dbg && s == 100 && i == 0 && lane == 0) p.dbg[blockIdx.x * RP_DBG + 15] = c2;
+      if (RP_TRACE(i, s) && lane == 0) { p.dbg[RP_EV(i, s, 0)] = c0; p.dbg[RP_EV(i, s, 1)] = c2; }
       const int row0 = ((bg * 2 + (s & 1)) * p.dirs + dir) * 64;
       for (int g = 0; g < gps; ++g) {
         long long w0 = clock64();
@@ -158,7 +165,8 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                            gg * gsz);
         }
         __syncwarp();
-        if (p.dbg && s == 100 && i == 0 && g < 8 && lane == 0) p.dbg[blockIdx.x * 128 + 16 + g] = clock64();
+        if (p.dbg && s == 100 && i == 0 && g < 8 && lane == 0) p.dbg[blockIdx.x * RP_DBG + 16 + g] = clock64();
+        if (RP_TRACE(i, s) && g < 5 && lane == 0) p.dbg[RP_EV(i, s, 2 + g)] = clock64();
         if (++cur_slot == n_groups) { cur_slot = 0; cur_phase ^= 1; }
       }
       d_issue += clock64() - c2;
@@ -184,10 +192,10 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       for (int i = 0; i < NIF; ++i) before[i] += (unsigned)Tg[i];
     }
     if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 128 + 0] = d_spin;
-      p.dbg[blockIdx.x * 128 + 1] = d_fence;
-      p.dbg[blockIdx.x * 128 + 2] = d_issue;
-      p.dbg[blockIdx.x * 128 + 11] = d_empty;
+      p.dbg[blockIdx.x * RP_DBG + 0] = d_spin;
+      p.dbg[blockIdx.x * RP_DBG + 1] = d_fence;
+      p.dbg[blockIdx.x * RP_DBG + 2] = d_issue;
+      p.dbg[blockIdx.x * RP_DBG + 11] = d_empty;
     }
   } else if (warp == 1) {
     // ---- MMA issuer (leader CTA only): one tcgen05.mma.cta_group::2 per K = 16 slice drives both SMs ----
@@ -212,7 +220,8 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           else d_waitn += clock64() - w0;
           tc_fence_after();
           if (elect_one_sync()) {
-            if (p.dbg && s == 100 && i == 0 && g < 8) p.dbg[blockIdx.x * 128 + 40 + g] = clock64();
+            if (p.dbg && s == 100 && i == 0 && g < 8) p.dbg[blockIdx.x * RP_DBG + 40 + g] = clock64();
+            if (RP_TRACE(i, s) && g < 5) p.dbg[RP_EV(i, s, 7 + g)] = clock64();
             const uint32_t a0 = a_lo + (uint32_t)(grp * gsz) * stage16;
             const uint32_t b0 = w_lo + (uint32_t)i0 * (RP_W_BYTES >> 4);
             const int nch = i1 - i0;
@@ -233,7 +242,8 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           __syncwarp();
           if (++grp == n_groups) { grp = 0; fphase ^= 1; }
         }
-        if (p.dbg && s == 100 && i == 0 && lane == 0) p.dbg[blockIdx.x * 128 + 64] = clock64();
+        if (p.dbg && s == 100 && i == 0 && lane == 0) p.dbg[blockIdx.x * RP_DBG + 64] = clock64();
+        if (RP_TRACE(i, s) && lane == 0) p.dbg[RP_EV(i, s, 12)] = clock64();
         d_rest += clock64() - m0;
         return true;
       };
@@ -252,9 +262,9 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         }
       }
       if (p.dbg && lane == 0) {
-        p.dbg[blockIdx.x * 128 + 3] = d_wait0;
-        p.dbg[blockIdx.x * 128 + 4] = d_rest;
-        p.dbg[blockIdx.x * 128 + 10] = d_waitn;
+        p.dbg[blockIdx.x * RP_DBG + 3] = d_wait0;
+        p.dbg[blockIdx.x * RP_DBG + 4] = d_rest;
+        p.dbg[blockIdx.x * RP_DBG + 10] = d_waitn;
       }
     }
   } else if (warp == RP_PUB_WARP) {
@@ -292,20 +302,21 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
               // stream a stale row of h_t (results differ from run to run).
               red_release_gpu_add(ctr0 + (size_t)i * 2 * kRnnCounterStride, 1u);   // publish h_t of this group
               if (p.dbg && i == 0 && s == 100) {
-                p.dbg[blockIdx.x * 128 + 120] = q0; p.dbg[blockIdx.x * 128 + 121] = q2; p.dbg[blockIdx.x * 128 + 122] = q3;
+                p.dbg[blockIdx.x * RP_DBG + 120] = q0; p.dbg[blockIdx.x * RP_DBG + 121] = q2; p.dbg[blockIdx.x * RP_DBG + 122] = q3;
               }
             }
             __syncwarp();
             if (*(volatile int*)p.abort_flag) { go = false; break; }   // (after the publish: off the step's critical path)
             const long long q1 = clock64();
             d_pub += q1 - q0;
-            if (p.dbg && i == 0 && s == 99 && lane == 0) p.dbg[blockIdx.x * 128 + 66] = q1;
-            if (p.dbg && i == 0 && s == 100 && lane == 0) p.dbg[blockIdx.x * 128 + 67] = q1;
+            if (RP_TRACE(i, s) && lane == 0) { p.dbg[RP_EV(i, s, 15)] = q0; p.dbg[RP_EV(i, s, 16)] = q1; }
+            if (p.dbg && i == 0 && s == 99 && lane == 0) p.dbg[blockIdx.x * RP_DBG + 66] = q1;
+            if (p.dbg && i == 0 && s == 100 && lane == 0) p.dbg[blockIdx.x * RP_DBG + 67] = q1;
           }
         }
       }
     }
-    if (p.dbg && lane == 0) p.dbg[blockIdx.x * 128 + 12] = d_pub;
+    if (p.dbg && lane == 0) p.dbg[blockIdx.x * RP_DBG + 12] = d_pub;
   } else {
     // ---- epilogue: 8 warps.  TMEM lane quarter q = warp % 4: sequences (q & 1) * 32 + lane of this CTA's group, gate
     //      columns of CTA (q >> 1) of the pair; the two warps of a quarter split those 64 columns.
@@ -384,7 +395,8 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       const bool active = row_ok && t < len;
       const bool ok = wait_abortable(&dfull[i], (uint32_t)((steps_before + (unsigned)s) & 1u), p.abort_flag);
       long long e2 = clock64();
-      if (p.dbg && s == 100 && i == 0 && et == 64) p.dbg[blockIdx.x * 128 + 65] = e2;
+      if (p.dbg && s == 100 && i == 0 && et == 64) p.dbg[blockIdx.x * RP_DBG + 65] = e2;
+      if (RP_TRACE(i, s) && et == 64) { p.dbg[RP_EV(i, s, 13)] = e2; p.dbg[RP_EV(i, s, 17)] = e1; }
       tc_fence_after();
       uint32_t r[32];
       tmem_ld32(t_addr + (uint32_t)(i * 64), r);
@@ -425,8 +437,9 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       }
       long long e4 = clock64();
       asm volatile("bar.arrive %0, %1;" ::"r"(2 + i), "r"(256 + 32) : "memory");   // -> publisher (also on abort)
+      if (RP_TRACE(i, s) && et == 64) p.dbg[RP_EV(i, s, 14)] = e4;
       if (p.dbg && s == 100 && i == 0 && lane == 0) {
-        unsigned long long* d = p.dbg + blockIdx.x * 128 + 72 + (warp - 2) * 6;
+        unsigned long long* d = p.dbg + blockIdx.x * RP_DBG + 72 + (warp - 2) * 6;
         d[0] = e1; d[1] = e2; d[2] = e3; d[3] = e4; d[4] = 0; d[5] = 0;
       }
       if (!ok) return false;
@@ -513,11 +526,11 @@ rnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       }
     }
     if (p.dbg && et == 64) {   // warp 4: quarter 0, an active row
-      p.dbg[blockIdx.x * 128 + 5] = e_load;
-      p.dbg[blockIdx.x * 128 + 6] = e_wait;
-      p.dbg[blockIdx.x * 128 + 7] = e_math;
-      p.dbg[blockIdx.x * 128 + 8] = e_bar;
-      p.dbg[blockIdx.x * 128 + 9] = e_pub;
+      p.dbg[blockIdx.x * RP_DBG + 5] = e_load;
+      p.dbg[blockIdx.x * RP_DBG + 6] = e_wait;
+      p.dbg[blockIdx.x * RP_DBG + 7] = e_math;
+      p.dbg[blockIdx.x * RP_DBG + 8] = e_bar;
+      p.dbg[blockIdx.x * RP_DBG + 9] = e_pub;
     }
   }
 done:
@@ -611,8 +624,8 @@ int rnn_layer_pair(const RnnLayer& L, const float* gx, const int32_t* d_len, int
   const int grid = dirs_per_launch * slots * cpd;
   unsigned long long* dbg = nullptr;
   if (debug) {
-    DSB_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * 128 * grid));
-    DSB_CUDA(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 128 * grid, st));
+    DSB_CUDA(cudaMalloc(&dbg, sizeof(unsigned long long) * RP_DBG * grid));
+    DSB_CUDA(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * RP_DBG * grid, st));
   }
   p.dbg = dbg;
   for (int l = 0; l < launches; ++l) {
@@ -646,9 +659,9 @@ int rnn_layer_pair(const RnnLayer& L, const float* gx, const int32_t* d_len, int
     count_launch();
   }
   if (debug) {
-    std::vector<unsigned long long> h(128 * grid);
+    std::vector<unsigned long long> h((size_t)RP_DBG * grid);
     DSB_CUDA(cudaStreamSynchronize(st));
-    DSB_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * 128 * grid, cudaMemcpyDeviceToHost));
+    DSB_CUDA(cudaMemcpy(h.data(), dbg, sizeof(unsigned long long) * RP_DBG * grid, cudaMemcpyDeviceToHost));
     cudaFree(dbg);
     const char* names[13] = {"prod.spin", "prod.fence", "prod.issue", "mma.wait_first", "mma.rest", "epi.gx_loads",
                              "epi.wait_mma", "epi.tmem+math", "epi.stage", "epi.y_store", "mma.wait_rest",
@@ -658,11 +671,11 @@ int rnn_layer_pair(const RnnLayer& L, const float* gx, const int32_t* d_len, int
                     "cycles/item (avg over CTAs | max CTA)\n", L.H, B, Tmax, grid, n_bgroups, n_items, slots, nif, pl.groups, pl.gsz);
     for (int k = 0; k < 13; ++k) {
       double sum = 0, mx = 0;
-      for (int cc = 0; cc < grid; ++cc) { double v = (double)h[cc * 128 + k] / items; sum += v; mx = v > mx ? v : mx; }
+      for (int cc = 0; cc < grid; ++cc) { double v = (double)h[(size_t)cc * RP_DBG + k] / items; sum += v; mx = v > mx ? v : mx; }
       fprintf(stderr, "   %-16s %9.0f | %9.0f\n", names[k], sum / grid, mx);
     }
     for (int cc = 0; cc < grid; cc += grid / 2 + 1) {   // step-100 timeline of two CTAs (cycles since this CTA published step 99)
-      const unsigned long long* d = &h[cc * 128];
+      const unsigned long long* d = &h[(size_t)cc * RP_DBG];
       const long long t0 = (long long)d[66];
       fprintf(stderr, "   [cta %d] barrier passed %+lld | tma group issued:", cc, (long long)d[15] - t0);
       for (int i = 0; i < (nkc + pl.gsz - 1) / pl.gsz && i < 8; ++i) fprintf(stderr, " %lld", (long long)d[16 + i] - t0);
@@ -672,6 +685,22 @@ int rnn_layer_pair(const RnnLayer& L, const float* gx, const int32_t* d_len, int
               (long long)d[64] - t0, (long long)d[65] - t0, (long long)d[67] - t0);
       fprintf(stderr, "   [cta %d] publisher: barrier complete %+lld | store issued %+lld | store complete %+lld\n", cc,
               (long long)d[120] - t0, (long long)d[121] - t0, (long long)d[122] - t0);
+      {   // event trace of steps 100 and 101, all items in flight, in time order
+        static const char* ev[18] = {"producer: at the barrier", "producer: barrier passed", "box 1 issued", "box 2 issued", "box 3 issued",
+                                     "box 4 issued", "box 5 issued", "mma: box 1 landed", "mma: box 2 landed", "mma: box 3 landed",
+                                     "mma: box 4 landed", "mma: box 5 landed", "mma: all issued", "epilogue: accumulator complete",
+                                     "epilogue: staged, arrived", "publisher: barrier complete (issue time)", "publisher: published",
+                                     "epilogue: starts waiting"};
+        std::vector<std::pair<long long, std::string>> tr;
+        for (int i = 0; i < nif; ++i)
+          for (int ss = 0; ss < 2; ++ss)
+            for (int e = 0; e < 18; ++e) {
+              const unsigned long long v = d[128 + (i * 2 + ss) * 20 + e];
+              if (v) tr.emplace_back((long long)v - t0, "item " + std::to_string(i) + " step " + std::to_string(100 + ss) + "  " + ev[e]);
+            }
+        std::sort(tr.begin(), tr.end());
+        for (auto& x : tr) fprintf(stderr, "   [cta %d] %+8lld  %s\n", cc, x.first, x.second.c_str());
+      }
       for (int w = 0; w < 8; w += 3) {
         const unsigned long long* e = d + 72 + w * 6;
         fprintf(stderr, "   [cta %d] epilogue warp %d: wait from %+lld | dfull %+lld | math done %+lld | h stored, arrived %+lld\n",
