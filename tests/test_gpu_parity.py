@@ -764,3 +764,36 @@ def test_pair_recurrence_is_deterministic_at_the_headline_shape(B):
     for _ in range(3):
         again, _ = m(x, lens)
         assert torch.equal(again, first)
+
+
+def test_streaming_config4_1024_streams_match_the_oracle():
+    """BASELINE config 4 as benchmarked: CPUStreamingRNN shape (2 conv, 5 x 800 uni-GRU, lookahead 20), 1024 lock-step
+    streams, bf16 mode, against the ORACLE (model.py:156-284,517-537 restated) on eight different signals: stream s
+    carries signal s % 8, and streams from every part of the batch (first / last group of 64, group boundaries, CTA-set
+    boundaries) must reproduce their signal's oracle output within the bf16 bar."""
+    from danspeech_b200.audio.parsers import InferenceSpectrogramAudioParser
+    cfg = case_config("CPUStreamingRNN", {})
+    sd = syn.make_state_dict(seed=8, **cfg)
+    m = _model("CPUStreamingRNN", {}, seed=8, precision="bf16")
+    S, K, n_chunks = 1024, 8, 4
+    auds = [syn.synthetic_audio(8640 + 6240 * (n_chunks - 1), seed=270 + i) for i in range(K)]
+    specs = []
+    for a in auds:
+        sp = InferenceSpectrogramAudioParser()
+        specs.append([sp.parse_audio(c, is_last=(i == n_chunks - 1)).cpu() for i, c in enumerate(_stream_chunks(a))])
+    oracles = [om.StreamingOracle(sd, cfg["rnn_layers"], context=cfg["context"]) for _ in range(K)]
+    check = [0, 1, 2, 3, 4, 5, 6, 7, 63, 64, 127, 128, 341, 342, 511, 512, 683, 1000, 1023]
+    worst = 0.0
+    for i in range(n_chunks):
+        x = torch.stack([specs[s % K][i] for s in range(S)]).view(S, 1, 161, -1)
+        o = m(x.cuda(), i == 0, i == n_chunks - 1)
+        refs = [oracles[k].forward(specs[k][i].view(1, 1, 161, -1), i == 0, i == n_chunks - 1) for k in range(K)]
+        for s in check:
+            ref = refs[s % K]
+            if ref is None:
+                assert o is None
+            else:
+                assert tuple(o[s].shape) == tuple(ref[0].shape)
+                worst = max(worst, logit_rel_err(o[s].cpu().numpy(), ref[0].numpy()))
+    print("config 4, 1024 streams, bf16: worst logit rel err vs oracle %.2e" % worst)
+    assert worst < BF16_TOL
