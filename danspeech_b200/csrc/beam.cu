@@ -162,6 +162,7 @@ struct BeamSmem {
   int pidx[BM_MAXW];
   int surv[BM_MAXW];   // live prefix k is in the next beam
   int count, arena_count;
+  int n_dead;          // nodes that exist in the trie without being in the beam (kept for their descendants)
   int wsum[BM_THREADS / 32];
   float lpb_raw;
 };
@@ -229,6 +230,7 @@ beam_kernel(const BeamParams p) {
     a_parent[0] = -1; a_info[0] = 0xFF; a_wid[0] = -1;
     a_lpc[0] = BM_NEG; a_ref[0] = 1 << 28;   // the root is never removed
     sm.arena_count = 1;
+    sm.n_dead = 0;
   }
   __syncthreads();
 
@@ -439,13 +441,13 @@ beam_kernel(const BeamParams p) {
     __syncthreads();
     // ---- phase 3c: PathTrie::get_path_trie also refreshes (log_prob_c, timestep) of a child that EXISTS in the trie but
     //      is not in the beam (removed, kept for its descendants), whether or not the extension survives this step ----
+    //      (only when such nodes exist at all: the count lives in shared memory)
 #pragma unroll 1
-    for (int idx = tid; idx < n_active * C; idx += BM_THREADS) {
+    for (int idx = tid; sm.n_dead > 0 && idx < n_active * C; idx += BM_THREADS) {
       if (!(cand[idx] > BM_NEG)) continue;
       const int i = divC(idx), c = idx - i * C;
       const int par = S.node[i];
       // (a_ref and h_keys change through atomics, which act on L2: read them past the L1)
-      if (__ldcg(&a_ref[par]) <= 1) continue;              // no child of this prefix exists
       const uint32_t hk = ((uint32_t)par << 8) | (uint32_t)c;
       uint32_t slot = (hk * 0x9E3779B1u) >> p.h_shift;
       for (;;) {
@@ -590,18 +592,15 @@ beam_kernel(const BeamParams p) {
         {
           const uint32_t hk = ((uint32_t)S.node[i] << 8) | (uint32_t)c;
           uint32_t slot = (hk * 0x9E3779B1u) >> p.h_shift;
-          for (;;) {
-            const uint32_t k = *(volatile uint32_t*)&h_keys[slot];
-            if (k == hk) { id = __ldcg(&h_vals[slot]); break; }   // has been in the trie before
-            if (k == 0xFFFFFFFFu) {
-              const uint32_t old = atomicCAS(&h_keys[slot], 0xFFFFFFFFu, hk);   // (parent, symbol) pairs of a step are distinct
-              if (old == 0xFFFFFFFFu) {
-                id = atomicAdd(&sm.arena_count, 1);
-                h_vals[slot] = id;
-                fresh = true;
-                break;
-              }
+          for (;;) {   // one atomic round trip per probe: claim the slot if it is empty, else see who has it
+            const uint32_t old = atomicCAS(&h_keys[slot], 0xFFFFFFFFu, hk);   // (parent, symbol) pairs of a step are distinct
+            if (old == 0xFFFFFFFFu) {
+              id = atomicAdd(&sm.arena_count, 1);
+              h_vals[slot] = id;
+              fresh = true;
+              break;
             }
+            if (old == hk) { id = __ldcg(&h_vals[slot]); break; }   // has been in the trie before
             slot = (slot + 1) & p.h_mask;
           }
         }
@@ -613,6 +612,7 @@ beam_kernel(const BeamParams p) {
         if (id < p.max_nodes) {
           if (revived) {
             atomicAdd(&a_ref[id], 1);
+            atomicSub(&sm.n_dead, 1);
           } else {
             a_ref[id] = 1;
             a_lpc[id] = sm.lp[c];
@@ -646,8 +646,15 @@ beam_kernel(const BeamParams p) {
     for (int k = tid; k < n_active; k += BM_THREADS) {
       if (sm.surv[k]) continue;
       int n = S.node[k];
+      if (n <= 0 || n >= p.max_nodes) continue;
+      if (atomicSub(&a_ref[n], 1) != 1) {      // still has children: stays in the trie, outside the beam
+        atomicAdd(&sm.n_dead, 1);
+        continue;
+      }
+      n = S.parent[k];                          // deleted: release the parent (and its removed ancestors in turn)
       while (n > 0 && n < p.max_nodes) {
         if (atomicSub(&a_ref[n], 1) != 1) break;
+        atomicSub(&sm.n_dead, 1);               // a live node keeps its own reference, so this one was a removed node
         n = a_parent[n];
       }
     }
