@@ -152,6 +152,7 @@ struct BeamState {   // one live-beam buffer (shared memory)
   float lmsp[BM_MAXW];
   int lmwid[BM_MAXW], lmns[BM_MAXW], lmok[BM_MAXW];
   int rowok[BM_MAXW];   // dictionary row of this prefix's state is in the row cache
+  int gprobe[BM_MAXW];  // this prefix may have children that exist in the trie outside the beam (see phase 3c)
 };
 
 struct BeamSmem {
@@ -160,7 +161,8 @@ struct BeamSmem {
   int allowed[BM_MAXC];
   float selfb[BM_MAXW], selfnb[BM_MAXW], selfscore[BM_MAXW];
   int pidx[BM_MAXW];
-  int surv[BM_MAXW];   // live prefix k is in the next beam
+  int surv[BM_MAXW];   // live prefix k is in the next beam: its slot there + 1, else 0
+  int pslot[BM_MAXW];  // slot of live prefix k's parent in the current beam (-1: the parent is not live)
   int count, arena_count;
   int n_dead;          // nodes that exist in the trie without being in the beam (kept for their descendants)
   int wsum[BM_THREADS / 32];
@@ -226,7 +228,7 @@ beam_kernel(const BeamParams p) {
     s.node[0] = 0; s.parent[0] = -1; s.ch[0] = -1; s.dstate[0] = 0; s.ts[0] = 0;
     for (int h = 0; h < BM_HIST; ++h) s.hist[0][h] = T.id_bos;
     s.bprev[0] = 0.f; s.nbprev[0] = BM_NEG; s.score[0] = 0.f; s.lpc[0] = BM_NEG;
-    s.lmok[0] = 0; s.rowok[0] = 0;
+    s.lmok[0] = 0; s.rowok[0] = 0; s.gprobe[0] = 0;
     a_parent[0] = -1; a_info[0] = 0xFF; a_wid[0] = -1;
     a_lpc[0] = BM_NEG; a_ref[0] = 1 << 28;   // the root is never removed
     sm.arena_count = 1;
@@ -279,6 +281,7 @@ beam_kernel(const BeamParams p) {
 #pragma unroll 1
     for (int k = tid; k < n_active; k += BM_THREADS) {
       sm.pidx[k] = -1;
+      sm.pslot[k] = -1;
       sm.selfnb[k] = BM_NEG;
       sm.selfb[k] = BM_NEG;
     }
@@ -292,7 +295,7 @@ beam_kernel(const BeamParams p) {
     for (int k = tid >> 3; k < n_active; k += BM_THREADS >> 3) {   // 8 threads per prefix k scan the beam for its parent
       const int pk = S.parent[k];
       for (int i = tid & 7; i < n_active; i += 8)
-        if (S.node[i] == pk && i != k) sm.pidx[k] = i;
+        if (S.node[i] == pk && i != k) { sm.pidx[k] = i; sm.pslot[k] = i; }
     }
     lap(1);
     // ---- phase 2b (word LM): the LM score of closing the current word, one thread per prefix that has not got it
@@ -441,11 +444,14 @@ beam_kernel(const BeamParams p) {
     __syncthreads();
     // ---- phase 3c: PathTrie::get_path_trie also refreshes (log_prob_c, timestep) of a child that EXISTS in the trie but
     //      is not in the beam (removed, kept for its descendants), whether or not the extension survives this step ----
-    //      (only when such nodes exist at all: the count lives in shared memory)
+    //      Such a child of a live prefix comes about in two ways only -- it left the beam with descendants while its
+    //      parent was live, or its parent came back into the beam (was revived) -- and both mark the parent (gprobe),
+    //      so only the candidates of marked prefixes pay for a hash probe in global memory.
 #pragma unroll 1
     for (int idx = tid; sm.n_dead > 0 && idx < n_active * C; idx += BM_THREADS) {
       if (!(cand[idx] > BM_NEG)) continue;
       const int i = divC(idx), c = idx - i * C;
+      if (!S.gprobe[i]) continue;
       const int par = S.node[i];
       // (a_ref and h_keys change through atomics, which act on L2: read them past the L1)
       const uint32_t hk = ((uint32_t)par << 8) | (uint32_t)c;
@@ -580,9 +586,9 @@ beam_kernel(const BeamParams p) {
         for (int h = 0; h < BM_HIST; ++h) Nx.hist[r][h] = S.hist[k][h];
         Nx.bprev[r] = sm.selfb[k]; Nx.nbprev[r] = sm.selfnb[k]; Nx.score[r] = sm.selfscore[k];
         Nx.lmsp[r] = S.lmsp[k]; Nx.lmwid[r] = S.lmwid[k]; Nx.lmns[r] = S.lmns[k]; Nx.lmok[r] = S.lmok[k];
-        Nx.rowok[r] = 1;
+        Nx.rowok[r] = 1; Nx.gprobe[r] = S.gprobe[k];
         sm.pidx[r] = k;   // (pidx is free again here) source slot of the dictionary row, copied below by all threads
-        sm.surv[k] = 1;
+        sm.surv[k] = r + 1;
       } else {                // new prefix: parent i extended by symbol c
         const int idx = code - BM_MAXW;
         const int i = divC(idx), c = idx - i * C;
@@ -631,7 +637,7 @@ beam_kernel(const BeamParams p) {
           Nx.hist[r][h] = hv;
         }
         Nx.bprev[r] = BM_NEG; Nx.nbprev[r] = v; Nx.score[r] = v;
-        Nx.lmok[r] = 0; Nx.rowok[r] = 0;
+        Nx.lmok[r] = 0; Nx.rowok[r] = 0; Nx.gprobe[r] = revived ? 1 : 0;
         sm.pidx[r] = -1;
         if (fresh && id < p.max_nodes) {
           a_parent[id] = S.node[i];
@@ -649,6 +655,8 @@ beam_kernel(const BeamParams p) {
       if (n <= 0 || n >= p.max_nodes) continue;
       if (atomicSub(&a_ref[n], 1) != 1) {      // still has children: stays in the trie, outside the beam
         atomicAdd(&sm.n_dead, 1);
+        const int ps = sm.pslot[k];             // its parent, if it stays in the beam, has such a child from now on
+        if (ps >= 0 && sm.surv[ps]) Nx.gprobe[sm.surv[ps] - 1] = 1;
         continue;
       }
       n = S.parent[k];                          // deleted: release the parent (and its removed ancestors in turn)
