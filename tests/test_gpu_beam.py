@@ -1,7 +1,8 @@
 """GPU: BeamCTCDecoder (device prefix beam search + device n-gram LM) against the CPU oracle.
 
 Bars (BASELINE.json north star): beam top-1 transcripts identical on >= 99.5 % of utterances, beam
-scores within 1e-3 (relative to the score magnitude)."""
+scores within 1e-3 (relative to the score magnitude).  Asserted here: every hypothesis of every beam, with its
+character time steps, equal to the oracle's, scores to 1e-5."""
 import numpy as np
 import pytest
 import torch
@@ -36,25 +37,28 @@ def _spelled_probs(rng, vocab, B, T, noise=0.25):
     return probs.astype(np.float32), sorted(lens, reverse=True)
 
 
-def _compare(gpu, ref, probs, lens, min_match=0.995):
-    from danspeech_b200.deepspeech.decoder import BeamCTCDecoder  # noqa: F401
+def _compare(gpu, ref, probs, lens):
+    """Top beam: labels, score and character time steps equal to the oracle's on EVERY utterance (the GPU arena keeps
+    ctcdecode's PathTrie node identity and lifetime), and the whole beam: the same set of (labels, time steps) for all W
+    hypotheses and the same scores.  (Measured on the B200: identical on every utterance of every case below.)"""
     out, scores, ts, out_len = [x.cpu().numpy() for x in gpu.decode_device(torch.from_numpy(probs).cuda(),
                                                                             torch.IntTensor(lens))]
     r_out, r_scores, r_ts, r_len = ref.decode(probs, lens)
-    B = probs.shape[0]
-    same = 0
+    B, W = probs.shape[0], out.shape[1]
+    whole = 0
     for b in range(B):
         n, rn = out_len[b, 0], r_len[b, 0]
-        if n == rn and np.array_equal(out[b, 0, :n], r_out[b, 0, :rn]):
-            same += 1
-            assert abs(scores[b, 0] - r_scores[b, 0]) <= 1e-3 * max(1.0, abs(r_scores[b, 0]))
-    assert same / B >= min_match, "top-1 identical on %d / %d utterances" % (same, B)
-    # deeper in the beam the two implementations may keep different hypotheses at the pruning boundary
-    # (std::nth_element vs a full sort break ties differently): most of the top-8 scores must still agree
-    k = min(8, gpu._beam_width)
-    close = np.isclose(np.sort(scores[:, :k], axis=1), np.sort(r_scores[:, :k], axis=1), rtol=2e-3, atol=2e-3)
-    assert close.mean() >= 0.9, "only %.0f %% of the top-%d scores agree" % (100 * close.mean(), k)
-    return same
+        assert n == rn and np.array_equal(out[b, 0, :n], r_out[b, 0, :rn]), "top beam of utterance %d differs" % b
+        assert abs(scores[b, 0] - r_scores[b, 0]) <= 1e-5 * max(1.0, abs(r_scores[b, 0])), b
+        assert np.array_equal(ts[b, 0, :n], r_ts[b, 0, :rn]), "character time steps of utterance %d differ" % b
+        mine = {(tuple(out[b, j, :out_len[b, j]].tolist()), tuple(ts[b, j, :out_len[b, j]].tolist())) for j in range(W)}
+        theirs = {(tuple(r_out[b, j, :r_len[b, j]].tolist()), tuple(r_ts[b, j, :r_len[b, j]].tolist())) for j in range(W)}
+        whole += mine == theirs
+    print("whole beams (labels + time steps of all %d hypotheses) identical on %d / %d utterances" % (W, whole, B))
+    assert whole == B
+    k = min(8, W)
+    assert np.allclose(np.sort(scores[:, :k], axis=1), np.sort(r_scores[:, :k], axis=1), rtol=1e-5, atol=1e-5)
+    return whole
 
 
 @pytest.mark.parametrize("beam", [1, 16, 64, 100])
